@@ -1,0 +1,31 @@
+// Host-side glue shared by every translation unit of libdeeplip_b200.so:
+// thread-local error string, launch counter, driver-API tensor-map encoders.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/deeplip_b200.h"
+
+namespace dl {
+
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);          // cudaGetLastError -> DL_OK / DL_ERR_CUDA
+int device_sm_count();
+int require_sm100();                          // DL_OK or DL_ERR_UNSUPPORTED
+
+// 2-D tiled map over a row-major (rows, cols) 16-bit matrix with row pitch `ld` elements;
+// box = (box_cols, box_rows), 128-byte swizzle.
+int make_tiled_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows, uint32_t box_cols);
+
+// im2col map over an NHWC 16-bit activation tensor (pitch ldx elements per pixel): loads
+// `pixels` output positions x `channels` channels per request, 128-byte swizzle, zero OOB fill.
+int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int R, int S,
+                          int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                          uint32_t channels, uint32_t pixels);
+
+}  // namespace dl
+
+#define DL_CHECK_ARG(cond, ...) \
+  do { if (!(cond)) return dl::fail(DL_ERR_INVALID, __VA_ARGS__); } while (0)

@@ -1,0 +1,207 @@
+// K1: fused audio front end -- pre-emphasis + 400/160 framing + 512-point FFT power spectrum + triangular
+// mel filterbank + log (+ DCT-II, lifter, log-energy for MFCC), then per-utterance CMVN.
+// Restates python_speech_features v0.6 as the reference calls it (models/fusion_models/datasets.py:227-246)
+// and `_normalize` (:214-215).  HBM-bound by construction: 4 B/sample in, F*T*(4+2) B out; one warp per frame.
+#include <math.h>
+#include "dl_host.cuh"
+#include "dl_ptx.cuh"
+
+namespace dl {
+
+constexpr int kNfft = 512;
+constexpr int kFrameLen = 400;
+constexpr int kFrameStep = 160;
+constexpr int kMaxFilt = 64;
+constexpr float kPreemph = 0.97f;
+
+struct FrontendTables {
+  int nfilt;
+  int ncep;                  // number of coefficients written (F)
+  int kind;                  // 0 mfcc, 1 fbank, 2 logfbank
+  int bins[kMaxFilt + 2];    // FFT-bin edges of the triangular filters
+};
+
+__constant__ float2 c_twiddle[kNfft / 2];   // exp(-2 pi i k / 512)
+
+__device__ __forceinline__ int bitrev9(int v) { return __brev((unsigned)v) >> 23; }
+
+// grid (ceil(T/8), B); block 256 = 8 warps, one frame per warp.  Writes raw (pre-CMVN) features to
+// feat (B, F, T) f32.
+__global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __restrict__ wav,
+                                                              const int32_t* __restrict__ lengths, int nsamp, int T,
+                                                              FrontendTables tb, float* __restrict__ feat) {
+  __shared__ float2 buf[8][kNfft];
+  __shared__ float logmel[8][kMaxFilt];
+  __shared__ float dctm[kMaxFilt * 26];   // DCT rows (ncep x 26 filters), mfcc only
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 8 + warp;
+  const int F = tb.ncep;
+
+  if (tb.kind == 0) {
+    // scipy dct(type=2, norm='ortho') rows with the cepstral lifter (L=22) folded in
+    const int nf = tb.nfilt;
+    for (int i = threadIdx.x; i < F * nf; i += 256) {
+      const int n = i / nf, j = i % nf;
+      const float ortho = (n == 0) ? sqrtf(1.f / (float)nf) : sqrtf(2.f / (float)nf);
+      const float lift = 1.f + 11.f * sinpif((float)n / 22.f);
+      dctm[i] = ortho * lift * cospif((float)(n * (2 * j + 1)) / (float)(2 * nf));
+    }
+  }
+  __syncthreads();
+
+  const int len = lengths ? min(lengths[b], nsamp) : nsamp;
+  const int nfr = len <= kFrameLen ? 1 : 1 + (len - kFrameLen + kFrameStep - 1) / kFrameStep;
+  if (t >= T) return;
+  float* out = feat + (size_t)b * F * T + t;
+  if (t >= nfr) {   // padding frame of a ragged batch
+    for (int f = lane; f < F; f += 32) out[(size_t)f * T] = 0.f;
+    return;
+  }
+
+  // ---- load + pre-emphasis + zero pad to 512, bit-reversed for the in-place DIT FFT
+  const float* x = wav + (size_t)b * nsamp;
+  const int s0 = t * kFrameStep;
+  float2* z = buf[warp];
+  for (int i = lane; i < kNfft; i += 32) {
+    float v = 0.f;
+    const int s = s0 + i;
+    if (i < kFrameLen && s < len) {
+      const float cur = __ldg(x + s);
+      v = (s == 0) ? cur : cur - kPreemph * __ldg(x + s - 1);
+    }
+    z[bitrev9(i)] = make_float2(v, 0.f);
+  }
+  __syncwarp();
+  // ---- 9 radix-2 stages
+#pragma unroll 1
+  for (int st = 0; st < 9; ++st) {
+    const int half = 1 << st;
+    for (int i = lane; i < kNfft / 2; i += 32) {
+      const int grp = i >> st, pos = i & (half - 1);
+      const int i0 = (grp << (st + 1)) + pos, i1 = i0 + half;
+      const float2 w = c_twiddle[pos << (8 - st)];
+      const float2 a = z[i0], c = z[i1];
+      const float2 m = make_float2(c.x * w.x - c.y * w.y, c.x * w.y + c.y * w.x);
+      z[i0] = make_float2(a.x + m.x, a.y + m.y);
+      z[i1] = make_float2(a.x - m.x, a.y - m.y);
+    }
+    __syncwarp();
+  }
+  // ---- power spectrum (257 bins) in place (x component), total energy
+  float e = 0.f;
+  for (int k = lane; k <= kNfft / 2; k += 32) {
+    const float2 c = z[k];
+    const float pw = (c.x * c.x + c.y * c.y) * (1.f / (float)kNfft);
+    e += pw;
+    z[k].x = pw;
+  }
+  e = warp_sum(e);
+  if (e == 0.f) e = 2.220446049250313e-16f;
+  __syncwarp();
+  // ---- mel filterbank: lane j <-> filter j (two passes when nfilt > 32)
+  for (int j = lane; j < tb.nfilt; j += 32) {
+    const int b0 = tb.bins[j], b1 = tb.bins[j + 1], b2 = tb.bins[j + 2];
+    float s = 0.f;
+    for (int i = b0; i < b1; ++i) s = fmaf(z[i].x, (float)(i - b0) / (float)(b1 - b0), s);
+    for (int i = b1; i < b2; ++i) s = fmaf(z[i].x, (float)(b2 - i) / (float)(b2 - b1), s);
+    if (s == 0.f) s = 2.220446049250313e-16f;
+    logmel[warp][j] = (tb.kind == 1) ? s : logf(s);
+  }
+  __syncwarp();
+  if (tb.kind == 0) {
+    for (int n = lane; n < F; n += 32) {
+      float c = 0.f;
+      for (int j = 0; j < tb.nfilt; ++j) c = fmaf(dctm[n * tb.nfilt + j], logmel[warp][j], c);
+      if (n == 0) c = logf(e);          // appendEnergy=True
+      out[(size_t)n * T] = c;
+    }
+  } else {
+    for (int f = lane; f < F; f += 32) out[(size_t)f * T] = logmel[warp][f];
+  }
+}
+
+// grid B; block 256: warp w normalises coefficients w, w+8, ...  (biased std, + 2e-12), writes f32 in place
+// and the channels-last bf16 copy the TDNN consumes.
+__global__ void __launch_bounds__(256) frontend_cmvn_kernel(float* __restrict__ feat, const int32_t* __restrict__ lengths,
+                                                            int nsamp, int T, int F, int cmvn,
+                                                            uint16_t* __restrict__ out_bf16, int ld) {
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = lengths ? min(lengths[b], nsamp) : nsamp;
+  int nfr = len <= kFrameLen ? 1 : 1 + (len - kFrameLen + kFrameStep - 1) / kFrameStep;
+  nfr = min(nfr, T);
+  for (int f = warp; f < F; f += 8) {
+    float* row = feat + ((size_t)b * F + f) * T;
+    float mean = 0.f, inv = 1.f;
+    if (cmvn) {
+      float s = 0.f;
+      for (int t = lane; t < nfr; t += 32) s += row[t];
+      mean = warp_sum(s) / (float)nfr;
+      float q = 0.f;
+      for (int t = lane; t < nfr; t += 32) { const float d = row[t] - mean; q = fmaf(d, d, q); }
+      q = warp_sum(q) / (float)nfr;
+      inv = 1.f / (sqrtf(q) + 2e-12f);
+    }
+    for (int t = lane; t < T; t += 32) {
+      const float v = t < nfr ? (row[t] - mean) * inv : 0.f;
+      row[t] = v;
+      if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out_bf16)[((size_t)b * T + t) * ld + f] = __float2bfloat16_rn(v);
+    }
+  }
+  if (out_bf16) {   // zero the padded channels
+    for (int i = threadIdx.x; i < T * (ld - F); i += 256) {
+      const int t = i / (ld - F), c = F + i % (ld - F);
+      reinterpret_cast<__nv_bfloat16*>(out_bf16)[((size_t)b * T + t) * ld + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+static double hz2mel(double hz) { return 2595.0 * log10(1.0 + hz / 700.0); }
+static double mel2hz(double mel) { return 700.0 * (pow(10.0, mel / 2595.0) - 1.0); }
+
+static int upload_twiddles() {
+  static bool done = false;
+  if (done) return DL_OK;
+  float2 tw[kNfft / 2];
+  for (int k = 0; k < kNfft / 2; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)kNfft;
+    tw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  cudaError_t e = cudaMemcpyToSymbol(c_twiddle, tw, sizeof(tw));
+  if (e != cudaSuccess) return fail(DL_ERR_CUDA, "frontend twiddles: %s", cudaGetErrorString(e));
+  done = true;
+  return DL_OK;
+}
+
+}  // namespace dl
+
+extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
+                                    int cmvn, void* feat_bf16, int ld_bf16, float* feat_f32, int T, void* stream) {
+  using namespace dl;
+  DL_CHECK_ARG(wav && feat_f32, "frontend: wav and feat_f32 are required");
+  DL_CHECK_ARG(B > 0 && nsamp > 0, "frontend: empty batch");
+  DL_CHECK_ARG(kind >= 0 && kind <= 2, "frontend: kind must be 0 (mfcc), 1 (fbank) or 2 (logfbank)");
+  const int nfilt = kind == 0 ? 26 : F;
+  DL_CHECK_ARG(F >= 1 && F <= kMaxFilt && nfilt <= kMaxFilt && F <= nfilt, "frontend: F=%d out of range", F);
+  const int Texp = nsamp <= kFrameLen ? 1 : 1 + (nsamp - kFrameLen + kFrameStep - 1) / kFrameStep;
+  DL_CHECK_ARG(T == Texp, "frontend: T=%d but %d samples give %d frames", T, nsamp, Texp);
+  DL_CHECK_ARG(!feat_bf16 || ld_bf16 >= F, "frontend: ld_bf16 < F");
+  int st = upload_twiddles();
+  if (st != DL_OK) return st;
+
+  FrontendTables tb;
+  tb.nfilt = nfilt; tb.ncep = F; tb.kind = kind;
+  const double lo = hz2mel(0.0), hi = hz2mel(8000.0);
+  for (int i = 0; i < nfilt + 2; ++i) {
+    const double mel = lo + (hi - lo) * (double)i / (double)(nfilt + 1);
+    tb.bins[i] = (int)floor((kNfft + 1) * mel2hz(mel) / 16000.0);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((T + 7) / 8, B);
+  frontend_frames_kernel<<<grid, 256, 0, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
+  st = check_launch("frontend_frames_kernel");
+  if (st != DL_OK) return st;
+  frontend_cmvn_kernel<<<B, 256, 0, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, (uint16_t*)feat_bf16, ld_bf16);
+  return check_launch("frontend_cmvn_kernel");
+}

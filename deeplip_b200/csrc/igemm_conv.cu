@@ -1,0 +1,337 @@
+// Implicit-GEMM convolution for sm_100a.
+//
+//   D[m, n] = sum_{r,s,c} X[pixel(m) + (r,s), c] * Wt[n, (r,s,c)]        m = (img, p, q), n = cout
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer : operand A by TMA *im2col* loads straight from the NHWC activation tensor
+//                              (one [128 pixels x 64 channels] box per filter tap and channel chunk, zero
+//                              padding and stride handled by the TMA unit), operand B (packed weights) by a
+//                              tiled TMA load; both land in 128B-swizzled K-major shared memory.
+//   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into a double-buffered
+//                              fp32 accumulator in TMEM; tcgen05.commit releases smem stages / publishes tiles.
+//   warps 2..5  epilogue     : tcgen05.ld the accumulator, apply folded BatchNorm (scale, shift), residual add,
+//                              per-channel PReLU/LeakyReLU slope, write bf16 channels-last (+ optional fp32
+//                              side output) -- overlapped with the next tile's MMAs.
+//
+// Roofline: tensor pipe.  Algorithmic work = 2 * M * Cout * R*S*C flop per launch (DESIGN.md "Kernels").
+#include "dl_host.cuh"
+#include "dl_ptx.cuh"
+
+namespace dl {
+
+struct IgemmParams {
+  int M, P, Q, PQ;
+  int Cout;
+  int cchunks, R, S;
+  int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int num_m_blocks, num_n_blocks;
+  int ldy, ldf;
+  float f32_slope;
+  const float* scale;
+  const float* shift;
+  const float* slope;
+  const float* scale2;
+  const float* shift2;
+  const uint16_t* residual;
+  uint16_t* y;
+  float* yf;
+};
+
+template <int BLOCK_N>
+struct IgemmCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_K = 64;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 64) ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;   // two accumulator stages; 128 / 256 / 512 (power of two)
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int THREADS = 192;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const IgemmParams p) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(&tfull[0], 1);
+      mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], 128);
+      mbar_init(&tempty[1], 128);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_kb = p.R * p.S * p.cchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks;
+        const int n_blk = tile - m_blk * p.num_n_blocks;
+        const int m0 = m_blk * Cfg::BLOCK_M;
+        const int img = m0 / p.PQ;
+        const int rem = m0 - img * p.PQ;
+        const int pp = rem / p.Q;
+        const int qq = rem - pp * p.Q;
+        const int w0 = qq * p.stride_w - p.pad_w;
+        const int h0 = pp * p.stride_h - p.pad_h;
+        int kb = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+              tma_load_im2col_4d(sa, &mapA, &full[stage], cc * 64, w0, h0, img, (uint16_t)(s * p.dil_w),
+                                 (uint16_t)(r * p.dil_h));
+              tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full[stage], kb * 64, n_blk * BLOCK_N);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128_kmajor(sa);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle atom
+            umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;   // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks;
+      const int n_blk = tile - m_blk * p.num_n_blocks;
+      const long long row = (long long)m_blk * Cfg::BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        const int c0 = n_blk * BLOCK_N + j * 32;
+        if (c0 >= p.Cout) break;
+        uint32_t acc_r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + j * 32, acc_r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = c0 + g * 8;
+            if (c < p.Cout) {
+              float a[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(acc_r[g * 8 + i]);
+              if (p.yf != nullptr) {
+                float o[8];
+                if (p.scale2 != nullptr) {
+                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale2 + c));
+                  const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale2 + c + 4));
+                  const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift2 + c));
+                  const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.shift2 + c + 4));
+                  o[0] = fmaf(a[0], s0.x, h0.x); o[1] = fmaf(a[1], s0.y, h0.y);
+                  o[2] = fmaf(a[2], s0.z, h0.z); o[3] = fmaf(a[3], s0.w, h0.w);
+                  o[4] = fmaf(a[4], s1.x, h1.x); o[5] = fmaf(a[5], s1.y, h1.y);
+                  o[6] = fmaf(a[6], s1.z, h1.z); o[7] = fmaf(a[7], s1.w, h1.w);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) o[i] = a[i];
+                }
+                if (p.f32_slope != 1.0f) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * p.f32_slope;
+                }
+                float4* dst = reinterpret_cast<float4*>(p.yf + row * p.ldf + c);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+              }
+              if (p.y != nullptr) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
+                const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+                const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
+                float v[8];
+                v[0] = fmaf(a[0], s0.x, h0.x); v[1] = fmaf(a[1], s0.y, h0.y);
+                v[2] = fmaf(a[2], s0.z, h0.z); v[3] = fmaf(a[3], s0.w, h0.w);
+                v[4] = fmaf(a[4], s1.x, h1.x); v[5] = fmaf(a[5], s1.y, h1.y);
+                v[6] = fmaf(a[6], s1.z, h1.z); v[7] = fmaf(a[7], s1.w, h1.w);
+                if (p.residual != nullptr) {
+                  const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c));
+                  v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x);
+                  v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                  v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z);
+                  v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                }
+                const float4 l0 = __ldg(reinterpret_cast<const float4*>(p.slope + c));
+                const float4 l1 = __ldg(reinterpret_cast<const float4*>(p.slope + c + 4));
+                v[0] = v[0] > 0.f ? v[0] : v[0] * l0.x; v[1] = v[1] > 0.f ? v[1] : v[1] * l0.y;
+                v[2] = v[2] > 0.f ? v[2] : v[2] * l0.z; v[3] = v[3] > 0.f ? v[3] : v[3] * l0.w;
+                v[4] = v[4] > 0.f ? v[4] : v[4] * l1.x; v[5] = v[5] > 0.f ? v[5] : v[5] * l1.y;
+                v[6] = v[6] > 0.f ? v[6] : v[6] * l1.z; v[7] = v[7] > 0.f ? v[7] : v[7] * l1.w;
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]);
+                o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]);
+                o.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(p.y + row * p.ldy + c) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p,
+                        cudaStream_t stream) {
+  using Cfg = IgemmCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(DL_ERR_CUDA, "igemm smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  int grid = device_sm_count();
+  if (grid <= 0) grid = 148;
+  if (tiles < grid) grid = tiles;
+  igemm_conv_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+  return check_launch("igemm_conv_kernel");
+}
+
+}  // namespace dl
+
+extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
+                                  const float* slope, const void* residual, void* y, float* y_f32,
+                                  const float* scale2, const float* shift2, const dl_conv_desc* d, void* stream) {
+  using namespace dl;
+  DL_CHECK_ARG(x && w_packed && d, "conv_igemm: null x / w / desc");
+  DL_CHECK_ARG(y || y_f32, "conv_igemm: no output requested");
+  DL_CHECK_ARG(!y || (scale && shift && slope), "conv_igemm: bf16 output needs scale/shift/slope");
+  DL_CHECK_ARG(!residual || y, "conv_igemm: residual needs the bf16 output");
+  DL_CHECK_ARG((scale2 == nullptr) == (shift2 == nullptr), "conv_igemm: scale2/shift2 must come together");
+  DL_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->Cout > 0, "conv_igemm: empty shape");
+  DL_CHECK_ARG(d->ldx % 8 == 0 && d->ldx >= d->C, "conv_igemm: ldx must be >= C and a multiple of 8");
+  DL_CHECK_ARG(d->Cout % 8 == 0, "conv_igemm: Cout must be a multiple of 8 (pad the packed weights)");
+  DL_CHECK_ARG(!y || (d->ldy % 8 == 0 && d->ldy >= d->Cout), "conv_igemm: ldy must be >= Cout, multiple of 8");
+  DL_CHECK_ARG(!y_f32 || (d->ldf % 4 == 0 && d->ldf >= d->Cout), "conv_igemm: ldf must be >= Cout, multiple of 4");
+  DL_CHECK_ARG(d->R >= 1 && d->S >= 1 && d->stride_h >= 1 && d->stride_w >= 1 && d->dil_h >= 1 && d->dil_w >= 1 &&
+                   d->pad_h >= 0 && d->pad_w >= 0,
+               "conv_igemm: bad filter geometry");
+  DL_CHECK_ARG((d->S - 1) * d->dil_w <= 255 && (d->R - 1) * d->dil_h <= 255 && d->pad_w <= 127 && d->pad_h <= 127,
+               "conv_igemm: filter extent exceeds the TMA im2col offset range");
+  const int P = (d->H + 2 * d->pad_h - d->dil_h * (d->R - 1) - 1) / d->stride_h + 1;
+  const int Q = (d->W + 2 * d->pad_w - d->dil_w * (d->S - 1) - 1) / d->stride_w + 1;
+  DL_CHECK_ARG(P > 0 && Q > 0, "conv_igemm: input smaller than the filter");
+  int st = require_sm100();
+  if (st != DL_OK) return st;
+
+  const long long M = (long long)d->N * P * Q;
+  DL_CHECK_ARG(M < (1ll << 31) - 256, "conv_igemm: too many output pixels");
+  IgemmParams p;
+  p.M = (int)M; p.P = P; p.Q = Q; p.PQ = P * Q;
+  p.Cout = d->Cout;
+  p.cchunks = (d->C + 63) / 64;
+  p.R = d->R; p.S = d->S;
+  p.stride_h = d->stride_h; p.stride_w = d->stride_w;
+  p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  p.dil_h = d->dil_h; p.dil_w = d->dil_w;
+  p.ldy = d->ldy; p.ldf = d->ldf;
+  p.f32_slope = d->f32_slope;
+  p.scale = scale; p.shift = shift; p.slope = slope; p.scale2 = scale2; p.shift2 = shift2;
+  p.residual = static_cast<const uint16_t*>(residual);
+  p.y = static_cast<uint16_t*>(y);
+  p.yf = y_f32;
+  p.num_m_blocks = (int)((M + 127) / 128);
+
+  const int block_n = d->Cout <= 64 ? 64 : (d->Cout <= 128 ? 128 : 256);
+  p.num_n_blocks = (d->Cout + block_n - 1) / block_n;
+  const long long Ktot = (long long)d->R * d->S * p.cchunks * 64;
+
+  CUtensorMap mapA, mapB;
+  st = make_im2col_nhwc_bf16(&mapA, x, d->N, d->H, d->W, d->C, d->ldx, d->R, d->S, d->stride_h, d->stride_w, d->pad_h,
+                             d->pad_w, d->dil_h, d->dil_w, 64, 128);
+  if (st != DL_OK) return st;
+  st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot, (uint32_t)block_n, 64);
+  if (st != DL_OK) return st;
+
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (block_n) {
+    case 64: return launch_igemm<64>(mapA, mapB, p, s);
+    case 128: return launch_igemm<128>(mapA, mapB, p, s);
+    default: return launch_igemm<256>(mapA, mapB, p, s);
+  }
+}

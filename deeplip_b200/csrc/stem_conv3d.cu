@@ -1,0 +1,352 @@
+// K2: video stem -- Conv3d(1->64, k(5,7,7), s(1,2,2), p(2,3,3)) + BatchNorm3d + PReLU + MaxPool3d((1,3,3),(1,2,2),
+// (0,1,1)) fused into one persistent tcgen05 kernel that emits channels-last per-frame maps (so the reference's
+// NCTHW -> (N*T)CHW copy, models/video_models/model.py:9-13, disappears).  Optionally reads raw uint8 crops and
+// applies the reference preprocessing (x/255, centre crop, (x-mean)/std; dataloaders.py:19-24) in the load.
+//
+// GEMM view per frame: M = Ho*Wo conv pixels (row-major, 128 per tile), N = 64, K = 5 temporal taps x 64
+// (7 rows x 8 columns of the 7x7 window, zero-weight padding) -> one 64-wide K block per temporal tap.
+// With a single input channel TMA im2col cannot form operand A (16-byte minimum inner extent), so 8 producer
+// warps build the 128B-swizzled K-major A tile in shared memory from a small staged input strip; a single
+// thread issues tcgen05.mma into a double-buffered TMEM accumulator; 4 epilogue warps apply BN+PReLU, park the
+// bf16 conv rows in a shared-memory ring and max-pool completed rows straight to global memory.
+//
+// Roofline: tensor pipe; algorithmic work 2*Ho*Wo*64*245 flop per frame (DESIGN.md "Kernels").
+#include "dl_host.cuh"
+#include "dl_ptx.cuh"
+
+namespace dl {
+
+constexpr int kStemAStages = 4;
+constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 64 K (bf16)
+constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
+constexpr int kStemThreads = 13 * 32;               // 4 epilogue + 1 MMA + 8 producer warps
+constexpr int kProducerThreads = 256;
+constexpr int kStripMaxElems = 8;                   // prefetched strip elements per producer thread
+
+struct StemParams {
+  const void* x;
+  int is_u8;
+  int B, T, H, W, Hraw, Wraw, dh, dw;
+  float mean, inv_std;
+  int Ho, Wo, Hp, Wp, Mf, tiles_per_frame;
+  int ring_rows;        // power of two
+  int strip_rows, strip_w;
+  const float* scale;
+  const float* shift;
+  const float* slope;
+  uint16_t* y;
+  int frames;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ float stem_load_px(const StemParams& p, int b, int t, int iy, int ix) {
+  if (t < 0 || t >= p.T || iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return 0.f;
+  if (p.is_u8) {
+    const uint8_t* src = static_cast<const uint8_t*>(p.x);
+    const float u = (float)__ldg(src + (((size_t)b * p.T + t) * p.Hraw + (iy + p.dh)) * p.Wraw + (ix + p.dw));
+    return (u / 255.0f - p.mean) * p.inv_std;
+  }
+  const float* src = static_cast<const float*>(p.x);
+  return __ldg(src + (((size_t)b * p.T + t) * p.H + iy) * p.W + ix);
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                                           // kStemAStages x 16 KB
+  uint8_t* smB = smA + kStemAStages * kStemABytes;               // 40 KB
+  uint8_t* ring = smB + kStemBBytes;                             // ring_rows x Wo x 128 B
+  const int ring_bytes = p.ring_rows * p.Wo * 128;
+  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // 2 x strip_rows x strip_w bf16
+  const int strip_elems = p.strip_rows * p.strip_w;
+  float* chan = reinterpret_cast<float*>(strip + 2 * ((strip_elems + 7) & ~7));   // scale, shift, slope
+  uint64_t* bars = reinterpret_cast<uint64_t*>(chan + 192);
+  uint64_t* full = bars;                         // [kStemAStages]
+  uint64_t* empty = bars + kStemAStages;         // [kStemAStages]
+  uint64_t* tfull = bars + 2 * kStemAStages;     // [2]
+  uint64_t* tempty = tfull + 2;                  // [2]
+  uint64_t* wbar = tempty + 2;                   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < 192; i += kStemThreads) {
+    const int c = i & 63;
+    chan[i] = i < 64 ? p.scale[c] : (i < 128 ? p.shift[c] : p.slope[c]);
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < kStemAStages; ++s) {
+        mbar_init(&full[s], 8);      // one elected arrive per producer warp
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(&tfull[0], 1);
+      mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], 128);
+      mbar_init(&tempty[1], 128);
+      mbar_init(wbar, 1);
+      fence_mbar_init();
+      tma_prefetch_desc(&mapW);
+    }
+    __syncwarp();
+    tmem_alloc<128>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 5) {
+    // =============================================================== producers: build operand A
+    const int pt = threadIdx.x - 5 * 32;          // 0..255
+    const int arow = pt & 127;                    // A-tile row (conv pixel within the tile)
+    const int half = pt >> 7;                     // chunks [4*half, 4*half+4) of the 8 x 16 B row
+    int stage = 0;
+    uint32_t phase = 0;
+    int sbuf = 0;
+    float pre[kStripMaxElems];
+
+    // strip prefetch helper state for the NEXT (frame, tile, kt)
+    auto prefetch = [&](int frame, int tile, int kt) {
+      const int b = frame / p.T, t = frame - b * p.T;
+      const int y_first = (tile * 128) / p.Wo;
+      const int iy0 = 2 * y_first - 3;
+#pragma unroll
+      for (int j = 0; j < kStripMaxElems; ++j) {
+        const int idx = pt + j * kProducerThreads;
+        float v = 0.f;
+        if (idx < strip_elems) {
+          const int r = idx / p.strip_w, c = idx - r * p.strip_w;
+          v = stem_load_px(p, b, t + kt - 2, iy0 + r, c - 3);
+        }
+        pre[j] = v;
+      }
+    };
+
+    int frame = blockIdx.x, tile = 0, kt = 0;
+    if (frame < p.frames) prefetch(frame, tile, kt);
+    while (frame < p.frames) {
+      // 1. park the prefetched strip in shared memory (bf16)
+      uint16_t* sb = strip + sbuf * ((strip_elems + 7) & ~7);
+#pragma unroll
+      for (int j = 0; j < kStripMaxElems; ++j) {
+        const int idx = pt + j * kProducerThreads;
+        if (idx < strip_elems) reinterpret_cast<__nv_bfloat16*>(sb)[idx] = __float2bfloat16_rn(pre[j]);
+      }
+      // 2. start fetching the next stage's strip
+      int nframe = frame, ntile = tile, nkt = kt + 1;
+      if (nkt == 5) { nkt = 0; if (++ntile == p.tiles_per_frame) { ntile = 0; nframe += gridDim.x; } }
+      if (nframe < p.frames) prefetch(nframe, ntile, nkt);
+      named_bar_sync(1, kProducerThreads);
+      // 3. build this thread's half row of A: chunk kh = 8 consecutive input pixels of window row kh
+      mbar_wait(&empty[stage], phase ^ 1);
+      {
+        const int m0 = tile * 128;
+        const int m = m0 + arow;
+        const int y_first = m0 / p.Wo;
+        uint8_t* dst_row = smA + stage * kStemABytes + arow * 128;
+        const bool valid = m < p.Mf;
+        const int yy = m / p.Wo, xx = m - yy * p.Wo;
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(sb) + (2 * (yy - y_first) * p.strip_w + 2 * xx) / 2;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          const int kh = half * 4 + cidx;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (valid && kh < 7) {
+            const uint32_t* s = srow + (kh * p.strip_w) / 2;
+            v.x = s[0]; v.y = s[1]; v.z = s[2]; v.w = s[3];
+          }
+          *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
+      sbuf ^= 1;
+      frame = nframe; tile = ntile; kt = nkt;
+    }
+  } else if (warp == 4) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      mbar_expect_tx(wbar, kStemBBytes);
+      for (int kt = 0; kt < 5; ++kt) tma_load_2d(smB + kt * 8192, &mapW, wbar, kt * 64, 0);
+      mbar_wait(wbar, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int frame = blockIdx.x; frame < p.frames; frame += gridDim.x) {
+        for (int tile = 0; tile < p.tiles_per_frame; ++tile) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * 64;
+          for (int kt = 0; kt < 5; ++kt) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smA + stage * kStemABytes));
+            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smB + kt * 8192));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kt | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // =============================================================== epilogue: BN + PReLU -> ring -> max-pool
+    const int et = threadIdx.x;                 // 0..127 ; warp == TMEM lane quarter
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ring_mask = p.ring_rows - 1;
+    const int row_bytes = p.Wo * 128;
+    for (int frame = blockIdx.x; frame < p.frames; frame += gridDim.x) {
+      int py_done = 0;
+      uint16_t* yframe = p.y + (size_t)frame * p.Hp * p.Wp * 64;
+      for (int tile = 0; tile < p.tiles_per_frame; ++tile) {
+        const int m = tile * 128 + et;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 64;
+        tmem_ld_32x32(taddr, r0);
+        tmem_ld_32x32(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        if (m < p.Mf) {
+          const int yy = m / p.Wo, xx = m - yy * p.Wo;
+          uint8_t* dst = ring + (yy & ring_mask) * row_bytes + xx * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = ch * 8 + i;
+              const float a = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]);
+              const float z = fmaf(a, chan[c], chan[64 + c]);
+              v[i] = z > 0.f ? z : z * chan[128 + c];
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(dst + ((ch ^ (xx & 7)) << 4)) = o;
+          }
+        }
+        named_bar_sync(2, 128);
+        // pooled rows whose three conv rows are now complete
+        const int m_end = min((tile + 1) * 128, p.Mf);
+        const int rows_complete = m_end / p.Wo;               // conv rows 0 .. rows_complete-1 are final
+        const int py_ready = rows_complete / 2;               // needs conv row 2*py+1 <= rows_complete-1
+        const int items = (py_ready - py_done) * p.Wp * 8;
+        for (int it = et; it < items; it += 128) {
+          const int ch = it & 7;
+          const int pix = it >> 3;
+          const int pyo = pix / p.Wp, px = pix - pyo * p.Wp;
+          const int py = py_done + pyo;
+          __nv_bfloat162 best[4];
+          bool first = true;
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int cy = 2 * py + dy;
+            if (cy < 0) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int cx = 2 * px + dx;
+              if (cx < 0) continue;
+              const uint4 v = *reinterpret_cast<const uint4*>(ring + (cy & ring_mask) * row_bytes + cx * 128 +
+                                                              ((ch ^ (cx & 7)) << 4));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+              if (first) {
+                best[0] = h[0]; best[1] = h[1]; best[2] = h[2]; best[3] = h[3];
+                first = false;
+              } else {
+                best[0] = __hmax2(best[0], h[0]); best[1] = __hmax2(best[1], h[1]);
+                best[2] = __hmax2(best[2], h[2]); best[3] = __hmax2(best[3], h[3]);
+              }
+            }
+          }
+          *reinterpret_cast<uint4*>(yframe + ((size_t)py * p.Wp + px) * 64 + ch * 8) =
+              *reinterpret_cast<const uint4*>(best);
+        }
+        py_done = py_ready;
+        named_bar_sync(2, 128);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+}  // namespace dl
+
+extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
+                                            float mean, float std, const void* w_packed, const float* scale,
+                                            const float* shift, const float* slope, void* y, void* stream) {
+  using namespace dl;
+  DL_CHECK_ARG(x && w_packed && scale && shift && slope && y, "stem: null pointer");
+  DL_CHECK_ARG(B > 0 && T > 0, "stem: empty batch");
+  DL_CHECK_ARG(H >= 8 && W >= 8 && H % 4 == 0 && W % 4 == 0 && W <= 128, "stem: H, W must be multiples of 4, W <= 128");
+  if (is_u8) {
+    DL_CHECK_ARG(Hraw >= H && Wraw >= W && std != 0.f, "stem: raw crop smaller than the centre crop");
+  }
+  int st = require_sm100();
+  if (st != DL_OK) return st;
+
+  StemParams p;
+  p.x = x; p.is_u8 = is_u8;
+  p.B = B; p.T = T; p.H = H; p.W = W; p.Hraw = Hraw; p.Wraw = Wraw;
+  // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
+  p.dh = is_u8 ? (Hraw - H) / 2 : 0;
+  p.dw = is_u8 ? (Wraw - W) / 2 : 0;
+  p.mean = mean; p.inv_std = is_u8 ? 1.0f / std : 1.0f;
+  p.Ho = H / 2; p.Wo = W / 2; p.Hp = H / 4; p.Wp = W / 4;
+  p.Mf = p.Ho * p.Wo;
+  p.tiles_per_frame = (p.Mf + 127) / 128;
+  const int span = (127 + p.Wo - 1) / p.Wo;           // extra conv rows a tile can reach past its first row
+  int rr = 1;
+  while (rr < span + 6) rr <<= 1;
+  p.ring_rows = rr;
+  p.strip_rows = 2 * span + 7;
+  p.strip_w = W + 8;
+  DL_CHECK_ARG(p.strip_rows * p.strip_w <= kStripMaxElems * kProducerThreads, "stem: frame too small/wide for the strip");
+  p.scale = scale; p.shift = shift; p.slope = slope;
+  p.y = static_cast<uint16_t*>(y);
+  p.frames = B * T;
+
+  const int strip_elems = p.strip_rows * p.strip_w;
+  const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
+                      2 * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 16 * 8 + 16;
+  DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  CUtensorMap mapW;
+  st = make_tiled_2d_bf16(&mapW, w_packed, 64, 320, 320, 64, 64);
+  if (st != DL_OK) return st;
+  int grid = device_sm_count();
+  if (grid <= 0) grid = 148;
+  if (p.frames < grid) grid = p.frames;
+  stem_conv3d_kernel<<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
+  return check_launch("stem_conv3d_kernel");
+}

@@ -1,0 +1,229 @@
+"""Torch-tensor front door of the C ABI: pointer / shape plumbing only (no math happens here).
+
+Every function takes CUDA tensors, enqueues one or two kernels of libdeeplip_b200.so on the
+current CUDA stream and returns freshly allocated outputs.  bf16 activations are channels-last.
+"""
+import ctypes as C
+import torch
+
+from . import _lib
+from ._lib import ConvDesc
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('deeplip_b200 ops need CUDA tensors (there is no CPU fallback)')
+
+
+def ceil_to(x, m):
+    return (x + m - 1) // m * m
+
+
+def num_frames(nsamp, frame_len=400, step=160):
+    return 1 if nsamp <= frame_len else 1 + -(-(nsamp - frame_len) // step)
+
+
+# ------------------------------------------------------------------ K1
+FEAT_KINDS = {'mfcc': 0, 'fbank': 1, 'logfbank': 2}
+
+
+def frontend_features(wav, feat_type='mfcc', n_feat=24, cmvn=True, lengths=None, ld=None):
+    """wav (B, nsamp) f32 -> (feat_f32 (B,F,T), feat_bf16 (B,T,ld))."""
+    _need_cuda(wav, lengths)
+    wav = wav.contiguous().float()
+    B, nsamp = wav.shape
+    T = num_frames(nsamp)
+    ld = ld or ceil_to(n_feat, 64)
+    f32 = torch.empty((B, n_feat, T), device=wav.device, dtype=torch.float32)
+    b16 = torch.empty((B, T, ld), device=wav.device, dtype=torch.bfloat16)
+    st = _lib.lib().dl_frontend_features(_ptr(wav), _ptr(lengths), B, nsamp, FEAT_KINDS[feat_type], n_feat,
+                                         int(bool(cmvn)), _ptr(b16), ld, _ptr(f32), T, _stream())
+    _lib.check(st, 'dl_frontend_features')
+    return f32, b16
+
+
+def nct_to_ntc_bf16(x, ld=None):
+    _need_cuda(x)
+    x = x.contiguous().float()
+    B, Cc, T = x.shape
+    ld = ld or ceil_to(Cc, 64)
+    y = torch.empty((B, T, ld), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dl_nct_to_ntc_bf16(_ptr(x), B, Cc, T, _ptr(y), ld, _stream()), 'dl_nct_to_ntc_bf16')
+    return y
+
+
+# ------------------------------------------------------------------ K2
+def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std=0.165):
+    """x: (B,T,H,W) f32 normalised frames, or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T, H/4, W/4, 64) bf16."""
+    _need_cuda(x, w_packed, scale, shift, slope)
+    x = x.contiguous()
+    B, T = x.shape[0], x.shape[1]
+    if x.dtype == torch.uint8:
+        Hraw, Wraw = x.shape[2], x.shape[3]
+        H, W = crop
+        is_u8 = 1
+    else:
+        x = x.float()
+        H, W = x.shape[2], x.shape[3]
+        Hraw, Wraw, is_u8 = H, W, 0
+    y = torch.empty((B * T, H // 4, W // 4, 64), device=x.device, dtype=torch.bfloat16)
+    st = _lib.lib().dl_stem_conv3d_bn_prelu_pool(_ptr(x), is_u8, B, T, H, W, Hraw, Wraw, float(mean), float(std),
+                                                 _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope), _ptr(y),
+                                                 _stream())
+    _lib.check(st, 'dl_stem_conv3d_bn_prelu_pool')
+    return y
+
+
+# ------------------------------------------------------------------ K3 / K5 / K7
+def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=(1, 1), scale=None, shift=None,
+               slope=None, residual=None, want_bf16=True, want_f32=False, scale2=None, shift2=None,
+               f32_slope=1.0):
+    """x: (N,H,W,ldx) bf16 channels-last.  Returns (y_bf16 (N,P,Q,Cout) | None, y_f32 (N*P*Q,Cout) | None)."""
+    _need_cuda(x, w_packed, scale, shift, slope, residual, scale2, shift2)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    N, H, W, ldx = x.shape
+    P = (H + 2 * pad[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
+    Q = (W + 2 * pad[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
+    y = torch.empty((N, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    yf = torch.empty((N * P * Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.numel() == y.numel()
+    d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], Cout, Cout,
+                 float(f32_slope))
+    st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
+                                       _ptr(residual), _ptr(y), _ptr(yf), _ptr(scale2), _ptr(shift2),
+                                       C.byref(d), _stream())
+    _lib.check(st, 'dl_conv_igemm_bf16')
+    return y, yf
+
+
+# ------------------------------------------------------------------ K4 / K6
+def frame_pool_temporal_mean(x, B, T, lengths=None, want_frames=True, want_mean=True):
+    """x: (B*T, P, Q, C) bf16 -> (frame_feats (B,T,C) f32 | None, utt_mean (B,C) f32 | None)."""
+    _need_cuda(x, lengths)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    Cc = x.shape[-1]
+    HW = x.numel() // (B * T * Cc)
+    ff = torch.empty((B, T, Cc), device=x.device, dtype=torch.float32) if want_frames else None
+    um = torch.empty((B, Cc), device=x.device, dtype=torch.float32) if want_mean else None
+    st = _lib.lib().dl_frame_pool_temporal_mean(_ptr(x), B, T, HW, Cc, _ptr(lengths), _ptr(ff), _ptr(um), _stream())
+    _lib.check(st, 'dl_frame_pool_temporal_mean')
+    return ff, um
+
+
+def stat_pool(x, Cc, lengths=None, want_f32=True, want_bf16=True, logits=None):
+    """x: (B,T,ldx) bf16 -> (out_f32 (B,2C) | None, out_bf16 (B,2C) | None); attentive if logits given."""
+    _need_cuda(x, lengths, logits)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 3
+    B, T, ldx = x.shape
+    of = torch.empty((B, 2 * Cc), device=x.device, dtype=torch.float32) if want_f32 else None
+    ob = torch.empty((B, 2 * Cc), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    if logits is None:
+        st = _lib.lib().dl_stat_pool(_ptr(x), B, T, Cc, ldx, _ptr(lengths), _ptr(of), _ptr(ob), 2 * Cc, _stream())
+        _lib.check(st, 'dl_stat_pool')
+    else:
+        st = _lib.lib().dl_attn_stat_pool(_ptr(x), _ptr(logits), B, T, Cc, ldx, _ptr(lengths), _ptr(of), _ptr(ob),
+                                          2 * Cc, _stream())
+        _lib.check(st, 'dl_attn_stat_pool')
+    return of, ob
+
+
+def attn_logits(h_f32, v, k):
+    _need_cuda(h_f32, v)
+    rows, Hd = h_f32.shape
+    e = torch.empty((rows,), device=h_f32.device, dtype=torch.float32)
+    st = _lib.lib().dl_attn_logits(_ptr(h_f32), rows, Hd, Hd, _ptr(v), float(k), _ptr(e), _stream())
+    _lib.check(st, 'dl_attn_logits')
+    return e
+
+
+# ------------------------------------------------------------------ K8
+def znorm_concat(a, v, biased=False, video_first=False, l2norm=False, want_bf16=False):
+    _need_cuda(a, v)
+    a = a.contiguous().float()
+    v = v.contiguous().float()
+    B, Da = a.shape
+    Dv = v.shape[1]
+    out = torch.empty((B, Da + Dv), device=a.device, dtype=torch.float32)
+    ob = torch.empty((B, Da + Dv), device=a.device, dtype=torch.bfloat16) if want_bf16 else None
+    st = _lib.lib().dl_znorm_concat(_ptr(a), Da, _ptr(v), Dv, B, int(biased), int(video_first), int(l2norm),
+                                    _ptr(out), _ptr(ob), _stream())
+    _lib.check(st, 'dl_znorm_concat')
+    return (out, ob) if want_bf16 else out
+
+
+def lowfer(e1, e2):
+    _need_cuda(e1, e2)
+    e1 = e1.contiguous().float()
+    e2 = e2.contiguous().float()
+    B, D = e1.shape
+    out = torch.empty((B, 3 * D), device=e1.device, dtype=torch.float32)
+    _lib.check(_lib.lib().dl_lowfer(_ptr(e1), _ptr(e2), B, D, _ptr(out), _stream()), 'dl_lowfer')
+    return out
+
+
+def l2_normalize(x, want_bf16=False):
+    _need_cuda(x)
+    x = x.contiguous().float()
+    B, D = x.shape
+    out = torch.empty_like(x)
+    ob = torch.empty((B, D), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    _lib.check(_lib.lib().dl_l2_normalize(_ptr(x), B, D, _ptr(out), _ptr(ob), _stream()), 'dl_l2_normalize')
+    return (out, ob) if want_bf16 else out
+
+
+def affine_act(x, scale=None, shift=None, slope=1.0, ld=None, want_bf16=True, want_f32=False):
+    """lrelu(x*scale+shift) on (rows,C) f32 -> (bf16 (rows,ld) | None, f32 (rows,C) | None)."""
+    _need_cuda(x, scale, shift)
+    x = x.contiguous().float()
+    rows, Cc = x.shape
+    ld = ld or Cc
+    y = torch.empty((rows, ld), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    yf = torch.empty((rows, Cc), device=x.device, dtype=torch.float32) if want_f32 else None
+    st = _lib.lib().dl_affine_act(_ptr(x), rows, Cc, _ptr(scale), _ptr(shift), float(slope), _ptr(y), ld, _ptr(yf),
+                                  _stream())
+    _lib.check(st, 'dl_affine_act')
+    return y, yf
+
+
+# ------------------------------------------------------------------ K9
+def cosine_score_trials(emb, enrol, test):
+    _need_cuda(emb, enrol, test)
+    emb = emb.contiguous().float()
+    assert enrol.dtype == torch.int32 and test.dtype == torch.int32
+    n = enrol.numel()
+    scores = torch.empty((n,), device=emb.device, dtype=torch.float32)
+    st = _lib.lib().dl_cosine_score_trials(_ptr(emb), emb.shape[0], emb.shape[1], _ptr(enrol), _ptr(test), n,
+                                           _ptr(scores), _stream())
+    _lib.check(st, 'dl_cosine_score_trials')
+    return scores
+
+
+def score_fusion_trials(emb_a, emb_v, enrol, test):
+    _need_cuda(emb_a, emb_v, enrol, test)
+    emb_a = emb_a.contiguous().float()
+    emb_v = emb_v.contiguous().float()
+    n = enrol.numel()
+    scores = torch.empty((n,), device=emb_a.device, dtype=torch.float32)
+    st = _lib.lib().dl_score_fusion_trials(_ptr(emb_a), emb_a.shape[1], _ptr(emb_v), emb_v.shape[1], emb_a.shape[0],
+                                           _ptr(enrol), _ptr(test), n, _ptr(scores), _stream())
+    _lib.check(st, 'dl_score_fusion_trials')
+    return scores
+
+
+def gather_scores(S, rows, cols):
+    _need_cuda(S, rows, cols)
+    n = rows.numel()
+    out = torch.empty((n,), device=S.device, dtype=torch.float32)
+    st = _lib.lib().dl_gather_scores(_ptr(S), S.stride(0), _ptr(rows), _ptr(cols), n, _ptr(out), _stream())
+    _lib.check(st, 'dl_gather_scores')
+    return out

@@ -1,0 +1,98 @@
+"""Drop-in for models/video_models/model.py: Lipreading (:61-105) with extract_feats=True.
+
+forward(x: (B,1,T,H,W) f32, lengths) -> (B,T,512) f32, exactly the reference contract used by
+train_fusion.py:71-76, 348, 400 and train_video.py:99-106.  The Conv3d stem runs as one fused
+tcgen05 kernel (conv + BN + PReLU + max-pool, channels-last output), the ResNet-18 trunk as
+implicit-GEMM kernels, the pooling tail as a warp-shuffle reduction.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops, packing
+from .resnet import ResNet, BasicBlock
+
+
+def threeD_to_2D_tensor(x):
+    n_batch, n_channels, s_time, sx, sy = x.shape
+    return x.transpose(1, 2).reshape(n_batch * s_time, n_channels, sx, sy)
+
+
+class Lipreading(nn.Module):
+    def __init__(self, hidden_dim=256, backbone_type='resnet', num_classes=500, relu_type='prelu',
+                 tcn_options={}, width_mult=1.0, extract_feats=False):
+        super().__init__()
+        self.extract_feats = extract_feats
+        self.backbone_type = backbone_type
+        if backbone_type != 'resnet':
+            # conf/video_config.json:2 and conf/fusion_config.yaml:75 both select 'resnet'
+            raise NotImplementedError("only backbone_type='resnet' is on the B200 hot path (SURVEY 2)")
+        if not extract_feats:
+            raise NotImplementedError('the MS-TCN classification head (extract_feats=False) is outside the '
+                                      'extraction hot path (SURVEY 8(f) N3); construct with extract_feats=True')
+        self.frontend_nout = 64
+        self.backend_out = 512
+        self.trunk = ResNet(BasicBlock, [2, 2, 2, 2], relu_type=relu_type)
+        frontend_relu = nn.PReLU(num_parameters=self.frontend_nout) if relu_type == 'prelu' else nn.ReLU()
+        self.frontend3D = nn.Sequential(
+            nn.Conv3d(1, self.frontend_nout, kernel_size=(5, 7, 7), stride=(1, 2, 2), padding=(2, 3, 3), bias=False),
+            nn.BatchNorm3d(self.frontend_nout),
+            frontend_relu,
+            nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1)))
+        self._pk = None
+
+    # -- checkpoints: tolerate 'module.' prefixes and the TCN head keys a reference checkpoint carries
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        sd = {}
+        for k, v in state_dict.items():
+            k = k[7:] if k.startswith('module.') else k
+            if k.startswith('tcn.'):
+                continue
+            sd[k] = v
+        out = super().load_state_dict(sd, strict=strict, **kw)
+        self.invalidate()
+        return out
+
+    def invalidate(self):
+        self._pk = None
+        self.trunk.invalidate()
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self.invalidate()
+        return out
+
+    def _packed(self):
+        if self._pk is None:
+            conv, bn, act = self.frontend3D[0], self.frontend3D[1], self.frontend3D[2]
+            pk = {'w': packing.pack_stem_weight(conv.weight.detach())}
+            pk['s'], pk['h'] = packing.fold_bn(bn.weight.detach(), bn.bias.detach(), bn.running_mean,
+                                               bn.running_var, eps=bn.eps)
+            if isinstance(act, nn.PReLU):
+                pk['a'] = act.weight.detach().float().expand(64).contiguous()
+            else:
+                pk['a'] = torch.zeros(64, device=conv.weight.device)
+            self._pk = pk
+        return self._pk
+
+    def trunk_maps(self, x):
+        """x: (B,T,H,W) f32 normalised frames or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T,3,3,512) bf16."""
+        if self.training:
+            raise RuntimeError('deeplip_b200.Lipreading is inference-only: call .eval() (BN uses running stats)')
+        pk = self._packed()
+        y = ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'])
+        return self.trunk.forward_nhwc(y)
+
+    def forward(self, x, lengths=None):
+        B, C, T, H, W = x.size()
+        assert C == 1
+        y = self.trunk_maps(x[:, 0])
+        feats, _ = ops.frame_pool_temporal_mean(y, B, T, want_frames=True, want_mean=False)
+        return feats                      # (B, T, 512); lengths unused when extract_feats (model.py:105)
+
+    def utterance_embedding(self, x, lengths=None):
+        """Fused form of train_fusion.py:400: mean over the (valid) frames of each clip -> (B,512).
+        x as in trunk_maps; lengths: int32 CUDA tensor of valid frame counts (zero-padded tails)."""
+        B, T = x.shape[0], x.shape[1]
+        y = self.trunk_maps(x)
+        _, mean = ops.frame_pool_temporal_mean(y, B, T, lengths=lengths, want_frames=False, want_mean=True)
+        return mean

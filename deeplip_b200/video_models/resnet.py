@@ -1,0 +1,158 @@
+"""Drop-in for models/video_models/resnet.py (BasicBlock :28-69, ResNet :72-127).
+
+Parameters live in ordinary nn.Conv2d / nn.BatchNorm2d / nn.PReLU containers with the reference's
+attribute names, so reference checkpoints load unchanged; the containers are never *called* --
+forward runs dl_conv_igemm_bf16 (tcgen05 implicit GEMM, BN/PReLU/residual fused) on channels-last
+bf16 activations.  Inference (eval) only.
+"""
+import math
+import torch
+import torch.nn as nn
+
+from .. import ops, packing
+
+
+def conv3x3(in_planes, out_planes, stride=1):
+    return nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=stride, padding=1, bias=False)
+
+
+def downsample_basic_block(inplanes, outplanes, stride):
+    return nn.Sequential(nn.Conv2d(inplanes, outplanes, kernel_size=1, stride=stride, bias=False),
+                         nn.BatchNorm2d(outplanes))
+
+
+def _slope_of(act, planes, device):
+    if isinstance(act, nn.PReLU):
+        w = act.weight.detach().float()
+        return (w.expand(planes) if w.numel() == 1 else w).contiguous()
+    return torch.zeros(planes, device=device)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, relu_type='relu'):
+        super().__init__()
+        assert relu_type in ['relu', 'prelu']
+        self.conv1 = conv3x3(inplanes, planes, stride)
+        self.bn1 = nn.BatchNorm2d(planes)
+        if relu_type == 'relu':
+            self.relu1 = nn.ReLU(inplace=True)
+            self.relu2 = nn.ReLU(inplace=True)
+        else:
+            self.relu1 = nn.PReLU(num_parameters=planes)
+            self.relu2 = nn.PReLU(num_parameters=planes)
+        self.conv2 = conv3x3(planes, planes)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+        self.inplanes, self.planes = inplanes, planes
+        self._pk = None
+
+    def _packed(self):
+        if self._pk is None:
+            dev = self.conv1.weight.device
+            pk = {}
+            pk['w1'] = packing.pack_conv_weight(self.conv1.weight.detach())
+            pk['s1'], pk['h1'] = packing.fold_bn(self.bn1.weight.detach(), self.bn1.bias.detach(),
+                                                 self.bn1.running_mean, self.bn1.running_var, eps=self.bn1.eps)
+            pk['a1'] = _slope_of(self.relu1, self.planes, dev)
+            pk['w2'] = packing.pack_conv_weight(self.conv2.weight.detach())
+            pk['s2'], pk['h2'] = packing.fold_bn(self.bn2.weight.detach(), self.bn2.bias.detach(),
+                                                 self.bn2.running_mean, self.bn2.running_var, eps=self.bn2.eps)
+            pk['a2'] = _slope_of(self.relu2, self.planes, dev)
+            if self.downsample is not None:
+                dconv, dbn = self.downsample[0], self.downsample[1]
+                pk['wd'] = packing.pack_conv_weight(dconv.weight.detach())
+                pk['sd'], pk['hd'] = packing.fold_bn(dbn.weight.detach(), dbn.bias.detach(), dbn.running_mean,
+                                                     dbn.running_var, eps=dbn.eps)
+                pk['ad'] = torch.ones(self.planes, device=dev)       # identity activation on the skip
+            self._pk = pk
+        return self._pk
+
+    def forward_nhwc(self, x):
+        """x: (N,H,W,inplanes) bf16 -> (N,P,Q,planes) bf16  (reference forward :56-69)."""
+        pk = self._packed()
+        st = (self.stride, self.stride)
+        out, _ = ops.conv_igemm(x, pk['w1'], self.inplanes, self.planes, 3, 3, st, (1, 1), (1, 1),
+                                pk['s1'], pk['h1'], pk['a1'])
+        if self.downsample is not None:
+            res, _ = ops.conv_igemm(x, pk['wd'], self.inplanes, self.planes, 1, 1, st, (0, 0), (1, 1),
+                                    pk['sd'], pk['hd'], pk['ad'])
+        else:
+            res = x
+        out, _ = ops.conv_igemm(out, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1),
+                                pk['s2'], pk['h2'], pk['a2'], residual=res)
+        return out
+
+    def forward(self, x):
+        y = self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+        return y.permute(0, 3, 1, 2).float()
+
+
+class ResNet(nn.Module):
+    def __init__(self, block, layers, num_classes=1000, relu_type='relu', gamma_zero=False,
+                 avg_pool_downsample=False):
+        self.inplanes = 64
+        self.relu_type = relu_type
+        self.gamma_zero = gamma_zero
+        if avg_pool_downsample:
+            raise NotImplementedError('avg_pool_downsample is never enabled by the reference configs')
+        self.downsample_block = downsample_basic_block
+        super().__init__()
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        for m in self.modules():       # reference default init, resnet.py:88-96
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+        if self.gamma_zero:
+            for m in self.modules():
+                if isinstance(m, BasicBlock):
+                    m.bn2.weight.data.zero_()
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = self.downsample_block(inplanes=self.inplanes, outplanes=planes * block.expansion,
+                                               stride=stride)
+        layers = [block(self.inplanes, planes, stride, downsample, relu_type=self.relu_type)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes, relu_type=self.relu_type))
+        return nn.Sequential(*layers)
+
+    def invalidate(self):
+        for m in self.modules():
+            if isinstance(m, BasicBlock):
+                m._pk = None
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self.invalidate()
+        return out
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.invalidate()
+        return out
+
+    def forward_nhwc(self, x):
+        """(N,H,W,64) bf16 -> (N,P,Q,512) bf16, before the global average pool."""
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                x = blk.forward_nhwc(x)
+        return x
+
+    def forward(self, x):
+        """Reference signature: (N,64,H,W) f32 -> (N,512) f32 (resnet.py:120-127)."""
+        y = self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+        N = y.shape[0]
+        feats, _ = ops.frame_pool_temporal_mean(y, N, 1, want_frames=True, want_mean=False)
+        return feats.view(N, -1)

@@ -1,0 +1,166 @@
+/*
+ * deeplip_b200 -- C ABI of the B200 (sm_100a) kernels behind the DeepLip audio-visual
+ * embedding-extraction + trial-scoring hot path.
+ *
+ * The reference (DanielMengLiu/DeepLip) has no FFI of its own: the boundary it exposes is the
+ * Python module interface of models/audio_models, models/video_models and models/fusion_models
+ * (SURVEY.md 8(b)).  Every entry point below replaces the PyTorch/NumPy/sklearn library call(s)
+ * made at the cited reference lines; the drop-in nn.Modules in deeplip_b200/ bind them with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers + sizes; no torch types; caller owns every buffer (no allocation here);
+ *   - work is ENQUEUED on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - returns DL_OK (0) or a negative DL_ERR_* code; dl_last_error() gives the message (thread-local);
+ *   - never throws; there is no CPU fallback: without a CUDA device every compute call fails.
+ *   - "bf16" buffers are raw 16-bit bfloat16; activations are channels-last.
+ */
+#ifndef DEEPLIP_B200_H
+#define DEEPLIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DL_OK 0
+#define DL_ERR_INVALID (-1)     /* bad argument / unsupported shape                       */
+#define DL_ERR_CUDA (-2)        /* CUDA runtime / driver error (launch, tensor-map encode) */
+#define DL_ERR_UNSUPPORTED (-3) /* device is not sm_100                                    */
+
+int dl_version(void);
+const char* dl_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+long long dl_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  audio front end.  Replaces python_speech_features.{mfcc,fbank,logfbank} + `_normalize`
+ *     (models/fusion_models/datasets.py:227-246, 214-215).  wav: (B, nsamp) f32 ->
+ *     feat_bf16: (B, T, ld_bf16) channels-last bf16 (zero padded to ld_bf16 channels; may be NULL),
+ *     feat_f32 : (B, F, T) f32, the layout the reference hands to the model (required: it doubles
+ *                as the pre-CMVN scratch, this library never allocates).
+ *     kind: 0 = mfcc(numcep=F, nfilt=26), 1 = fbank(nfilt=F), 2 = logfbank(nfilt=F).
+ *     lengths: per-utterance valid sample counts (device int32, may be NULL = nsamp for all);
+ *     T must equal 1 + ceil((nsamp - 400) / 160) for the padded length nsamp (16 kHz, 25/10 ms).
+ */
+int dl_frontend_features(const float* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
+                         int cmvn, void* feat_bf16, int ld_bf16, float* feat_f32, int T, void* stream);
+
+/* (B, C, T) f32 -> (B, T, ldc) bf16 channels-last, zero padded: the layout change in front of the
+ * TDNN for callers that bring their own features (models/audio_models/tdnn.py:89 input). */
+int dl_nct_to_ntc_bf16(const float* x, int B, int C, int T, void* y, int ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  video stem.  Replaces Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) + BatchNorm3d + PReLU +
+ *     MaxPool3d((1,3,3),(1,2,2),(0,1,1)) and the NCTHW -> (N*T)CHW copy
+ *     (models/video_models/model.py:81-85, 9-13).
+ *     Input either f32 frames (B, T, H, W) already normalised (u8 == 0) or raw u8 crops
+ *     (B, T, Hraw, Wraw) with the reference preprocessing fused into the load (u8 == 1):
+ *     x/255 -> centre crop to HxW -> (x-mean)/std  (models/video_models/dataloaders.py:19-24).
+ *     w_packed: (64, 320) bf16 = [cout][kt][kh*8+kw] zero padded (see deeplip_b200/packing.py).
+ *     y: (B*T, H/4, W/4, 64) bf16 channels-last.
+ */
+int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
+                                 float mean, float std, const void* w_packed, const float* scale,
+                                 const float* shift, const float* slope, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3/K5/K7  implicit-GEMM convolution on tcgen05 tensor cores (TMA im2col operand A, TMA tiled
+ *     operand B, fp32 accumulation in TMEM) with a fused epilogue:
+ *         v = acc * scale[c] + shift[c] (+ residual);  y = v > 0 ? v : v * slope[c]
+ *     Replaces nn.Conv2d + BatchNorm2d + PReLU (+ residual add) in BasicBlock
+ *     (models/video_models/resnet.py:56-69), the 1x1 stride-2 downsample (resnet.py:13-17),
+ *     nn.Conv1d + BatchNorm1d + LeakyReLU in TDNN_Block (models/audio_models/tdnn.py:35-43, H = R = 1)
+ *     and nn.Linear + BatchNorm1d + LeakyReLU in the heads (tdnn.py:93-100, model_fusion.py:19-24;
+ *     H = W = R = S = 1).
+ *     x        : (N, H, W, ldx) bf16 channels-last, C logical channels (ldx % 8 == 0)
+ *     w_packed : (Cout, R*S*ceil64(C)) bf16, K index = (r*S + s) * ceil64(C) + c
+ *     y        : (N*P*Q, ldy) bf16 or NULL;  residual: same layout as y or NULL
+ *     y_f32    : (N*P*Q, ldf) f32 or NULL = lrelu(acc * scale2[c] + shift2[c], f32_slope)  (side output,
+ *                e.g. x_a of extract_embedding, tdnn.py:93; scale2/shift2 NULL = raw accumulator)
+ *     Cout % 8 == 0.
+ */
+typedef struct dl_conv_desc {
+  int N, H, W, C, ldx;
+  int Cout, R, S;
+  int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int ldy, ldf;
+  float f32_slope;   /* leaky slope applied to the f32 side output (1.0f = none) */
+} dl_conv_desc;
+
+int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
+                       const float* slope, const void* residual, void* y, float* y_f32, const float* scale2,
+                       const float* shift2, const dl_conv_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  per-frame global average pool + masked temporal mean.  Replaces AdaptiveAvgPool2d(1)
+ *     (models/video_models/resnet.py:125-126), `_average_batch` (model.py:16-17) and
+ *     torch.mean(..., dim=0) over one clip (train_fusion.py:400).
+ *     x: (B*T, HW, C) bf16 -> frame_feats (B, T, C) f32 (may be NULL), utt_mean (B, C) f32 (may be
+ *     NULL) = mean over the first lengths[b] frames (lengths NULL = T).
+ */
+int dl_frame_pool_temporal_mean(const void* x, int B, int T, int HW, int C, const int32_t* lengths,
+                                float* frame_feats, float* utt_mean, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  statistics pooling.  Replaces MeanStdPooling (models/audio_models/pooling.py:18-26):
+ *     mean || unbiased std over time.  x: (B, T, ldx) bf16 channels-last, C channels ->
+ *     out_f32 (B, 2C) f32 (may be NULL) and out_bf16 (B, ld_out) bf16 (may be NULL).
+ *     lengths: valid frames per utterance (NULL = T) for ragged batches.
+ */
+int dl_stat_pool(const void* x, int B, int T, int C, int ldx, const int32_t* lengths, float* out_f32,
+                 void* out_bf16, int ld_out, void* stream);
+
+/* Attentive statistics pooling tail (models/audio_models/pooling.py:96-106): given the attention
+ * logits e (B, T) f32 (= v . relu(W x + b) + k, produced with dl_conv_igemm_bf16 + dl_attn_logits),
+ * alpha = softmax_T(e); mean = sum alpha x; std = sqrt(sum alpha x^2 - mean^2).  Same outputs as
+ * dl_stat_pool. */
+int dl_attn_stat_pool(const void* x, const float* logits, int B, int T, int C, int ldx,
+                      const int32_t* lengths, float* out_f32, void* out_bf16, int ld_out, void* stream);
+/* e[b,t] = sum_h v[h] * relu(h[b,t,h]) + k   (pooling.py:97-99); h: (B*T, ldh) f32 = W x + b. */
+int dl_attn_logits(const float* h, int rows, int Hd, int ldh, const float* v, float k, float* e,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K8  fusion.
+ *  dl_znorm_concat: Trainer.feature_normalize x2 + torch.cat([audio, video], 1)
+ *     (train_fusion.py:233-238, 405-410; unbiased std) or, with biased != 0 and video_first != 0,
+ *     the NumPy variant feature_normalize + hstack((video, audio)) (models/fusion_models/utils.py:
+ *     465-471, 524-527).  Optionally L2-normalises the fused row (what cosine scoring needs).
+ *     a: (B, Da) f32, v: (B, Dv) f32 -> out (B, Da+Dv) f32, out_bf16 optional (B, Da+Dv) bf16.
+ *  dl_lowfer: LowFER.forward's live path cat([e1, sigmoid(e2), e1*sigmoid(e2)], 1)
+ *     (models/fusion_models/LBP.py:46-50).
+ *  dl_l2_normalize: F.normalize(xv) (train_audio.py:430) / the row normalisation inside
+ *     sklearn cosine_similarity (zero norm -> divide by 1).
+ */
+int dl_znorm_concat(const float* a, int Da, const float* v, int Dv, int B, int biased, int video_first,
+                    int l2norm, float* out, void* out_bf16, void* stream);
+int dl_lowfer(const float* e1, const float* e2, int B, int D, float* out, void* stream);
+int dl_l2_normalize(const float* x, int B, int D, float* out, void* out_bf16, void* stream);
+/* y = lrelu(x * scale[c] + shift[c], slope) on f32 (rows, C): bf16 copy (rows, ldc, zero padded) and/or f32
+ * copy (rows, C).  BatchNorm1d + LeakyReLU after the heads (tdnn.py:103-111) and the f32 -> bf16 hand-off. */
+int dl_affine_act(const float* x, int rows, int C, const float* scale, const float* shift, float slope,
+                  void* y_bf16, int ldc, float* y_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9  trial scoring.  Replaces the per-trial sklearn cosine_similarity loop
+ *     (models/fusion_models/utils.py:272-279): scores[i] = cos(emb[enrol[i]], emb[test[i]]).
+ *     emb: (N_utt, D) f32 (need not be normalised); enrol/test: int32[n_trials] rows into emb.
+ *     dl_score_fusion adds the 0.5/0.5 score fusion of utils.py:343-377 (second embedding table,
+ *     eps = 1e-8 clamp on the video norms like F.cosine_similarity).
+ */
+int dl_cosine_score_trials(const float* emb, int n_utt, int D, const int32_t* enrol, const int32_t* test,
+                           int n_trials, float* scores, void* stream);
+int dl_score_fusion_trials(const float* emb_a, int Da, const float* emb_v, int Dv, int n_utt,
+                           const int32_t* enrol, const int32_t* test, int n_trials, float* scores,
+                           void* stream);
+/* Dense formulation: gather scores[i] = S[enrol_row[i], test_col[i]] from a score matrix S (ld) f32
+ * produced by dl_conv_igemm_bf16 on L2-normalised bf16 embeddings (enrol x test^T). */
+int dl_gather_scores(const float* S, int ld, const int32_t* rows, const int32_t* cols, int n_trials,
+                     float* scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPLIP_B200_H */

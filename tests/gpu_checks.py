@@ -1,0 +1,226 @@
+"""Kernel-level parity checks: CUDA path (through the C ABI) vs the CPU oracle on seeded inputs.
+Each check returns a dict of error metrics and raises AssertionError when out of tolerance.
+Used by tests/test_gpu_*.py and tools/gpu_diag.py."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from deeplip_b200 import ops, packing, synth
+from oracle import frontend_np, models_ref, scoring_ref
+
+DEV = 'cuda'
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel_err(a, b):
+    a = a.float().cpu()
+    b = b.float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def conv_case(N, H, W, C, Cout, R, S, stride=1, pad=0, dil=(1, 1), residual=False, f32=False, seed=0, ld=None,
+              tol=1.5e-2):
+    g = torch.Generator().manual_seed(seed)
+    ld = ld or packing.ceil_to(C, 8)
+    x = bf16r(torch.randn(N, H, W, C, generator=g))
+    w = bf16r(torch.randn(Cout, C, R, S, generator=g) / (C * R * S) ** 0.5)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.2
+    slope = torch.rand(Cout, generator=g) * 0.5
+    acc = F.conv2d(x.permute(0, 3, 1, 2), w, None, stride=stride, padding=pad, dilation=dil)   # (N,Cout,P,Q)
+    ref = acc * scale[None, :, None, None] + shift[None, :, None, None]
+    res = None
+    if residual:
+        res = bf16r(torch.randn(ref.shape, generator=g))
+        ref = ref + res
+    ref = torch.where(ref > 0, ref, ref * slope[None, :, None, None])
+    xpad = torch.zeros(N, H, W, ld)
+    xpad[..., :C] = x
+    coutp = packing.ceil_to(Cout, 8)
+    st = (stride, stride) if isinstance(stride, int) else stride
+    pd = (pad, pad) if isinstance(pad, int) else pad
+    y, yf = ops.conv_igemm(
+        xpad.to(DEV).to(torch.bfloat16), packing.pack_conv_weight(w.to(DEV), coutp), C, coutp, R, S, st, pd, dil,
+        packing.pad_vec(scale.to(DEV), coutp), packing.pad_vec(shift.to(DEV), coutp),
+        packing.pad_vec(slope.to(DEV), coutp),
+        residual=(None if res is None else _pad_last(res.permute(0, 2, 3, 1), coutp).to(DEV).to(torch.bfloat16).contiguous()),
+        want_f32=f32)
+    torch.cuda.synchronize()
+    out = {}
+    got = y.float().cpu()[..., :Cout].permute(0, 3, 1, 2)
+    out['bf16_rel'] = rel_err(got, ref)
+    if coutp != Cout:
+        out['pad_abs'] = float(y.float().cpu()[..., Cout:].abs().max())
+    if f32:
+        P, Q = acc.shape[2], acc.shape[3]
+        gotf = yf.cpu().view(N, P, Q, coutp)[..., :Cout].permute(0, 3, 1, 2)
+        out['f32_rel'] = rel_err(gotf, acc)
+        assert out['f32_rel'] < 2e-3, out
+    assert out['bf16_rel'] < tol, out
+    assert out.get('pad_abs', 0.0) == 0.0, out
+    return out
+
+
+def _pad_last(t, n):
+    if t.shape[-1] == n:
+        return t
+    out = torch.zeros(*t.shape[:-1], n)
+    out[..., :t.shape[-1]] = t
+    return out
+
+
+CONV_CASES = {
+    'l1_3x3_64': dict(N=3, H=22, W=22, C=64, Cout=64, R=3, S=3, stride=1, pad=1, residual=True),
+    'l2_3x3s2_64_128': dict(N=3, H=22, W=22, C=64, Cout=128, R=3, S=3, stride=2, pad=1),
+    'l2_1x1s2_64_128': dict(N=3, H=22, W=22, C=64, Cout=128, R=1, S=1, stride=2, pad=0),
+    'l2_3x3_128': dict(N=2, H=11, W=11, C=128, Cout=128, R=3, S=3, stride=1, pad=1, residual=True),
+    'l3_3x3s2_128_256': dict(N=2, H=11, W=11, C=128, Cout=256, R=3, S=3, stride=2, pad=1),
+    'l3_3x3_256': dict(N=5, H=6, W=6, C=256, Cout=256, R=3, S=3, stride=1, pad=1, residual=True),
+    'l4_3x3s2_256_512': dict(N=5, H=6, W=6, C=256, Cout=512, R=3, S=3, stride=2, pad=1),
+    'l4_3x3_512': dict(N=40, H=3, W=3, C=512, Cout=512, R=3, S=3, stride=1, pad=1, residual=True),
+    'tdnn_k5_24_512': dict(N=2, H=1, W=50, C=64, Cout=512, R=1, S=5),
+    'tdnn_k3d3_512': dict(N=2, H=1, W=140, C=512, Cout=512, R=1, S=3, dil=(1, 3)),
+    'tdnn_k1_512_1500': dict(N=2, H=1, W=130, C=512, Cout=1500, R=1, S=1),
+    'fc_3000_512': dict(N=5, H=1, W=1, C=3000, Cout=512, R=1, S=1, f32=True),
+    'many_tiles': dict(N=64, H=22, W=22, C=64, Cout=64, R=3, S=3, stride=1, pad=1, residual=True),
+}
+
+
+def stem_case(B=2, T=6, H=88, W=88, u8=False, seed=0):
+    sd = synth.make_video_state_dict(seed=seed + 1, randomize=True)
+    if u8:
+        raw = torch.from_numpy(synth.lip_crops_u8([1] * B, T=T, H=H + 8, W=W + 8, seed=seed + 1))
+        x = torch.stack([models_ref.video_preprocess(r, crop=H) for r in raw])        # (B,T,H,W) f32
+        xin = raw.to(DEV)
+    else:
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(B, T, H, W, generator=g)
+        xin = x.to(DEV)
+    sdr = dict(sd)
+    sdr['frontend3D.0.weight'] = bf16r(sd['frontend3D.0.weight'])
+    ref = models_ref.video_frontend3d(sdr, bf16r(x)[:, None])                          # (B,64,T,H/4,W/4)
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(B * T, H // 4, W // 4, 64)
+    w = packing.pack_stem_weight(sd['frontend3D.0.weight'].to(DEV))
+    s, h = packing.fold_bn(sd['frontend3D.1.weight'], sd['frontend3D.1.bias'], sd['frontend3D.1.running_mean'],
+                           sd['frontend3D.1.running_var'])
+    y = ops.stem_conv3d(xin, w, s.to(DEV), h.to(DEV), sd['frontend3D.2.weight'].to(DEV), crop=(H, W))
+    torch.cuda.synchronize()
+    out = {'rel': rel_err(y, ref)}
+    d = (y.float().cpu() - ref).abs()
+    out['worst'] = [int(v) for v in np.unravel_index(int(d.argmax()), d.shape)]
+    assert out['rel'] < 1.5e-2, out
+    return out
+
+
+def stat_pool_case(B=3, T=277, C=1500, seed=0, lengths=None):
+    g = torch.Generator().manual_seed(seed)
+    ld = packing.ceil_to(C, 8)
+    x = bf16r(torch.randn(B, T, C, generator=g) * 2 + 0.5)
+    xp = _pad_last(x, ld)
+    ln = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=DEV)
+    f32, b16 = ops.stat_pool(xp.to(DEV).to(torch.bfloat16), C, lengths=ln)
+    torch.cuda.synchronize()
+    if lengths is None:
+        ref = models_ref.mean_std_pooling(x.permute(0, 2, 1))
+    else:
+        ref = torch.cat([models_ref.mean_std_pooling(x[i:i + 1, :l].permute(0, 2, 1)) for i, l in enumerate(lengths)])
+    out = {'abs': float((f32.cpu() - ref).abs().max()), 'bf16_rel': rel_err(b16, ref)}
+    assert out['abs'] < 2e-5 and out['bf16_rel'] < 5e-3, out
+    return out
+
+
+def attn_pool_case(B=3, T=120, C=512, Hd=64, seed=0):
+    from deeplip_b200.audio_models.pooling import AttentiveStatPooling
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(B, C, T, generator=g))
+    m = AttentiveStatPooling(C, Hd)
+    sd = {'pooling.' + k: v.detach().clone() for k, v in m.state_dict().items()}
+    sd['pooling.W'] = bf16r(sd['pooling.W'])
+    m.load_state_dict({k[8:]: v for k, v in sd.items()})
+    ref = models_ref.attentive_stat_pooling(sd, x)
+    got = m.to(DEV)(x.to(DEV))
+    torch.cuda.synchronize()
+    out = {'abs': float((got.cpu() - ref).abs().max())}
+    assert out['abs'] < 2e-3, out
+    return out
+
+
+def frame_pool_case(B=3, T=7, HW=9, C=512, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(B * T, HW, C, generator=g))
+    lengths = [T, max(1, T - 2), max(1, T // 2)][:B]
+    ff, um = ops.frame_pool_temporal_mean(x.view(B * T, 3, 3, C).to(DEV).to(torch.bfloat16), B, T,
+                                          lengths=torch.tensor(lengths, dtype=torch.int32, device=DEV))
+    torch.cuda.synchronize()
+    ref_f = x.mean(dim=1).view(B, T, C)
+    ref_m = models_ref.temporal_mean(ref_f, lengths)
+    out = {'frames_abs': float((ff.cpu() - ref_f).abs().max()), 'mean_abs': float((um.cpu() - ref_m).abs().max())}
+    assert out['frames_abs'] < 1e-5 and out['mean_abs'] < 1e-5, out
+    return out
+
+
+def fusion_case(B=9, D=512, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, D, generator=g) * 3 + 1
+    v = torch.randn(B, D, generator=g) * 0.5 - 2
+    ref = models_ref.concat_fusion(a, v)
+    got = ops.znorm_concat(a.to(DEV), v.to(DEV))
+    ref_np = np.stack([scoring_ref.featurefusion_embedding(a[i].numpy(), v[i].numpy()) for i in range(B)])
+    got_np = ops.znorm_concat(a.to(DEV), v.to(DEV), biased=True, video_first=True)
+    got_l2 = ops.znorm_concat(a.to(DEV), v.to(DEV), l2norm=True)
+    lf = ops.lowfer(a.to(DEV), v.to(DEV))
+    l2 = ops.l2_normalize(a.to(DEV))
+    torch.cuda.synchronize()
+    out = {'concat_abs': float((got.cpu() - ref).abs().max()),
+           'np_abs': float(np.abs(got_np.cpu().numpy() - ref_np).max()),
+           'l2_abs': float((got_l2.cpu() - F.normalize(ref, dim=1)).abs().max()),
+           'lowfer_abs': float((lf.cpu() - models_ref.lowfer_forward(a, v)).abs().max()),
+           'l2n_abs': float((l2.cpu() - F.normalize(a, dim=1)).abs().max())}
+    assert max(out.values()) < 2e-5, out
+    return out
+
+
+def scoring_case(n_utt=500, D=1024, n_trials=3000, seed=0):
+    rng = np.random.default_rng(seed)
+    emb = synth.structured_embeddings(rng.integers(0, 30, n_utt), dim=D, seed=seed + 1)
+    emb[7] = 0.0                                     # zero row: sklearn divides by 1
+    enrol = rng.integers(0, n_utt, n_trials).astype(np.int32)
+    test = rng.integers(0, n_utt, n_trials).astype(np.int32)
+    enrol[:3], test[:3] = 7, (7, 8, 9)
+    got = ops.cosine_score_trials(torch.from_numpy(emb).to(DEV), torch.from_numpy(enrol).to(DEV),
+                                  torch.from_numpy(test).to(DEV))
+    torch.cuda.synchronize()
+    ref = scoring_ref.cosine_scores_vec(emb, enrol, test)
+    loop = np.concatenate(scoring_ref.cosine_scores_loop(emb, enrol[:200], test[:200]))
+    out = {'abs': float(np.abs(got.cpu().numpy() - ref).max()), 'loop_abs': float(np.abs(got.cpu().numpy()[:200] - loop).max())}
+    embv = synth.structured_embeddings(rng.integers(0, 30, n_utt), dim=512, seed=seed + 2)
+    gf = ops.score_fusion_trials(torch.from_numpy(emb).to(DEV), torch.from_numpy(embv).to(DEV),
+                                 torch.from_numpy(enrol).to(DEV), torch.from_numpy(test).to(DEV))
+    reff = 0.5 * ref + 0.5 * np.array([scoring_ref.torch_cosine_eps(embv[a].astype(np.float64), embv[b].astype(np.float64))
+                                       for a, b in zip(enrol, test)])
+    out['fusion_abs'] = float(np.abs(gf.cpu().numpy() - reff).max())
+    assert max(out.values()) < 2e-6, out
+    return out
+
+
+def frontend_case(B=3, nsamp=16000, feat_type='mfcc', n_feat=24, seed=0, lengths=None):
+    wav = synth.speech_like_audio(list(range(B)), nsamp=nsamp, seed=seed + 1)
+    ln = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=DEV)
+    f32, b16 = ops.frontend_features(torch.from_numpy(wav).to(DEV), feat_type, n_feat, lengths=ln)
+    torch.cuda.synchronize()
+    opts = dict(num_cep=n_feat, num_bin=n_feat)
+    out = {'abs': 0.0}
+    for i in range(B):
+        n = nsamp if lengths is None else lengths[i]
+        ref = frontend_np.extract_feature(wav[i, :n].astype(np.float64), 16000, feat_type, opts).T    # (F,T_i)
+        got = f32[i].cpu().numpy()
+        out['abs'] = max(out['abs'], float(np.abs(got[:, :ref.shape[1]] - ref).max()))
+        if ref.shape[1] < got.shape[1]:
+            assert np.all(got[:, ref.shape[1]:] == 0)
+        gb = b16[i].float().cpu().numpy()[:ref.shape[1], :n_feat].T
+        out['bf16_abs'] = max(out.get('bf16_abs', 0.0), float(np.abs(gb - ref).max()))
+    assert out['abs'] < 2e-3 and out['bf16_abs'] < 5e-2, out
+    return out
