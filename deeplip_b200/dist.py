@@ -1,0 +1,76 @@
+"""Multi-GPU plumbing: one process per GPU, utterances sharded with no data-path
+collective during extraction, ONE all_gather of the fused embeddings before scoring, trial lines
+sharded across ranks, scores gathered for the CPU EER step.  The reference has no distributed code
+(only single-process nn.DataParallel, unwrapped before extraction: train_fusion.py:318-328).
+Device-agnostic: runs on NCCL/CUDA in production and on gloo/CPU tensors in the unit tests.
+"""
+import os
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's env (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_size(n, world):
+    return -(-n // world)
+
+
+def shard_range(n, rank, world):
+    """Contiguous block of utterance indices owned by `rank` (equal padded shards)."""
+    per = shard_size(n, world)
+    return min(rank * per, n), min((rank + 1) * per, n)
+
+
+def all_gather_rows(local_rows, n_total, rank, world):
+    """local_rows: (n_local, D) rows [lo,hi) of a (n_total, D) table -> the full table on every rank.
+    Shards are padded to equal size so a single all_gather_into_tensor moves everything."""
+    if world == 1:
+        return local_rows
+    per = shard_size(n_total, world)
+    D = local_rows.shape[1]
+    send = local_rows
+    if local_rows.shape[0] != per:
+        send = torch.zeros((per, D), device=local_rows.device, dtype=local_rows.dtype)
+        send[:local_rows.shape[0]] = local_rows
+    full = torch.empty((per * world, D), device=local_rows.device, dtype=local_rows.dtype)
+    dist.all_gather_into_tensor(full, send.contiguous())
+    return full[:n_total]
+
+
+def gather_scores(local_scores, n_total, rank, world):
+    """Concatenate per-rank score slices (contiguous trial shards) into the full vector on every rank."""
+    if world == 1:
+        return local_scores
+    per = shard_size(n_total, world)
+    send = torch.zeros((per,), device=local_scores.device, dtype=local_scores.dtype)
+    send[:local_scores.numel()] = local_scores
+    full = torch.empty((per * world,), device=local_scores.device, dtype=local_scores.dtype)
+    dist.all_gather_into_tensor(full, send)
+    return full[:n_total]
+
+
+def max_over_ranks(value, device):
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

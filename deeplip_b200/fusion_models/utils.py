@@ -1,0 +1,99 @@
+"""Scoring side of models/fusion_models/utils.py (and its near-duplicate
+models/audio_models/utils.py): eer_cos_* (:251-283), *_scorefusion (:331-435),
+*_featurefusion (:437-522), feature_normalize (:524-527).
+
+The reference re-reads two .npy files and calls sklearn once PER TRIAL; here the embedding table is
+resident on the GPU and one kernel (dl_cosine_score_trials) scores the whole list through the
+(enrol_idx, test_idx) gather.  EER stays on the CPU with the very same sklearn / scipy calls
+(:280-282), so EER parity reduces to score parity.
+"""
+import os
+import numpy as np
+import torch
+
+from .. import ops
+from ..trials import TrialList
+
+
+def eer_from_scores(y_true, y_pred):
+    """models/fusion_models/utils.py:280-282."""
+    from sklearn.metrics import roc_curve
+    from scipy.optimize import brentq
+    from scipy.interpolate import interp1d
+    fpr, tpr, threshold = roc_curve(y_true, y_pred, pos_label=1)
+    eer = brentq(lambda x: 1. - x - interp1d(fpr, tpr)(x), 0., 1.)
+    threshold = interp1d(fpr, threshold)(eer)
+    return eer, threshold
+
+
+def feature_normalize(data):
+    """utils.py:524-527 on a (N,D) table: biased std per row, no eps -- on the device."""
+    z = ops.znorm_concat(data, data, biased=True)
+    return z[:, :data.shape[1]].contiguous()
+
+
+def _dev(x, device):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.to(device)
+
+
+def score_trials(emb, trials, device='cuda', lo=None, hi=None):
+    """scores[i] = cos(emb[enrol[i]], emb[test[i]]) for trial lines [lo, hi) -> torch f32 (on device)."""
+    sl = slice(lo, hi)
+    return ops.cosine_score_trials(_dev(emb, device).float(), _dev(trials.enrol_idx[sl], device),
+                                   _dev(trials.test_idx[sl], device))
+
+
+def score_trials_fusion(emb_audio, emb_video, trials, device='cuda'):
+    """0.5 cos(audio) + 0.5 cos(video) (utils.py:343-344, 372-377)."""
+    return ops.score_fusion_trials(_dev(emb_audio, device).float(), _dev(emb_video, device).float(),
+                                   _dev(trials.enrol_idx, device), _dev(trials.test_idx, device))
+
+
+def score_trials_featurefusion(emb_audio, emb_video, trials, device='cuda'):
+    """biased z-norm per modality, hstack((video, audio)), cosine (utils.py:465-472)."""
+    fused = ops.znorm_concat(_dev(emb_audio, device).float(), _dev(emb_video, device).float(), biased=True,
+                             video_first=True)
+    return ops.cosine_score_trials(fused, _dev(trials.enrol_idx, device), _dev(trials.test_idx, device))
+
+
+def eer_cos(trials, emb, device='cuda'):
+    s = score_trials(emb, trials, device)
+    return eer_from_scores(trials.labels, s.cpu().numpy())
+
+
+# ---------------------------------------------------------------- on-disk hand-off (reference wire format)
+def utt_to_relpath(utt):
+    return utt.replace('.wav', '.npy')
+
+
+def save_embeddings(root, utts, emb):
+    """One (1,D) float32 .npy per utterance at <root>/<dirname(utt)>/<basename>.npy
+    (train_fusion.py:414-417)."""
+    emb = emb.detach().cpu().numpy() if torch.is_tensor(emb) else np.asarray(emb)
+    for u, e in zip(utts, emb):
+        path = os.path.join(root, utt_to_relpath(u))
+        os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+        np.save(path, e.reshape(1, -1).astype(np.float32))
+
+
+def load_embeddings(root, utts):
+    """Read each utterance's .npy ONCE (the reference reads two per trial, utils.py:276-277)."""
+    return np.stack([np.load(os.path.join(root, utt_to_relpath(u))).reshape(-1) for u in utts]).astype(np.float32)
+
+
+def _eer_cos_dir(exp_dir, sub, trial_path, root='exp', device='cuda'):
+    trials = TrialList.from_file(trial_path)
+    emb = load_embeddings(os.path.join(root, str(exp_dir), sub), trials.utts)
+    return eer_cos(trials, emb, device)
+
+
+def eer_cos_grid(exp_dir, trial_path='data/data_audio/trial_grid_2w.txt', root='exp', device='cuda'):
+    """Reference signature eer_cos_grid(exp_dir) -> (eer, threshold) (utils.py:268-283)."""
+    return _eer_cos_dir(exp_dir, 'test_em_grid', trial_path, root, device)
+
+
+def eer_cos_lomgrid(exp_dir, trial_path='data/data_audio/trial_lomgrid_2w.txt', root='exp', device='cuda'):
+    """utils.py:251-266."""
+    return _eer_cos_dir(exp_dir, 'test_em_lomgrid', trial_path, root, device)

@@ -1,0 +1,76 @@
+"""Batched audio-visual embedding extraction: the B200 form of the reference's per-utterance loop
+`Trainer.extract_test_xv_grid` / `extract_test_xv_lomgrid` (train_fusion.py:317-420).
+
+Reference order per utterance (train_fusion.py:386-417):
+    wav -> MFCC + CMVN (DataLoader worker)        -> model_audio.extract_embedding -> xv_audio (1,512)
+    clips -> /255, centre crop, (x-.421)/.165     -> model_video per clip -> mean over frames -> mean over clips
+    feature_normalize x2 -> cat([audio, video])   -> np.save
+Here a whole batch of utterances goes through the same arithmetic in ~45 kernel launches, nothing
+leaves the device, and ragged batches carry `lengths` (zero-padded tails are exact for the video
+branch; the audio branch masks its pooling).
+"""
+import torch
+
+from . import ops
+from .fusion_models import model_fusion as fusion_mod
+
+
+class AVExtractor:
+    FUSIONS = ('concat', 'concat_np', 'linear', 'lowfer', 'audio', 'video')
+
+    def __init__(self, audio_model, video_model, fusion='concat', fusion_model=None, feat_type='mfcc',
+                 n_feat=24, cmvn=True, l2norm=False):
+        if fusion not in self.FUSIONS:
+            raise NotImplementedError('fusion %r (have %s)' % (fusion, ', '.join(self.FUSIONS)))
+        self.audio, self.video = audio_model, video_model
+        self.fusion, self.fusion_model = fusion, fusion_model
+        self.feat_type, self.n_feat, self.cmvn, self.l2norm = feat_type, n_feat, cmvn, l2norm
+
+    def audio_embedding(self, wav, wav_lengths=None):
+        """wav (B,nsamp) f32 CUDA -> xv (B,E) f32 (LMCL convention: 2nd fc output, train_fusion.py:390)."""
+        _, feat = ops.frontend_features(wav, self.feat_type, self.n_feat, self.cmvn, lengths=wav_lengths)
+        frames = None
+        if wav_lengths is not None:
+            frames = torch.where(wav_lengths <= 400, torch.ones_like(wav_lengths),
+                                 1 + torch.div(wav_lengths - 400 + 159, 160, rounding_mode='floor')).to(torch.int32)
+        xv, _ = self.audio.embed_ntc(feat, frames)
+        return xv
+
+    def video_embedding(self, video, video_lengths=None):
+        """video (B,T,H,W) f32 / (B,T,96,96) u8, or (B,G,T,..) for G clips per utterance -> (B,512)."""
+        if video.dim() == 5:
+            B, G = video.shape[:2]
+            em = self.video.utterance_embedding(video.reshape(B * G, *video.shape[2:]),
+                                                None if video_lengths is None else video_lengths.reshape(-1))
+            return em.view(B, G, -1).mean(dim=1)      # mean over clips (train_fusion.py:401)
+        return self.video.utterance_embedding(video, video_lengths)
+
+    def fuse(self, xv_audio, em_video):
+        if self.fusion == 'concat':          # F0, the default executed at test time
+            return ops.znorm_concat(xv_audio, em_video, l2norm=self.l2norm)
+        if self.fusion == 'concat_np':       # F3, models/fusion_models/utils.py:465-471
+            return ops.znorm_concat(xv_audio, em_video, biased=True, video_first=True, l2norm=self.l2norm)
+        if self.fusion == 'linear':          # F1 on cat([audio, video])
+            return self.fusion_model(torch.cat([xv_audio, em_video], dim=1))
+        if self.fusion == 'lowfer':          # F2
+            return ops.lowfer(xv_audio, em_video)
+        return xv_audio if self.fusion == 'audio' else em_video
+
+    @torch.no_grad()
+    def extract(self, wav, video, wav_lengths=None, video_lengths=None):
+        xv = self.audio_embedding(wav, wav_lengths) if self.fusion != 'video' else None
+        em = self.video_embedding(video, video_lengths) if self.fusion != 'audio' else None
+        return self.fuse(xv, em)
+
+
+def build_models(device='cuda', audio_arch='etdnn', pooling='statistic', seed=1, randomize=True):
+    """Random-init (seeded) audio + video drop-in models in eval mode, as bench/tests use them."""
+    from . import synth
+    from .audio_models.tdnn import SpeakerEmbNet
+    from .video_models.model import Lipreading
+    aopts = synth.audio_opts(audio_arch, pooling)
+    audio = SpeakerEmbNet(aopts)
+    audio.load_state_dict(synth.make_audio_state_dict(aopts, seed=seed, randomize=randomize))
+    video = Lipreading(relu_type='prelu', backbone_type='resnet', extract_feats=True, tcn_options=synth.TCN_OPTIONS)
+    video.load_state_dict(synth.make_video_state_dict(seed=seed, randomize=randomize))
+    return audio.to(device).eval(), video.to(device).eval()
