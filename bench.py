@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- AV embedding extraction (+ trial scoring) throughput on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic GRID-shaped utterances per GPU
+(75 frames of 96x96 uint8 lip crops -> centre-crop 88x88, + 3 s of 16 kHz audio): MFCC front end ->
+E-TDNN audio embedding, Conv3d stem -> ResNet-18 trunk -> temporal mean, z-norm + concat fusion
+(train_fusion.py:386-410), then -- for N > 1 -- the NCCL all_gather of the step's fused embeddings.
+`value` = utterances/s of the whole job with inputs resident in HBM; `e2e` = the same through the
+public API from pinned HOST buffers (H2D of wav + crops and D2H of the embeddings inside the timed
+region).  Trial scoring over a trial_grid_v1-shaped list (20 000 trials) is timed separately and
+reported under "scoring".  `--impl reference` times the CPU oracle port of the same path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+T_FRAMES, RAW_HW, CROP_HW, NSAMP = 75, 96, 88, 48000
+GFLOP_TRUNK_PER_UTT = 42.870        # ResNet-18 body, SURVEY 8(d)
+GFLOP_STEM_PER_UTT = 4.5535
+GFLOP_AUDIO_PER_UTT = 2.550 + 0.0036
+METRIC = 'av_utterances_per_sec'
+UNIT = 'utt/s'
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'],
+                'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'src': 'fallback'}
+
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix='clocks_', suffix='.csv')
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 4:]           # drop the idle head/tail samples
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- inputs
+def synth_batch(B, seed):
+    """uint8 crops (B,75,96,96) + wav (B,48000) f32 with speaker structure (deeplip_b200.synth)."""
+    from deeplip_b200 import synth
+    rng = np.random.default_rng(seed)
+    spk = rng.integers(1, 34, B)
+    # crops: speaker field + noise; generated once per speaker then perturbed per utterance (cheap)
+    raw = synth.lip_crops_u8(spk, T=4, H=RAW_HW, W=RAW_HW, seed=seed)
+    raw = np.tile(raw, (1, (T_FRAMES + 3) // 4, 1, 1))[:, :T_FRAMES]
+    noise = rng.integers(-6, 7, raw.shape, dtype=np.int16)
+    raw = np.clip(raw.astype(np.int16) + noise, 0, 255).astype(np.uint8)
+    wav = synth.speech_like_audio(spk, nsamp=NSAMP, seed=seed)
+    return raw, wav
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def oracle_av_extract(raw, wav, sda, sdv, aopts):
+    """CPU restatement of train_fusion.py:386-410 per utterance (B=1 per clip, like the reference)."""
+    from oracle import frontend_np, models_ref
+    outs = []
+    with torch.no_grad():
+        for i in range(raw.shape[0]):
+            feat = torch.from_numpy(frontend_np.extract_feature(wav[i].astype(np.float64)).T)[None]
+            xv, _ = models_ref.speaker_extract_embedding(sda, feat, aopts)
+            x = models_ref.video_preprocess(torch.from_numpy(raw[i]))[None, None]
+            em = models_ref.lipreading_features(sdv, x).squeeze(0).mean(dim=0, keepdim=True)
+            outs.append(models_ref.concat_fusion(xv, em))
+    return torch.cat(outs)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from deeplip_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    aopts = synth.audio_opts('etdnn', 'statistic')
+    sda = synth.make_audio_state_dict(aopts, seed=1)
+    sdv = synth.make_video_state_dict(seed=1)
+    per_step = args.ref_utts
+    raw, wav = synth_batch(per_step, seed=1)
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle_av_extract(raw[:1], wav[:1], sda, sdv, aopts)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_av_extract(raw, wav, sda, sdv, aopts)
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, per_gpu_batch=per_step),
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d utterances/step x %d steps, per-utterance B=1 loop like '
+                                       'train_fusion.py:386-410 (oracle/ port of the reference modules)' %
+                                       (per_step, args.steps)},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_batch):
+    return {'workload': 'configs[2]-shaped AV extraction: E-TDNN(mfcc-24) audio + Conv3d/ResNet-18 video + z-norm '
+                        'concat fusion, GRID utterances (75x96x96 u8 crops -> 88x88, 3 s 16 kHz audio); '
+                        'video-only configs[1] is its dominant part',
+            'per_gpu_batch': per_gpu_batch, 'global_batch': per_gpu_batch * args.gpus,
+            'frames': T_FRAMES, 'crop': CROP_HW, 'audio_samples': NSAMP, 'parallelism': 'dp%d' % args.gpus,
+            'l2': '256 MiB memset between steps (inside the timed region) + 4 rotating input batches'}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local):
+    from deeplip_b200 import _lib, dist as dl_dist, synth
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    from deeplip_b200.fusion_models import utils as U
+    from deeplip_b200.trials import TrialList
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    audio, video = build_models(dev, seed=1)
+    ex = AVExtractor(audio, video, fusion='concat')
+
+    nrot = 4
+    host, devb = [], []
+    for r in range(nrot):
+        raw, wav = synth_batch(B, seed=100 * rank + r + 1)
+        hr, hw = torch.from_numpy(raw).pin_memory(), torch.from_numpy(wav).pin_memory()
+        host.append((hr, hw))
+        devb.append((hr.to(dev), hw.to(dev)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_total = B * world
+
+    def step(i, from_host=False):
+        if from_host:
+            hr, hw = host[i % nrot]
+            raw_d, wav_d = hr.to(dev, non_blocking=True), hw.to(dev, non_blocking=True)
+        else:
+            raw_d, wav_d = devb[i % nrot]
+        emb = ex.extract(wav_d, raw_d)
+        if world > 1:
+            emb = dl_dist.all_gather_rows(emb, n_total, rank, world)
+        if from_host:
+            return emb.to('cpu', non_blocking=False)
+        return emb
+
+    def timed(nsteps, from_host):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dl_dist.barrier()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        ev0.record()
+        for i in range(nsteps):
+            flush.zero_()
+            step(i, from_host)
+        ev1.record()
+        torch.cuda.synchronize()
+        dl_dist.barrier()
+        ms = dl_dist.max_over_ranks(ev0.elapsed_time(ev1), dev)
+        return ms, _lib.launch_count() - l0
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms, launches = timed(args.steps, from_host=False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.steps * n_total / (ms / 1e3)
+
+    for i in range(2):
+        step(i, from_host=True)
+    ms_e2e, _ = timed(args.steps, from_host=True)
+    e2e = args.steps * n_total / (ms_e2e / 1e3)
+    h2d = B * (T_FRAMES * RAW_HW * RAW_HW + NSAMP * 4)
+    d2h = n_total * 1024 * 4
+
+    # ---- roofline of the dominant kernel (igemm_conv_kernel): the 19 trunk launches of one step
+    peaks = measured_peaks()
+    pk = video._packed()
+    from deeplip_b200 import ops
+    stem_out = ops.stem_conv3d(devb[0][0], pk['w'], pk['s'], pk['h'], pk['a'], crop=(CROP_HW, CROP_HW))
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(max(3, min(args.steps, 10))):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        video.trunk.forward_nhwc(stem_out)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    trunk_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+    trunk_tflops = GFLOP_TRUNK_PER_UTT * B / trunk_ms          # GFLOP / ms == TFLOP/s
+    roofline = {'kernel': 'igemm_conv_kernel (19 ResNet-18 trunk launches of one step)', 'bound': 'tensor',
+                'achieved': trunk_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': trunk_tflops / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'peak_src': peaks['src'] + ' (sustained bf16 cuBLAS)', 'launches': 19,
+                'avg_launch_ms': trunk_ms / 19, 'flop_per_launch': GFLOP_TRUNK_PER_UTT * B * 1e9 / 19}
+    # stem + audio, for the record
+    evs = []
+    for i in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.stem_conv3d(devb[i % nrot][0], pk['w'], pk['s'], pk['h'], pk['a'], crop=(CROP_HW, CROP_HW))
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    stem_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+    evs = []
+    for i in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ex.audio_embedding(devb[i % nrot][1])
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    audio_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+
+    # ---- trial scoring on a trial_grid_v1-shaped list, sharded over ranks
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    scoring = None
+    try:
+        import gpu_checks
+        tmp = tempfile.mkdtemp()
+        tl = TrialList.from_file(gpu_checks.make_trial_file(os.path.join(tmp, 'trial_grid_shape.txt'), 'grid'))
+        emb = torch.from_numpy(synth.structured_embeddings([synth.speaker_of_utt(u) for u in tl.utts],
+                                                           dim=1024, seed=3, within=6.0)).to(dev)
+        sl = tl.shard(rank, world)
+        en = torch.from_numpy(tl.enrol_idx[sl]).to(dev)
+        te = torch.from_numpy(tl.test_idx[sl]).to(dev)
+        for _ in range(3):
+            ops.cosine_score_trials(emb, en, te)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(10):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            s_loc = ops.cosine_score_trials(emb, en, te)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        sc_ms = dl_dist.max_over_ranks(statistics.median(a.elapsed_time(b) for a, b in evs), dev)
+        s_all = dl_dist.gather_scores(s_loc, len(tl), rank, world)
+        eer, _ = U.eer_from_scores(tl.labels, s_all.cpu().numpy())
+        alg_bytes = len(tl.utts) * 1024 * 4 + len(tl) * 12
+        scoring = {'trials_per_sec': len(tl) / (sc_ms / 1e3), 'ms': sc_ms, 'n_trials': len(tl), 'n_utts': len(tl.utts),
+                   'dim': 1024, 'eer': float(eer),
+                   'roofline': {'bound': 'hbm', 'achieved': alg_bytes / world / (sc_ms / 1e3) / 1e9,
+                                'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                'frac': alg_bytes / world / (sc_ms / 1e3) / 1e9 / peaks['hbm_gbs'], 'traffic': None}}
+    except Exception as e:      # scoring is reported next to the headline, it must not sink it
+        scoring = {'error': repr(e)[:200]}
+
+    if rank != 0:
+        return
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        aopts = synth.audio_opts('etdnn', 'statistic')
+        sda, sdv = synth.make_audio_state_dict(aopts, seed=1), synth.make_video_state_dict(seed=1)
+        raw, wav = host[0][0].numpy(), host[0][1].numpy()
+        oracle_av_extract(raw[:1], wav[:1], sda, sdv, aopts)
+        n, t0 = 0, time.perf_counter()
+        ref_rows = []
+        while n < B and (time.perf_counter() - t0 < 12.0 or n < 4):
+            ref_rows.append(oracle_av_extract(raw[n:n + 1], wav[n:n + 1], sda, sdv, aopts))
+            n += 1
+        dt = time.perf_counter() - t0
+        got = ex.extract(devb[0][1][:n].contiguous(), devb[0][0][:n].contiguous()).cpu().double()
+        ref = torch.cat(ref_rows).double()
+        cos = ((got * ref).sum(1) / (got.norm(dim=1) * ref.norm(dim=1))).min().item()
+        cpu = {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': '%d of the %d utterances of batch 0, per-utterance B=1 loop (train_fusion.py:386-410) '
+                         'through oracle/ (torch fp32 CPU + NumPy MFCC)' % (n, B),
+               'parity_min_cosine_vs_gpu': cos}
+
+    total_gflop = (GFLOP_TRUNK_PER_UTT + GFLOP_STEM_PER_UTT + GFLOP_AUDIO_PER_UTT) * n_total
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': workload_config(args, B),
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
+            'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'scoring': scoring,
+            'step_tflops': total_gflop / (ms / args.steps),
+            'breakdown_ms': {'stem': stem_ms, 'trunk': trunk_ms, 'audio_frontend_tdnn': audio_ms},
+            'stem_tflops': GFLOP_STEM_PER_UTT * B / stem_ms}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='utterances per GPU per step')
+    ap.add_argument('--ref-utts', type=int, default=4, help='utterances per step of the CPU reference arm')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    if world > 1:
+        from deeplip_b200 import dist as dl_dist
+        dl_dist.init_from_env('nccl')
+    if world != args.gpus and rank == 0:
+        print('warning: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)' % (args.gpus, world),
+              file=sys.stderr)
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

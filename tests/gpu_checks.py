@@ -224,3 +224,210 @@ def frontend_case(B=3, nsamp=16000, feat_type='mfcc', n_feat=24, seed=0, lengths
         out['bf16_abs'] = max(out.get('bf16_abs', 0.0), float(np.abs(gb - ref).max()))
     assert out['abs'] < 2e-3 and out['bf16_abs'] < 5e-2, out
     return out
+
+
+# ======================================================================================== model level
+def cosine_rows(a, b):
+    a = a.double().cpu().reshape(a.shape[0], -1)
+    b = b.double().cpu().reshape(b.shape[0], -1)
+    return (a * b).sum(1) / (a.norm(dim=1) * b.norm(dim=1))
+
+
+def video_model_case(B=2, T=6, seed=1, u8=True, speakers=None):
+    """Lipreading drop-in vs the fp32 oracle (pure fp32 weights/inputs: the real tolerance test)."""
+    from deeplip_b200.video_models.model import Lipreading
+    sd = synth.make_video_state_dict(seed=seed, randomize=True)
+    m = Lipreading(relu_type='prelu', backbone_type='resnet', extract_feats=True, tcn_options=synth.TCN_OPTIONS)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    raw = torch.from_numpy(synth.lip_crops_u8(speakers or list(range(B)), T=T, seed=seed))
+    x = torch.stack([models_ref.video_preprocess(r) for r in raw])              # (B,T,88,88)
+    with torch.no_grad():
+        ref = models_ref.lipreading_features(sd, x[:, None])
+        got = m(x[:, None].to(DEV), lengths=[T] * B)
+        emb_u8 = m.utterance_embedding(raw.to(DEV)) if u8 else None
+    torch.cuda.synchronize()
+    out = {'frame_cos_min': float(cosine_rows(got.reshape(B * T, -1), ref.reshape(B * T, -1)).min()),
+           'rel': rel_err(got, ref)}
+    if u8:
+        out['utt_cos_min'] = float(cosine_rows(emb_u8, ref.mean(dim=1)).min())
+        assert out['utt_cos_min'] > 0.999, out
+    assert out['frame_cos_min'] > 0.999, out
+    return out
+
+
+def video_golden_case():
+    import os
+    from deeplip_b200.video_models.model import Lipreading
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'video_small.npz'))
+    sd = synth.make_video_state_dict(seed=1, randomize=True)
+    m = Lipreading(relu_type='prelu', backbone_type='resnet', extract_feats=True, tcn_options=synth.TCN_OPTIONS)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    raw = torch.from_numpy(synth.lip_crops_u8([3, 3, 7], T=6, seed=1)).to(DEV)
+    with torch.no_grad():
+        y = m.trunk_maps(raw)
+        feats, _ = ops.frame_pool_temporal_mean(y, 3, 6)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(gold['feats'])
+    out = {'cos_min': float(cosine_rows(feats.reshape(18, -1), ref.reshape(18, -1)).min()), 'rel': rel_err(feats, ref)}
+    assert out['cos_min'] > 0.999, out
+    return out
+
+
+def audio_model_case(arch='etdnn', pooling='statistic', B=3, nsamp=24000, seed=1, lengths=None):
+    from deeplip_b200.audio_models.tdnn import SpeakerEmbNet
+    o = synth.audio_opts(arch, pooling)
+    sd = synth.make_audio_state_dict(o, seed=seed, randomize=True)
+    net = SpeakerEmbNet(o)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    wav = synth.speech_like_audio(list(range(B)), nsamp=nsamp, seed=seed)
+    feats = np.stack([frontend_np.extract_feature(w.astype(np.float64)).T for w in wav])     # (B,24,T)
+    x = torch.from_numpy(feats)
+    with torch.no_grad():
+        xv_ref, xa_ref = models_ref.speaker_extract_embedding(sd, x, o)
+        fw_ref = models_ref.speaker_forward(sd, x, o)
+        xv, xa = net.extract_embedding(x.to(DEV))
+        fw = net(x.to(DEV))
+    torch.cuda.synchronize()
+    out = {'xv_cos_min': float(cosine_rows(xv, xv_ref).min()), 'xa_cos_min': float(cosine_rows(xa, xa_ref).min()),
+           'fw_cos_min': float(cosine_rows(fw, fw_ref).min()), 'xv_rel': rel_err(xv, xv_ref)}
+    assert min(out['xv_cos_min'], out['xa_cos_min'], out['fw_cos_min']) > 0.999, out
+    return out
+
+
+def audio_golden_case():
+    import os
+    from deeplip_b200.audio_models.tdnn import SpeakerEmbNet
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'audio_small.npz'))
+    wav = synth.speech_like_audio([3, 3, 7], nsamp=16000, seed=1)
+    out = {}
+    for arch in ('etdnn', 'tdnn'):
+        for pool in ('statistic', 'attentive_statistic'):
+            o = synth.audio_opts(arch, pool)
+            net = SpeakerEmbNet(o)
+            net.load_state_dict(synth.make_audio_state_dict(o, seed=1, randomize=True))
+            net = net.to(DEV).eval()
+            with torch.no_grad():
+                f32, b16 = ops.frontend_features(torch.from_numpy(wav).to(DEV))
+                xv, xa = net.embed_ntc(b16)
+            torch.cuda.synchronize()
+            k = '%s_%s' % (arch, pool)
+            out[k] = float(cosine_rows(xv, torch.from_numpy(gold[k + '_xv'])).min())
+            out[k + '_xa'] = float(cosine_rows(xa, torch.from_numpy(gold[k + '_xa'])).min())
+    assert min(out.values()) > 0.999, out
+    return out
+
+
+def fusion_golden_case():
+    import os
+    from deeplip_b200.fusion_models.model_fusion import model_fusion, concat_fusion
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fusion_small.npz'))
+    x = torch.from_numpy(synth.structured_embeddings([1, 1, 2, 3, 4], dim=1024, seed=1)).to(DEV)
+    out = {}
+    for ef in (True, False):
+        m = model_fusion(1024, 512, 62, ef)
+        m.load_state_dict(synth.make_fusion_state_dict(seed=1))
+        m = m.to(DEV).eval()
+        with torch.no_grad():
+            y = m(x)
+        torch.cuda.synchronize()
+        out['linear_%d_cos' % ef] = float(cosine_rows(y, torch.from_numpy(gold['linear_%d' % ef])).min())
+    c = concat_fusion(x[:, :512].contiguous(), x[:, 512:].contiguous())
+    out['concat_abs'] = float((c.cpu() - torch.from_numpy(gold['concat'])).abs().max())
+    assert out['linear_1_cos'] > 0.9999 and out['linear_0_cos'] > 0.9999 and out['concat_abs'] < 1e-5, out
+    return out
+
+
+def make_trial_file(path, kind='grid', seed=1, n_target=4000, n_non=16000):
+    """Synthetic trial list with the shape of database/trial_{grid,lomgrid}_v1.txt:
+    targets first, then non-targets; '<label> <utt1> <utt2>' + trailing TAB (grid) / space (lomgrid)."""
+    rng = np.random.default_rng(seed)
+    spk = [s for s in range(1, 35) if s != 21] if kind == 'grid' else list(range(2, 56, 1))[:36]
+    per = 900 if kind == 'grid' else 100
+    def utt(s, i):
+        return 's%d/u%05d.wav' % (s, i) if kind == 'grid' else 's%d_l_u%05d.wav' % (s, i)
+    tail = '\t' if kind == 'grid' else ' '
+    lines = []
+    for _ in range(n_target):
+        s = spk[rng.integers(len(spk))]
+        a, b = rng.choice(per, 2, replace=False)
+        lines.append('1 %s %s%s' % (utt(s, a), utt(s, b), tail))
+    for _ in range(n_non):
+        s1, s2 = rng.choice(len(spk), 2, replace=False)
+        lines.append('0 %s %s%s' % (utt(spk[s1], rng.integers(per)), utt(spk[s2], rng.integers(per)), tail))
+    with open(path, 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    return path
+
+
+def scoring_full_case(tmpdir, kind='grid'):
+    """Full 20 000-trial list: GPU scores vs the float64 oracle, EER within 0.05 % absolute,
+    identical trial indexing, and size-independent properties (symmetry, self-score = 1)."""
+    import os
+    from deeplip_b200.trials import TrialList
+    from deeplip_b200.fusion_models import utils as U
+    path = make_trial_file(os.path.join(tmpdir, 'trial_%s.txt' % kind), kind)
+    tl = TrialList.from_file(path)
+    labels, pairs = scoring_ref.parse_trials(path)
+    table, enrol, test = scoring_ref.utterance_table(pairs)
+    assert table == tl.utts and np.array_equal(enrol, tl.enrol_idx) and np.array_equal(test, tl.test_idx)
+    assert np.array_equal(labels, tl.labels)
+    emb = synth.structured_embeddings([synth.speaker_of_utt(u) for u in tl.utts], dim=1024, seed=3, within=6.0)
+    s = U.score_trials(emb, tl).cpu().numpy()
+    ref = scoring_ref.cosine_scores_vec(emb, enrol, test)
+    eer_g, thr_g = U.eer_from_scores(tl.labels, s)
+    eer_r, thr_r = scoring_ref.eer_from_scores(labels, list(ref.astype(np.float32).reshape(-1, 1)))
+    # properties: swapping enrol/test gives the same score; scoring an utterance against itself gives 1
+    sw = ops.cosine_score_trials(torch.from_numpy(emb).to(DEV), torch.from_numpy(test).to(DEV),
+                                 torch.from_numpy(enrol).to(DEV)).cpu().numpy()
+    idx = torch.arange(len(tl.utts), dtype=torch.int32, device=DEV)
+    self_s = ops.cosine_score_trials(torch.from_numpy(emb).to(DEV), idx, idx).cpu().numpy()
+    out = {'n_utts': len(tl.utts), 'score_abs': float(np.abs(s - ref).max()), 'eer': float(eer_g),
+           'eer_abs_diff': float(abs(eer_g - eer_r)), 'swap_abs': float(np.abs(s - sw).max()),
+           'self_abs': float(np.abs(self_s - 1).max())}
+    assert out['score_abs'] < 1e-5 and out['eer_abs_diff'] < 5e-4 and out['swap_abs'] == 0.0 and out['self_abs'] < 1e-6, out
+    assert 0.005 < out['eer'] < 0.45, out        # the synthetic list must not be degenerate
+    return out
+
+
+def pipeline_case(B=4, T=8, nsamp=24000, seed=1):
+    """AV extraction end to end (wav + u8 crops -> fused embedding) vs the oracle chain; scores on all
+    pairs within 1e-3; ragged batch == per-utterance runs."""
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    audio, video = build_models(DEV, seed=seed)
+    ex = AVExtractor(audio, video)
+    spk = [1, 1, 2, 3][:B]
+    wav = synth.speech_like_audio(spk, nsamp=nsamp, seed=seed)
+    raw = synth.lip_crops_u8(spk, T=T, seed=seed)
+    got = ex.extract(torch.from_numpy(wav).to(DEV), torch.from_numpy(raw).to(DEV))
+    torch.cuda.synchronize()
+    o = synth.audio_opts('etdnn', 'statistic')
+    sda = synth.make_audio_state_dict(o, seed=seed)
+    sdv = synth.make_video_state_dict(seed=seed)
+    feats = torch.from_numpy(np.stack([frontend_np.extract_feature(w.astype(np.float64)).T for w in wav]))
+    with torch.no_grad():
+        xv, _ = models_ref.speaker_extract_embedding(sda, feats, o)
+        x = torch.stack([models_ref.video_preprocess(torch.from_numpy(r)) for r in raw])
+        em = models_ref.temporal_mean(models_ref.lipreading_features(sdv, x[:, None]))
+        ref = models_ref.concat_fusion(xv, em)
+    out = {'emb_cos_min': float(cosine_rows(got, ref).min())}
+    pairs = [(i, j) for i in range(B) for j in range(B)]
+    e = np.array([p[0] for p in pairs], dtype=np.int32)
+    t = np.array([p[1] for p in pairs], dtype=np.int32)
+    s_got = ops.cosine_score_trials(got, torch.from_numpy(e).to(DEV), torch.from_numpy(t).to(DEV)).cpu().numpy()
+    s_ref = scoring_ref.cosine_scores_vec(ref.numpy(), e, t)
+    out['score_abs'] = float(np.abs(s_got - s_ref).max())
+    # ragged: utterance 1 truncated; batched (padded + lengths) must equal running it alone
+    wl = torch.tensor([nsamp, nsamp - 5000] + [nsamp] * (B - 2), dtype=torch.int32, device=DEV)
+    vl = torch.tensor([T, T - 3] + [T] * (B - 2), dtype=torch.int32, device=DEV)
+    wav2 = wav.copy(); wav2[1, nsamp - 5000:] = 0
+    raw_f = torch.stack([models_ref.video_preprocess(torch.from_numpy(r)) for r in raw])
+    raw_f[1, T - 3:] = 0
+    rag = ex.extract(torch.from_numpy(wav2).to(DEV), raw_f.to(DEV), wl, vl)
+    alone = ex.extract(torch.from_numpy(wav2[1:2, :nsamp - 5000]).to(DEV), raw_f[1:2, :T - 3].contiguous().to(DEV))
+    torch.cuda.synchronize()
+    out['ragged_abs'] = float((rag[1] - alone[0]).abs().max())
+    assert out['emb_cos_min'] > 0.999 and out['score_abs'] < 1e-3 and out['ragged_abs'] < 1e-5, out
+    return out

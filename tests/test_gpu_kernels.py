@@ -1,0 +1,69 @@
+"""-m gpu: kernel-level parity, CUDA path (through the C ABI) vs the CPU oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import gpu_checks as G
+else:
+    G = None
+
+
+@pytest.mark.parametrize('name', ['l1_3x3_64', 'l2_3x3s2_64_128', 'l2_1x1s2_64_128', 'l2_3x3_128', 'l3_3x3s2_128_256',
+                                  'l3_3x3_256', 'l4_3x3s2_256_512', 'l4_3x3_512', 'tdnn_k5_24_512', 'tdnn_k3d3_512',
+                                  'tdnn_k1_512_1500', 'fc_3000_512', 'many_tiles'])
+def test_conv_igemm(name):
+    G.conv_case(**G.CONV_CASES[name])
+
+
+def test_conv_igemm_rejects_bad_shapes():
+    from deeplip_b200 import ops
+    x = torch.zeros(1, 4, 4, 12, device='cuda', dtype=torch.bfloat16)          # ldx not a multiple of 8
+    w = torch.zeros(8, 64, device='cuda', dtype=torch.bfloat16)
+    v = torch.zeros(8, device='cuda')
+    with pytest.raises(RuntimeError, match='ldx'):
+        ops.conv_igemm(x, w, 12, 8, scale=v, shift=v, slope=v)
+
+
+@pytest.mark.parametrize('kw', [dict(B=1, T=3, H=16, W=16), dict(B=2, T=6), dict(B=2, T=5, u8=True),
+                                dict(B=1, T=1, H=32, W=64)])
+def test_stem(kw):
+    G.stem_case(**kw)
+
+
+def test_stat_pool():
+    G.stat_pool_case()
+    G.stat_pool_case(B=3, T=100, C=520, lengths=[100, 37, 2])
+    G.stat_pool_case(B=1, T=2, C=8)
+
+
+def test_attn_stat_pool():
+    G.attn_pool_case()
+
+
+def test_frame_pool_temporal_mean():
+    G.frame_pool_case()
+    G.frame_pool_case(B=1, T=1)
+
+
+def test_fusion_kernels():
+    G.fusion_case()
+
+
+def test_scoring_kernels():
+    G.scoring_case()
+    G.scoring_case(n_utt=10, D=6, n_trials=1)
+
+
+def test_scoring_empty_list():
+    from deeplip_b200 import ops
+    emb = torch.randn(4, 16, device='cuda')
+    e = torch.zeros(0, dtype=torch.int32, device='cuda')
+    assert ops.cosine_score_trials(emb, e, e).numel() == 0
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(feat_type='logfbank', n_feat=60), dict(feat_type='fbank', n_feat=24),
+                                dict(B=3, nsamp=20000, lengths=[20000, 12345, 300]), dict(B=1, nsamp=48000)])
+def test_frontend(kw):
+    G.frontend_case(**kw)

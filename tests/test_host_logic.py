@@ -1,0 +1,155 @@
+"""CPU suite: host-side logic (trial parsing, packing, sharding), the C-ABI library loads and exports
+every symbol include/deeplip_b200.h declares, no compute call succeeds without a GPU, and the
+multi-rank plumbing works on gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_build_and_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from deeplip_b200 import _lib
+    hdr = re.sub(r'/\*.*?\*/', '', open(os.path.join(ROOT, 'include', 'deeplip_b200.h')).read(), flags=re.S)
+    declared = set(re.findall(r'\b(dl_\w+)\s*\(', hdr))
+    assert len(declared) >= 17
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_lib.SIGNATURES) <= declared
+    assert _lib.lib().dl_version() >= 100
+
+
+def test_argument_validation_without_touching_the_gpu():
+    from deeplip_b200 import _lib
+    l = _lib.lib()
+    assert l.dl_stat_pool(None, 1, 1, 8, 8, None, None, None, 0, None) == -1
+    assert b'null' in l.dl_last_error()
+    d = _lib.ConvDesc(1, 4, 4, 12, 12, 8, 1, 1, 1, 1, 0, 0, 1, 1, 8, 8, 1.0)
+    one = ctypes.c_void_p(16)
+    assert l.dl_conv_igemm_bf16(one, one, one, one, one, None, one, None, None, None, ctypes.byref(d), None) == -1
+    assert b'ldx' in l.dl_last_error()
+    assert l.dl_frontend_features(one, None, 1, 48000, 0, 24, 1, None, 64, one, 298, None) == -1
+    assert b'299' in l.dl_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-only behaviour')
+def test_no_cpu_fallback():
+    from deeplip_b200 import ops
+    from deeplip_b200.pipeline import build_models
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ops.znorm_concat(torch.randn(2, 8), torch.randn(2, 8))
+    audio, video = build_models('cpu')
+    with pytest.raises(RuntimeError):
+        video(torch.zeros(1, 1, 2, 88, 88), lengths=[2])
+    with pytest.raises(RuntimeError):
+        audio.extract_embedding(torch.zeros(1, 24, 100))
+
+
+def test_trial_list_parsing_matches_oracle(tmp_path):
+    from deeplip_b200.trials import TrialList
+    from oracle import scoring_ref
+    import gpu_checks as G
+    for kind in ('grid', 'lomgrid'):
+        p = G.make_trial_file(str(tmp_path / ('t_%s.txt' % kind)), kind, n_target=200, n_non=700)
+        tl = TrialList.from_file(p)
+        labels, pairs = scoring_ref.parse_trials(p)
+        table, enrol, test = scoring_ref.utterance_table(pairs)
+        assert table == tl.utts
+        assert np.array_equal(enrol, tl.enrol_idx) and np.array_equal(test, tl.test_idx)
+        assert np.array_equal(labels, tl.labels) and tl.enrol_idx.dtype == np.int32
+    # edge cases: empty file, blank lines, malformed line
+    e = tmp_path / 'empty.txt'
+    e.write_text('\n\n')
+    assert len(TrialList.from_file(str(e))) == 0
+    b = tmp_path / 'bad.txt'
+    b.write_text('2 a b\n')
+    with pytest.raises(ValueError):
+        TrialList.from_file(str(b))
+    ref = '/root/reference/database/trial_grid_v1.txt'
+    if os.path.exists(ref):
+        tl = TrialList.from_file(ref)
+        assert len(tl) == 20000 and len(tl.utts) == 25834 and int(tl.labels.sum()) == 4000
+        sh = [tl.shard(r, 8) for r in range(8)]
+        assert sh[0] == slice(0, 2500) and sh[7] == slice(17500, 20000)
+
+
+def test_packing_layouts():
+    from deeplip_b200 import packing
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = packing.pack_conv_weight(w)
+    assert p.shape == (8, 9 * 64) and p.dtype == torch.bfloat16
+    assert float(p[1, (2 * 3 + 1) * 64 + 2]) == float(w[1, 2, 2, 1])           # K = (r*S+s)*64 + c
+    assert float(p[2:].abs().max()) == 0 and float(p[0, 3]) == 0
+    ws = torch.randn(64, 1, 5, 7, 7)
+    ps = packing.pack_stem_weight(ws)
+    assert ps.shape == (64, 320)
+    assert float(ps[5, 2 * 64 + 3 * 8 + 6]) == float(ws[5, 0, 2, 3, 6].to(torch.bfloat16))
+    assert float(ps[:, 7::8].abs().max()) == 0                                   # kw = 7 padding column
+    s, h = packing.fold_bn(torch.tensor([2.0]), torch.tensor([0.5]), torch.tensor([1.0]), torch.tensor([3.0]),
+                           conv_bias=torch.tensor([0.25]))
+    y = (0.7 + 0.25 - 1.0) / (3.0 + 1e-5) ** 0.5 * 2.0 + 0.5
+    assert abs(float(0.7 * s + h) - y) < 1e-6
+
+
+def test_state_dict_keys_match_the_reference_layout():
+    from deeplip_b200 import synth
+    from deeplip_b200.pipeline import build_models
+    audio, video = build_models('cpu')
+    vk = set(video.state_dict().keys())
+    assert set(synth.make_video_state_dict().keys()) == vk
+    assert 'frontend3D.0.weight' in vk and 'trunk.layer2.0.downsample.0.weight' in vk
+    assert tuple(video.state_dict()['frontend3D.0.weight'].shape) == (64, 1, 5, 7, 7)
+    ak = set(audio.state_dict().keys())
+    assert {'tdnn.0.context_layer.weight', 'tdnn.9.bn.running_var', 'fc1.weight', 'bn2.bias'} <= ak
+    assert tuple(audio.state_dict()['fc1.weight'].shape) == (512, 3000)
+    # DataParallel 'module.' prefix and TCN-head keys of a real checkpoint are tolerated
+    sd = {'module.' + k: v for k, v in synth.make_video_state_dict().items()}
+    sd['module.tcn.tcn_output.weight'] = torch.zeros(500, 768)
+    video.load_state_dict(sd)
+
+
+_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+from deeplip_b200 import dist as D, synth
+from deeplip_b200.trials import TrialList
+from oracle import scoring_ref
+import gpu_checks as G
+rank, world, _ = D.init_from_env('gloo')
+tl = TrialList.from_file(%(trial)r)
+n = len(tl.utts)
+full = torch.from_numpy(synth.structured_embeddings([synth.speaker_of_utt(u) for u in tl.utts], dim=32, seed=4))
+lo, hi = D.shard_range(n, rank, world)
+table = D.all_gather_rows(full[lo:hi].clone(), n, rank, world)            # each rank "extracted" only its shard
+assert torch.equal(table, full), 'all_gather_rows mismatch'
+sl = tl.shard(rank, world)
+loc = torch.from_numpy(scoring_ref.cosine_scores_vec(table.numpy(), tl.enrol_idx[sl], tl.test_idx[sl])).float()
+allsc = D.gather_scores(loc, len(tl), rank, world)
+ref = scoring_ref.cosine_scores_vec(full.numpy(), tl.enrol_idx, tl.test_idx).astype(np.float32)
+assert np.array_equal(allsc.numpy(), ref), 'sharded scores differ from the single-rank scores'
+assert D.max_over_ranks(rank + 1.5, 'cpu') == world + 0.5
+D.barrier(); dist.destroy_process_group()
+sys.stdout.write('rank %%d ok\n' %% rank); sys.stdout.flush()
+'''
+
+
+def test_two_rank_gloo_shard_gather_score(tmp_path):
+    import gpu_checks as G
+    trial = G.make_trial_file(str(tmp_path / 't.txt'), 'lomgrid', n_target=101, n_non=300)
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER % {'root': ROOT, 'trial': trial})
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
+           '127.0.0.1', '--master-port', '29611', str(script)]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=240)
+    text = out.stdout.decode()
+    assert out.returncode == 0, text[-2000:]
+    assert 'rank 0 ok' in text and 'rank 1 ok' in text

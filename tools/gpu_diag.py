@@ -39,6 +39,16 @@ run('attn_pool', G.attn_pool_case)
 run('stem_f32_small', G.stem_case, B=1, T=3, H=16, W=16)
 run('stem_f32', G.stem_case)
 run('stem_u8', G.stem_case, u8=True)
+run('video_model', G.video_model_case)
+run('video_golden', G.video_golden_case)
+run('audio_model_etdnn', G.audio_model_case)
+run('audio_model_tdnn_attn', G.audio_model_case, arch='tdnn', pooling='attentive_statistic')
+run('audio_golden', G.audio_golden_case)
+run('fusion_golden', G.fusion_golden_case)
+import tempfile
+run('scoring_full_grid', G.scoring_full_case, tmpdir=tempfile.mkdtemp(), kind='grid')
+run('scoring_full_lomgrid', G.scoring_full_case, tmpdir=tempfile.mkdtemp(), kind='lomgrid')
+run('pipeline', G.pipeline_case)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'diag.json'), 'w'), indent=1)
 print('PASS' if all(r['ok'] for r in res.values()) else 'FAIL', sum(r['ok'] for r in res.values()), '/', len(res))
