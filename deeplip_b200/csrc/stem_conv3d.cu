@@ -11,6 +11,7 @@
 // bf16 conv rows in a shared-memory ring and max-pool completed rows straight to global memory.
 //
 // Roofline: tensor pipe; algorithmic work 2*Ho*Wo*64*245 flop per frame (DESIGN.md "Kernels").
+#include <type_traits>
 #include "dl_host.cuh"
 #include "dl_ptx.cuh"
 
@@ -21,16 +22,15 @@ constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
 constexpr int kStemThreads = 13 * 32;               // 4 epilogue + 1 MMA + 8 producer warps
 constexpr int kProducerThreads = 256;
-constexpr int kStripMaxElems = 8;                   // prefetched strip elements per producer thread
+constexpr int kStripIters = 3;                      // strip rows per producer thread (rows rsub, rsub+8, rsub+16)
 
 struct StemParams {
   const void* x;
-  int is_u8;
   int B, T, H, W, Hraw, Wraw, dh, dw;
-  float mean, inv_std;
+  float u8_scale, u8_bias;                          // (u/255 - mean)/std == u * u8_scale + u8_bias
   int Ho, Wo, Hp, Wp, Mf, tiles_per_frame;
   int ring_rows;        // power of two
-  int strip_rows, strip_w;
+  int strip_rows, strip_pitch;                      // pitch = W + 12 elements (cols c = ix + 3, c in [0, W+8))
   const float* scale;
   const float* shift;
   const float* slope;
@@ -42,17 +42,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-__device__ __forceinline__ float stem_load_px(const StemParams& p, int b, int t, int iy, int ix) {
-  if (t < 0 || t >= p.T || iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return 0.f;
-  if (p.is_u8) {
-    const uint8_t* src = static_cast<const uint8_t*>(p.x);
-    const float u = (float)__ldg(src + (((size_t)b * p.T + t) * p.Hraw + (iy + p.dh)) * p.Wraw + (ix + p.dw));
-    return (u / 255.0f - p.mean) * p.inv_std;
-  }
-  const float* src = static_cast<const float*>(p.x);
-  return __ldg(src + (((size_t)b * p.T + t) * p.H + iy) * p.W + ix);
-}
-
+template <bool kU8>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -61,8 +51,8 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   uint8_t* smB = smA + kStemAStages * kStemABytes;               // 40 KB
   uint8_t* ring = smB + kStemBBytes;                             // ring_rows x Wo x 128 B
   const int ring_bytes = p.ring_rows * p.Wo * 128;
-  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // 2 x strip_rows x strip_w bf16
-  const int strip_elems = p.strip_rows * p.strip_w;
+  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // 2 x strip_rows x strip_pitch bf16
+  const int strip_elems = p.strip_rows * p.strip_pitch;
   float* chan = reinterpret_cast<float*>(strip + 2 * ((strip_elems + 7) & ~7));   // scale, shift, slope
   uint64_t* bars = reinterpret_cast<uint64_t*>(chan + 192);
   uint64_t* full = bars;                         // [kStemAStages]
@@ -103,62 +93,112 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
 
   if (warp >= 5) {
     // =============================================================== producers: build operand A
+    // Strip fill: lane <-> group of 4 input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global
+    // load), warp <-> strip rows rsub, rsub+8, rsub+16.  Loads for stage s+1 are issued before stage s is
+    // built and are only touched (converted, stored) one iteration later, so their latency is hidden.
     const int pt = threadIdx.x - 5 * 32;          // 0..255
     const int arow = pt & 127;                    // A-tile row (conv pixel within the tile)
     const int half = pt >> 7;                     // chunks [4*half, 4*half+4) of the 8 x 16 B row
+    const int grp = pt & 31;
+    const int rsub = pt >> 5;
+    const int ix0 = 4 * grp - 4;
+    const bool col_ok = ix0 >= 0 && ix0 < p.W;            // whole group inside the image (W % 4 == 0)
+    const bool grp_ok = grp <= p.W / 4 + 2;               // group touches the strip at all
+    const int SP = p.strip_pitch;
+    const int strip_buf = (strip_elems + 7) & ~7;
     int stage = 0;
     uint32_t phase = 0;
     int sbuf = 0;
-    float pre[kStripMaxElems];
+    typename std::conditional<kU8, uint32_t, float4>::type raw[kStripIters];
+    uint32_t vmask = 0;
 
-    // strip prefetch helper state for the NEXT (frame, tile, kt)
-    auto prefetch = [&](int frame, int tile, int kt) {
-      const int b = frame / p.T, t = frame - b * p.T;
-      const int y_first = (tile * 128) / p.Wo;
-      const int iy0 = 2 * y_first - 3;
+    auto issue = [&](int b, int t, int tile, int kt) {
+      const int tt = t + kt - 2;
+      const int iy0 = 2 * ((tile * 128) / p.Wo) - 3;
+      vmask = 0;
+      if (!(col_ok && tt >= 0 && tt < p.T)) return;
 #pragma unroll
-      for (int j = 0; j < kStripMaxElems; ++j) {
-        const int idx = pt + j * kProducerThreads;
-        float v = 0.f;
-        if (idx < strip_elems) {
-          const int r = idx / p.strip_w, c = idx - r * p.strip_w;
-          v = stem_load_px(p, b, t + kt - 2, iy0 + r, c - 3);
+      for (int i = 0; i < kStripIters; ++i) {
+        const int r = rsub + 8 * i;
+        const int iy = iy0 + r;
+        if (r < p.strip_rows && iy >= 0 && iy < p.H) {
+          if constexpr (kU8) {
+            const uint8_t* src = static_cast<const uint8_t*>(p.x) +
+                                 (((size_t)b * p.T + tt) * p.Hraw + (iy + p.dh)) * p.Wraw + (ix0 + p.dw);
+            raw[i] = __ldg(reinterpret_cast<const uint32_t*>(src));
+          } else {
+            const float* src = static_cast<const float*>(p.x) + (((size_t)b * p.T + tt) * p.H + iy) * p.W + ix0;
+            raw[i] = __ldg(reinterpret_cast<const float4*>(src));
+          }
+          vmask |= 1u << i;
         }
-        pre[j] = v;
       }
     };
 
     int frame = blockIdx.x, tile = 0, kt = 0;
-    if (frame < p.frames) prefetch(frame, tile, kt);
+    int fb = frame / p.T, ft = frame - fb * p.T;
+    if (frame < p.frames) issue(fb, ft, 0, 0);
+    int arel = 0;
+    bool avalid = false;
     while (frame < p.frames) {
-      // 1. park the prefetched strip in shared memory (bf16)
-      uint16_t* sb = strip + sbuf * ((strip_elems + 7) & ~7);
+      // 1. park the prefetched strip rows in shared memory (bf16); strip column c = ix + 3
+      uint16_t* sb = strip + sbuf * strip_buf;
+      if (grp_ok) {
 #pragma unroll
-      for (int j = 0; j < kStripMaxElems; ++j) {
-        const int idx = pt + j * kProducerThreads;
-        if (idx < strip_elems) reinterpret_cast<__nv_bfloat16*>(sb)[idx] = __float2bfloat16_rn(pre[j]);
+        for (int i = 0; i < kStripIters; ++i) {
+          const int r = rsub + 8 * i;
+          if (r < p.strip_rows) {
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            if (vmask & (1u << i)) {
+              if constexpr (kU8) {
+                const uint32_t u = raw[i];
+                v0 = fmaf((float)(u & 0xffu), p.u8_scale, p.u8_bias);
+                v1 = fmaf((float)((u >> 8) & 0xffu), p.u8_scale, p.u8_bias);
+                v2 = fmaf((float)((u >> 16) & 0xffu), p.u8_scale, p.u8_bias);
+                v3 = fmaf((float)(u >> 24), p.u8_scale, p.u8_bias);
+              } else {
+                v0 = raw[i].x; v1 = raw[i].y; v2 = raw[i].z; v3 = raw[i].w;
+              }
+            }
+            __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(sb) + r * SP + 4 * grp;   // c = 4*grp - 1 + j
+            if (grp > 0) row[-1] = __float2bfloat16_rn(v0);
+            *reinterpret_cast<uint32_t*>(row) = pack_bf16x2(v1, v2);
+            row[2] = __float2bfloat16_rn(v3);
+          }
+        }
       }
       // 2. start fetching the next stage's strip
-      int nframe = frame, ntile = tile, nkt = kt + 1;
-      if (nkt == 5) { nkt = 0; if (++ntile == p.tiles_per_frame) { ntile = 0; nframe += gridDim.x; } }
-      if (nframe < p.frames) prefetch(nframe, ntile, nkt);
+      int nframe = frame, ntile = tile, nkt = kt + 1, nb = fb, nt = ft;
+      if (nkt == 5) {
+        nkt = 0;
+        if (++ntile == p.tiles_per_frame) {
+          ntile = 0;
+          nframe += gridDim.x;
+          nb = nframe / p.T;
+          nt = nframe - nb * p.T;
+        }
+      }
+      if (nframe < p.frames) issue(nb, nt, ntile, nkt);
       named_bar_sync(1, kProducerThreads);
       // 3. build this thread's half row of A: chunk kh = 8 consecutive input pixels of window row kh
-      mbar_wait(&empty[stage], phase ^ 1);
-      {
+      if (kt == 0) {
         const int m0 = tile * 128;
         const int m = m0 + arow;
         const int y_first = m0 / p.Wo;
-        uint8_t* dst_row = smA + stage * kStemABytes + arow * 128;
-        const bool valid = m < p.Mf;
+        avalid = m < p.Mf;
         const int yy = m / p.Wo, xx = m - yy * p.Wo;
-        const uint32_t* srow = reinterpret_cast<const uint32_t*>(sb) + (2 * (yy - y_first) * p.strip_w + 2 * xx) / 2;
+        arel = (2 * (yy - y_first) * SP + 2 * xx) >> 1;      // uint32 index of strip[(2*(yy-y_first)), 2*xx]
+      }
+      mbar_wait(&empty[stage], phase ^ 1);
+      {
+        uint8_t* dst_row = smA + stage * kStemABytes + arow * 128;
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(sb) + arel;
 #pragma unroll
         for (int cidx = 0; cidx < 4; ++cidx) {
           const int kh = half * 4 + cidx;
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (valid && kh < 7) {
-            const uint32_t* s = srow + (kh * p.strip_w) / 2;
+          if (avalid && kh < 7) {
+            const uint32_t* s = srow + kh * (SP >> 1);
             v.x = s[0]; v.y = s[1]; v.z = s[2]; v.w = s[3];
           }
           *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v;
@@ -169,7 +209,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       if (lane == 0) mbar_arrive(&full[stage]);
       if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
       sbuf ^= 1;
-      frame = nframe; tile = ntile; kt = nkt;
+      frame = nframe; tile = ntile; kt = nkt; fb = nb; ft = nt;
     }
   } else if (warp == 4) {
     // =============================================================== MMA issuer
@@ -303,7 +343,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   using namespace dl;
   DL_CHECK_ARG(x && w_packed && scale && shift && slope && y, "stem: null pointer");
   DL_CHECK_ARG(B > 0 && T > 0, "stem: empty batch");
-  DL_CHECK_ARG(H >= 8 && W >= 8 && H % 4 == 0 && W % 4 == 0 && W <= 128, "stem: H, W must be multiples of 4, W <= 128");
+  DL_CHECK_ARG(H >= 8 && W >= 32 && H % 4 == 0 && W % 4 == 0 && W <= 116, "stem: H, W must be multiples of 4, 32 <= W <= 116");
   if (is_u8) {
     DL_CHECK_ARG(Hraw >= H && Wraw >= W && std != 0.f, "stem: raw crop smaller than the centre crop");
   }
@@ -311,12 +351,16 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   if (st != DL_OK) return st;
 
   StemParams p;
-  p.x = x; p.is_u8 = is_u8;
+  p.x = x;
   p.B = B; p.T = T; p.H = H; p.W = W; p.Hraw = Hraw; p.Wraw = Wraw;
   // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
   p.dh = is_u8 ? (Hraw - H) / 2 : 0;
   p.dw = is_u8 ? (Wraw - W) / 2 : 0;
-  p.mean = mean; p.inv_std = is_u8 ? 1.0f / std : 1.0f;
+  p.u8_scale = is_u8 ? 1.0f / (255.0f * std) : 1.0f;
+  p.u8_bias = is_u8 ? -mean / std : 0.0f;
+  if (is_u8) {
+    DL_CHECK_ARG(Wraw % 4 == 0 && p.dw % 4 == 0, "stem: u8 crops need Wraw and the crop offset to be multiples of 4");
+  }
   p.Ho = H / 2; p.Wo = W / 2; p.Hp = H / 4; p.Wp = W / 4;
   p.Mf = p.Ho * p.Wo;
   p.tiles_per_frame = (p.Mf + 127) / 128;
@@ -325,21 +369,22 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   while (rr < span + 6) rr <<= 1;
   p.ring_rows = rr;
   p.strip_rows = 2 * span + 7;
-  p.strip_w = W + 8;
-  DL_CHECK_ARG(p.strip_rows * p.strip_w <= kStripMaxElems * kProducerThreads, "stem: frame too small/wide for the strip");
+  p.strip_pitch = W + 12;
+  DL_CHECK_ARG(p.strip_rows <= 8 * kStripIters && W / 4 + 2 < 32, "stem: needs 32 <= W <= 116");
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.y = static_cast<uint16_t*>(y);
   p.frames = B * T;
 
-  const int strip_elems = p.strip_rows * p.strip_w;
+  const int strip_elems = p.strip_rows * p.strip_pitch;
   const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
                       2 * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 16 * 8 + 16;
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[is_u8 ? 1 : 0]) {
+    cudaError_t e = is_u8 ? cudaFuncSetAttribute(stem_conv3d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(stem_conv3d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
+    configured[is_u8 ? 1 : 0] = smem;
   }
   CUtensorMap mapW;
   st = make_tiled_2d_bf16(&mapW, w_packed, 64, 320, 320, 64, 64);
@@ -347,6 +392,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.frames < grid) grid = p.frames;
-  stem_conv3d_kernel<<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
+  if (is_u8) stem_conv3d_kernel<true><<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
+  else stem_conv3d_kernel<false><<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
   return check_launch("stem_conv3d_kernel");
 }

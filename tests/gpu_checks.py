@@ -189,7 +189,8 @@ def scoring_case(n_utt=500, D=1024, n_trials=3000, seed=0):
     emb[7] = 0.0                                     # zero row: sklearn divides by 1
     enrol = rng.integers(0, n_utt, n_trials).astype(np.int32)
     test = rng.integers(0, n_utt, n_trials).astype(np.int32)
-    enrol[:3], test[:3] = 7, (7, 8, 9)
+    k = min(3, n_trials)
+    enrol[:k], test[:k] = 7, np.array([7, 8, 9])[:k]
     got = ops.cosine_score_trials(torch.from_numpy(emb).to(DEV), torch.from_numpy(enrol).to(DEV),
                                   torch.from_numpy(test).to(DEV))
     torch.cuda.synchronize()

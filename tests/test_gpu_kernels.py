@@ -26,8 +26,8 @@ def test_conv_igemm_rejects_bad_shapes():
         ops.conv_igemm(x, w, 12, 8, scale=v, shift=v, slope=v)
 
 
-@pytest.mark.parametrize('kw', [dict(B=1, T=3, H=16, W=16), dict(B=2, T=6), dict(B=2, T=5, u8=True),
-                                dict(B=1, T=1, H=32, W=64)])
+@pytest.mark.parametrize('kw', [dict(B=1, T=3, H=32, W=32), dict(B=2, T=6), dict(B=2, T=5, u8=True),
+                                dict(B=1, T=1, H=16, W=64)])
 def test_stem(kw):
     G.stem_case(**kw)
 

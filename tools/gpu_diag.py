@@ -36,7 +36,7 @@ run('frontend_ragged', G.frontend_case, B=3, nsamp=20000, lengths=[20000, 12345,
 for k, kw in G.CONV_CASES.items():
     run('conv_' + k, G.conv_case, **kw)
 run('attn_pool', G.attn_pool_case)
-run('stem_f32_small', G.stem_case, B=1, T=3, H=16, W=16)
+run('stem_f32_small', G.stem_case, B=1, T=3, H=32, W=32)
 run('stem_f32', G.stem_case)
 run('stem_u8', G.stem_case, u8=True)
 run('video_model', G.video_model_case)
