@@ -37,6 +37,8 @@ struct IgemmParams {
   float* yf;
 };
 
+constexpr int kMaxCout = 2048;   // per-channel epilogue parameters staged in shared memory
+
 template <int BLOCK_N>
 struct IgemmCfg {
   static constexpr int BLOCK_M = 128;
@@ -47,19 +49,22 @@ struct IgemmCfg {
   static constexpr int STAGES = (BLOCK_N == 64) ? 8 : (BLOCK_N == 128 ? 6 : 4);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;   // two accumulator stages; 128 / 256 / 512 (power of two)
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
-  static constexpr int THREADS = 192;
+  static constexpr int PARAM_BYTES = 3 * kMaxCout * 4;                          // scale | shift | slope
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int THREADS = 320;                                           // TMA, MMA, 8 epilogue warps
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const IgemmParams p) {
   using Cfg = IgemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // round up inside the shared window (pointer arithmetic on the __shared__ symbol keeps LDS/STS addressing)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* prm = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::PARAM_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -81,12 +86,19 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
       mbar_init(&tfull[0], 1);
       mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], 128);
-      mbar_init(&tempty[1], 128);
+      mbar_init(&tempty[0], 256);
+      mbar_init(&tempty[1], 256);
       fence_mbar_init();
     }
     __syncwarp();
     tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  if (p.y != nullptr) {
+    for (int c = threadIdx.x; c < p.Cout; c += Cfg::THREADS) {
+      prm[c] = p.scale[c];
+      prm[kMaxCout + c] = p.shift[c];
+      prm[2 * kMaxCout + c] = p.slope[c];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -156,7 +168,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
   } else {
-    const int quarter = warp & 3;   // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    // ---------------------------------------------------------------- epilogue: 8 warps.  Warp w reads TMEM lane
+    // quarter (w & 3) -- a hardware restriction -- and every second 32-column chunk (chunk parity = (w-2) >> 2).
+    const int quarter = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const bool has_res = p.residual != nullptr;
+    const bool fast = p.y != nullptr && p.yf == nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -164,74 +181,110 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int n_blk = tile - m_blk * p.num_n_blocks;
       const long long row = (long long)m_blk * Cfg::BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      const int cbase = n_blk * BLOCK_N;
+      // residual of this warp's first chunk: requested BEFORE waiting for the accumulator so the L2 round trip
+      // overlaps the tile's MMAs
+      uint4 res[4];
+      {
+        const int c0 = cbase + chunk0 * 32;
+        if (has_res && row_ok && c0 + 32 <= p.Cout) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) res[g] = __ldg(rp + g);
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < BLOCK_N / 32; ++j) {
-        const int c0 = n_blk * BLOCK_N + j * 32;
+      for (int j = chunk0; j < BLOCK_N / 32; j += 2) {
+        const int c0 = cbase + j * 32;
         if (c0 >= p.Cout) break;
         uint32_t acc_r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + j * 32, acc_r);
-        tmem_ld_wait();
-        if (row_ok) {
+        const bool full_chunk = c0 + 32 <= p.Cout;
+        if (fast && full_chunk) {
+          // ---- straight-line path: parameters from shared memory, residual already in registers
+          uint4 res_cur[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) res_cur[g] = res[g];
+          if (has_res && row_ok && j + 2 < BLOCK_N / 32 && c0 + 96 <= p.Cout) {     // prefetch the next chunk's
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c0 + 64);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) res[g] = __ldg(rp + g);
+          }
+          tmem_ld_wait();
+          const float4* sc = reinterpret_cast<const float4*>(prm + c0);
+          const float4* sh = reinterpret_cast<const float4*>(prm + kMaxCout + c0);
+          const float4* sl = reinterpret_cast<const float4*>(prm + 2 * kMaxCout + c0);
+          uint4 o[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int c = c0 + g * 8;
-            if (c < p.Cout) {
+            float v[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 s4 = sc[2 * g + h], h4 = sh[2 * g + h];
+              v[4 * h + 0] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 0]), s4.x, h4.x);
+              v[4 * h + 1] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 1]), s4.y, h4.y);
+              v[4 * h + 2] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 2]), s4.z, h4.z);
+              v[4 * h + 3] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 3]), s4.w, h4.w);
+            }
+            if (has_res) {
+              const uint4 rr = res_cur[g];
+              v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+              v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 l4 = sl[2 * g + h];
+              v[4 * h + 0] = v[4 * h + 0] > 0.f ? v[4 * h + 0] : v[4 * h + 0] * l4.x;
+              v[4 * h + 1] = v[4 * h + 1] > 0.f ? v[4 * h + 1] : v[4 * h + 1] * l4.y;
+              v[4 * h + 2] = v[4 * h + 2] > 0.f ? v[4 * h + 2] : v[4 * h + 2] * l4.z;
+              v[4 * h + 3] = v[4 * h + 3] > 0.f ? v[4 * h + 3] : v[4 * h + 3] * l4.w;
+            }
+            o[g].x = pack_bf16x2(v[0], v[1]); o[g].y = pack_bf16x2(v[2], v[3]);
+            o[g].z = pack_bf16x2(v[4], v[5]); o[g].w = pack_bf16x2(v[6], v[7]);
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.y + row * p.ldy + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dst[g] = o[g];
+          }
+        } else {
+          // ---- general path: partial chunk and / or fp32 side output (heads, attention logits)
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int c = c0 + g * 8;
+              if (c >= p.Cout) continue;
               float a[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(acc_r[g * 8 + i]);
               if (p.yf != nullptr) {
                 float o[8];
-                if (p.scale2 != nullptr) {
-                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale2 + c));
-                  const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale2 + c + 4));
-                  const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift2 + c));
-                  const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.shift2 + c + 4));
-                  o[0] = fmaf(a[0], s0.x, h0.x); o[1] = fmaf(a[1], s0.y, h0.y);
-                  o[2] = fmaf(a[2], s0.z, h0.z); o[3] = fmaf(a[3], s0.w, h0.w);
-                  o[4] = fmaf(a[4], s1.x, h1.x); o[5] = fmaf(a[5], s1.y, h1.y);
-                  o[6] = fmaf(a[6], s1.z, h1.z); o[7] = fmaf(a[7], s1.w, h1.w);
-                } else {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) o[i] = a[i];
-                }
-                if (p.f32_slope != 1.0f) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) o[i] = o[i] > 0.f ? o[i] : o[i] * p.f32_slope;
+                for (int i = 0; i < 8; ++i) {
+                  o[i] = p.scale2 != nullptr ? fmaf(a[i], __ldg(p.scale2 + c + i), __ldg(p.shift2 + c + i)) : a[i];
+                  o[i] = o[i] > 0.f ? o[i] : o[i] * p.f32_slope;
                 }
                 float4* dst = reinterpret_cast<float4*>(p.yf + row * p.ldf + c);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
                 dst[1] = make_float4(o[4], o[5], o[6], o[7]);
               }
               if (p.y != nullptr) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
-                const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + c));
-                const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
                 float v[8];
-                v[0] = fmaf(a[0], s0.x, h0.x); v[1] = fmaf(a[1], s0.y, h0.y);
-                v[2] = fmaf(a[2], s0.z, h0.z); v[3] = fmaf(a[3], s0.w, h0.w);
-                v[4] = fmaf(a[4], s1.x, h1.x); v[5] = fmaf(a[5], s1.y, h1.y);
-                v[6] = fmaf(a[6], s1.z, h1.z); v[7] = fmaf(a[7], s1.w, h1.w);
-                if (p.residual != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaf(a[i], prm[c + i], prm[kMaxCout + c + i]);
+                if (has_res) {
                   const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c));
-                  v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x);
-                  v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                  v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z);
-                  v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                  v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                  v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
                 }
-                const float4 l0 = __ldg(reinterpret_cast<const float4*>(p.slope + c));
-                const float4 l1 = __ldg(reinterpret_cast<const float4*>(p.slope + c + 4));
-                v[0] = v[0] > 0.f ? v[0] : v[0] * l0.x; v[1] = v[1] > 0.f ? v[1] : v[1] * l0.y;
-                v[2] = v[2] > 0.f ? v[2] : v[2] * l0.z; v[3] = v[3] > 0.f ? v[3] : v[3] * l0.w;
-                v[4] = v[4] > 0.f ? v[4] : v[4] * l1.x; v[5] = v[5] > 0.f ? v[5] : v[5] * l1.y;
-                v[6] = v[6] > 0.f ? v[6] : v[6] * l1.z; v[7] = v[7] > 0.f ? v[7] : v[7] * l1.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * prm[2 * kMaxCout + c + i];
                 uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]);
-                o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]);
-                o.w = pack_bf16x2(v[6], v[7]);
+                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
                 *reinterpret_cast<uint4*>(p.y + row * p.ldy + c) = o;
               }
             }
@@ -285,7 +338,7 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   DL_CHECK_ARG((scale2 == nullptr) == (shift2 == nullptr), "conv_igemm: scale2/shift2 must come together");
   DL_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->Cout > 0, "conv_igemm: empty shape");
   DL_CHECK_ARG(d->ldx % 8 == 0 && d->ldx >= d->C, "conv_igemm: ldx must be >= C and a multiple of 8");
-  DL_CHECK_ARG(d->Cout % 8 == 0, "conv_igemm: Cout must be a multiple of 8 (pad the packed weights)");
+  DL_CHECK_ARG(d->Cout % 8 == 0 && d->Cout <= kMaxCout, "conv_igemm: Cout must be a multiple of 8, at most %d", kMaxCout);
   DL_CHECK_ARG(!y || (d->ldy % 8 == 0 && d->ldy >= d->Cout), "conv_igemm: ldy must be >= Cout, multiple of 8");
   DL_CHECK_ARG(!y_f32 || (d->ldf % 4 == 0 && d->ldf >= d->Cout), "conv_igemm: ldf must be >= Cout, multiple of 4");
   DL_CHECK_ARG(d->R >= 1 && d->S >= 1 && d->stride_h >= 1 && d->stride_w >= 1 && d->dil_h >= 1 && d->dil_w >= 1 &&

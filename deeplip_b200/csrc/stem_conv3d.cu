@@ -22,7 +22,7 @@ constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
 constexpr int kStemThreads = 13 * 32;               // 4 epilogue + 1 MMA + 8 producer warps
 constexpr int kProducerThreads = 256;
-constexpr int kStripIters = 3;                      // strip rows per producer thread (rows rsub, rsub+8, rsub+16)
+constexpr int kStripItersMax = 3;                   // strip rows per producer thread (rows rsub, rsub+8, rsub+16)
 
 struct StemParams {
   const void* x;
@@ -42,11 +42,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <bool kU8>
+template <bool kU8, int kIters>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // round up inside the shared window (pointer arithmetic on the __shared__ symbol keeps LDS/STS addressing)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smA = smem;                                           // kStemAStages x 16 KB
   uint8_t* smB = smA + kStemAStages * kStemABytes;               // 40 KB
   uint8_t* ring = smB + kStemBBytes;                             // ring_rows x Wo x 128 B
@@ -61,6 +62,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   uint64_t* tempty = tfull + 2;                  // [2]
   uint64_t* wbar = tempty + 2;                   // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  int* tile_iy0 = reinterpret_cast<int*>(wbar + 2);   // [tiles_per_frame <= 64] first input row of a tile's strip
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,6 +71,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     const int c = i & 63;
     chan[i] = i < 64 ? p.scale[c] : (i < 128 ? p.shift[c] : p.slope[c]);
   }
+  for (int i = threadIdx.x; i < p.tiles_per_frame; i += kStemThreads) tile_iy0[i] = 2 * ((i * 128) / p.Wo) - 3;
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < kStemAStages; ++s) {
@@ -94,7 +97,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   if (warp >= 5) {
     // =============================================================== producers: build operand A
     // Strip fill: lane <-> group of 4 input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global
-    // load), warp <-> strip rows rsub, rsub+8, rsub+16.  Loads for stage s+1 are issued before stage s is
+    // load), warp <-> strip rows rsub, rsub+8(, rsub+16).  Loads for stage s+1 are issued before stage s is
     // built and are only touched (converted, stored) one iteration later, so their latency is hidden.
     const int pt = threadIdx.x - 5 * 32;          // 0..255
     const int arow = pt & 127;                    // A-tile row (conv pixel within the tile)
@@ -106,48 +109,56 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     const bool grp_ok = grp <= p.W / 4 + 2;               // group touches the strip at all
     const int SP = p.strip_pitch;
     const int strip_buf = (strip_elems + 7) & ~7;
+    const size_t frame_elems = (size_t)p.Hraw * p.Wraw;
+    const int col_off = (kU8 ? p.dh * p.Wraw + p.dw : 0) + ix0;
     int stage = 0;
     uint32_t phase = 0;
     int sbuf = 0;
-    typename std::conditional<kU8, uint32_t, float4>::type raw[kStripIters];
+    typename std::conditional<kU8, uint32_t, float4>::type raw[kIters];
     uint32_t vmask = 0;
 
-    auto issue = [&](int b, int t, int tile, int kt) {
+    // request the strip rows of (frame fidx = b*T + t, temporal tap kt, tile)
+    auto issue = [&](int fidx, int t, int tile, int kt) {
       const int tt = t + kt - 2;
-      const int iy0 = 2 * ((tile * 128) / p.Wo) - 3;
       vmask = 0;
       if (!(col_ok && tt >= 0 && tt < p.T)) return;
+      const int iy0 = tile_iy0[tile];
+      if constexpr (kU8) {
+        const uint8_t* src = static_cast<const uint8_t*>(p.x) + (size_t)(fidx + kt - 2) * frame_elems + col_off;
 #pragma unroll
-      for (int i = 0; i < kStripIters; ++i) {
-        const int r = rsub + 8 * i;
-        const int iy = iy0 + r;
-        if (r < p.strip_rows && iy >= 0 && iy < p.H) {
-          if constexpr (kU8) {
-            const uint8_t* src = static_cast<const uint8_t*>(p.x) +
-                                 (((size_t)b * p.T + tt) * p.Hraw + (iy + p.dh)) * p.Wraw + (ix0 + p.dw);
-            raw[i] = __ldg(reinterpret_cast<const uint32_t*>(src));
-          } else {
-            const float* src = static_cast<const float*>(p.x) + (((size_t)b * p.T + tt) * p.H + iy) * p.W + ix0;
-            raw[i] = __ldg(reinterpret_cast<const float4*>(src));
+        for (int i = 0; i < kIters; ++i) {
+          const int iy = iy0 + rsub + 8 * i;
+          if (rsub + 8 * i < p.strip_rows && (unsigned)iy < (unsigned)p.H) {
+            raw[i] = __ldg(reinterpret_cast<const uint32_t*>(src + iy * p.Wraw));
+            vmask |= 1u << i;
           }
-          vmask |= 1u << i;
+        }
+      } else {
+        const float* src = static_cast<const float*>(p.x) + (size_t)(fidx + kt - 2) * frame_elems + col_off;
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) {
+          const int iy = iy0 + rsub + 8 * i;
+          if (rsub + 8 * i < p.strip_rows && (unsigned)iy < (unsigned)p.H) {
+            raw[i] = __ldg(reinterpret_cast<const float4*>(src + iy * p.Wraw));
+            vmask |= 1u << i;
+          }
         }
       }
     };
 
     int frame = blockIdx.x, tile = 0, kt = 0;
-    int fb = frame / p.T, ft = frame - fb * p.T;
-    if (frame < p.frames) issue(fb, ft, 0, 0);
-    int arel = 0;
+    int ft = frame % p.T;
+    if (frame < p.frames) issue(frame, ft, 0, 0);
+    const uint8_t* dst_swz = nullptr;             // this thread's A row inside a stage (+ stage offset later)
+    uint32_t arel = 0;
     bool avalid = false;
     while (frame < p.frames) {
       // 1. park the prefetched strip rows in shared memory (bf16); strip column c = ix + 3
-      uint16_t* sb = strip + sbuf * strip_buf;
+      __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip) + sbuf * strip_buf;
       if (grp_ok) {
 #pragma unroll
-        for (int i = 0; i < kStripIters; ++i) {
-          const int r = rsub + 8 * i;
-          if (r < p.strip_rows) {
+        for (int i = 0; i < kIters; ++i) {
+          if (rsub + 8 * i < p.strip_rows) {
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
             if (vmask & (1u << i)) {
               if constexpr (kU8) {
@@ -160,7 +171,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
                 v0 = raw[i].x; v1 = raw[i].y; v2 = raw[i].z; v3 = raw[i].w;
               }
             }
-            __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(sb) + r * SP + 4 * grp;   // c = 4*grp - 1 + j
+            __nv_bfloat16* row = sb + (rsub + 8 * i) * SP + 4 * grp;   // c = 4*grp - 1 + j
             if (grp > 0) row[-1] = __float2bfloat16_rn(v0);
             *reinterpret_cast<uint32_t*>(row) = pack_bf16x2(v1, v2);
             row[2] = __float2bfloat16_rn(v3);
@@ -168,49 +179,49 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
         }
       }
       // 2. start fetching the next stage's strip
-      int nframe = frame, ntile = tile, nkt = kt + 1, nb = fb, nt = ft;
+      int nframe = frame, ntile = tile, nkt = kt + 1, nt = ft;
       if (nkt == 5) {
         nkt = 0;
         if (++ntile == p.tiles_per_frame) {
           ntile = 0;
           nframe += gridDim.x;
-          nb = nframe / p.T;
-          nt = nframe - nb * p.T;
+          nt = nframe % p.T;
         }
       }
-      if (nframe < p.frames) issue(nb, nt, ntile, nkt);
+      if (nframe < p.frames) issue(nframe, nt, ntile, nkt);
       named_bar_sync(1, kProducerThreads);
       // 3. build this thread's half row of A: chunk kh = 8 consecutive input pixels of window row kh
       if (kt == 0) {
-        const int m0 = tile * 128;
-        const int m = m0 + arow;
-        const int y_first = m0 / p.Wo;
+        const int m = tile * 128 + arow;
         avalid = m < p.Mf;
         const int yy = m / p.Wo, xx = m - yy * p.Wo;
-        arel = (2 * (yy - y_first) * SP + 2 * xx) >> 1;      // uint32 index of strip[(2*(yy-y_first)), 2*xx]
+        arel = (uint32_t)((2 * yy - 3 - tile_iy0[tile]) * SP + 2 * xx) >> 1;   // uint32 index into the strip
       }
       mbar_wait(&empty[stage], phase ^ 1);
       {
         uint8_t* dst_row = smA + stage * kStemABytes + arow * 128;
-        const uint32_t* srow = reinterpret_cast<const uint32_t*>(sb) + arel;
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(sb) + arel + half * 4 * (SP >> 1);
+        uint4 v[4];
 #pragma unroll
         for (int cidx = 0; cidx < 4; ++cidx) {
-          const int kh = half * 4 + cidx;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (avalid && kh < 7) {
-            const uint32_t* s = srow + kh * (SP >> 1);
-            v.x = s[0]; v.y = s[1]; v.z = s[2]; v.w = s[3];
+          v[cidx] = make_uint4(0u, 0u, 0u, 0u);
+          if (avalid && (half == 0 || cidx < 3)) {
+            const uint32_t* sp = srow + cidx * (SP >> 1);
+            v[cidx].x = sp[0]; v[cidx].y = sp[1]; v[cidx].z = sp[2]; v[cidx].w = sp[3];
           }
-          *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v;
         }
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx)
+          *reinterpret_cast<uint4*>(dst_row + (((half * 4 + cidx) ^ (arow & 7)) << 4)) = v[cidx];
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[stage]);
       if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
       sbuf ^= 1;
-      frame = nframe; tile = ntile; kt = nkt; fb = nb; ft = nt;
+      frame = nframe; tile = ntile; kt = nkt; ft = nt;
     }
+    (void)dst_swz;
   } else if (warp == 4) {
     // =============================================================== MMA issuer
     if (lane == 0) {
@@ -370,29 +381,28 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   p.ring_rows = rr;
   p.strip_rows = 2 * span + 7;
   p.strip_pitch = W + 12;
-  DL_CHECK_ARG(p.strip_rows <= 8 * kStripIters && W / 4 + 2 < 32, "stem: needs 32 <= W <= 116");
+  DL_CHECK_ARG(p.strip_rows <= 8 * kStripItersMax && W / 4 + 2 < 32, "stem: needs 32 <= W <= 116");
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.y = static_cast<uint16_t*>(y);
   p.frames = B * T;
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
-                      2 * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 16 * 8 + 16;
+                      2 * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 16 * 8 + 16 + 64 * 4;
+  DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[is_u8 ? 1 : 0]) {
-    cudaError_t e = is_u8 ? cudaFuncSetAttribute(stem_conv3d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(stem_conv3d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
-    configured[is_u8 ? 1 : 0] = smem;
-  }
   CUtensorMap mapW;
   st = make_tiled_2d_bf16(&mapW, w_packed, 64, 320, 320, 64, 64);
   if (st != DL_OK) return st;
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.frames < grid) grid = p.frames;
-  if (is_u8) stem_conv3d_kernel<true><<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
-  else stem_conv3d_kernel<false><<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
+  const int iters = p.strip_rows <= 16 ? 2 : 3;
+  void (*kern)(const CUtensorMap, const StemParams) =
+      is_u8 ? (iters == 2 ? stem_conv3d_kernel<true, 2> : stem_conv3d_kernel<true, 3>)
+            : (iters == 2 ? stem_conv3d_kernel<false, 2> : stem_conv3d_kernel<false, 3>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
+  kern<<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
   return check_launch("stem_conv3d_kernel");
 }
