@@ -471,8 +471,8 @@ extern "C" int dl_nct_to_ntc_bf16(const float* x, int B, int C, int T, void* y, 
 
 extern "C" int dl_cosine_score_trials(const float* emb, int n_utt, int D, const int32_t* enrol, const int32_t* test,
                                       int n_trials, float* scores, void* stream) {
-  DL_CHECK_ARG(emb && enrol && test && scores && n_utt > 0 && D > 0, "cosine_score: bad argument");
   if (n_trials == 0) return DL_OK;
+  DL_CHECK_ARG(emb && enrol && test && scores && n_utt > 0 && D > 0, "cosine_score: bad argument");
   DL_CHECK_ARG(n_trials > 0, "cosine_score: negative trial count");
   cosine_trials_kernel<<<(n_trials + 7) / 8, 256, 0, (cudaStream_t)stream>>>(emb, n_utt, D, enrol, test, n_trials,
                                                                             scores);
@@ -482,8 +482,8 @@ extern "C" int dl_cosine_score_trials(const float* emb, int n_utt, int D, const 
 extern "C" int dl_score_fusion_trials(const float* emb_a, int Da, const float* emb_v, int Dv, int n_utt,
                                       const int32_t* enrol, const int32_t* test, int n_trials, float* scores,
                                       void* stream) {
-  DL_CHECK_ARG(emb_a && emb_v && enrol && test && scores && n_utt > 0 && Da > 0 && Dv > 0, "score_fusion: bad argument");
   if (n_trials == 0) return DL_OK;
+  DL_CHECK_ARG(emb_a && emb_v && enrol && test && scores && n_utt > 0 && Da > 0 && Dv > 0, "score_fusion: bad argument");
   DL_CHECK_ARG(n_trials > 0, "score_fusion: negative trial count");
   score_fusion_kernel<<<(n_trials + 7) / 8, 256, 0, (cudaStream_t)stream>>>(emb_a, Da, emb_v, Dv, n_utt, enrol, test,
                                                                            n_trials, scores);
@@ -492,8 +492,8 @@ extern "C" int dl_score_fusion_trials(const float* emb_a, int Da, const float* e
 
 extern "C" int dl_gather_scores(const float* S, int ld, const int32_t* rows, const int32_t* cols, int n_trials,
                                 float* scores, void* stream) {
-  DL_CHECK_ARG(S && rows && cols && scores && ld > 0, "gather_scores: bad argument");
   if (n_trials == 0) return DL_OK;
+  DL_CHECK_ARG(S && rows && cols && scores && ld > 0, "gather_scores: bad argument");
   gather_scores_kernel<<<(n_trials + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, ld, rows, cols, n_trials, scores);
   return check_launch("gather_scores_kernel");
 }

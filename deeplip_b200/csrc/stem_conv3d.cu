@@ -20,9 +20,8 @@ namespace dl {
 constexpr int kStemAStages = 4;
 constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 64 K (bf16)
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
-constexpr int kStemThreads = 13 * 32;               // 4 epilogue + 1 MMA + 8 producer warps
-constexpr int kProducerThreads = 256;
-constexpr int kStripItersMax = 3;                   // strip rows per producer thread (rows rsub, rsub+8, rsub+16)
+constexpr int kStemThreads = 15 * 32;               // 4 epilogue + 1 MMA + 2 loader + 8 builder warps
+constexpr int kStripRowsMax = 24;                   // loader warp lw fills strip rows lw, lw+2, ...
 
 struct StemParams {
   const void* x;
@@ -36,6 +35,18 @@ struct StemParams {
   const float* slope;
   uint16_t* y;
   int frames;
+};
+
+// (frame, tile, temporal tap) of a pipeline stage; every role walks the same sequence.
+struct StemCursor {
+  int frame, tile, kt, ft, stride, tiles;
+  __device__ StemCursor(int first, int stride_, int tiles_) : frame(first), tile(0), kt(0), ft(0), stride(stride_), tiles(tiles_) {}
+  __device__ __forceinline__ void advance() {
+    if (++kt == 5) {
+      kt = 0;
+      if (++tile == tiles) { tile = 0; frame += stride; }
+    }
+  }
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -52,17 +63,20 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   uint8_t* smB = smA + kStemAStages * kStemABytes;               // 40 KB
   uint8_t* ring = smB + kStemBBytes;                             // ring_rows x Wo x 128 B
   const int ring_bytes = p.ring_rows * p.Wo * 128;
-  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // 2 x strip_rows x strip_pitch bf16
+  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // 4 x strip_rows x strip_pitch bf16
   const int strip_elems = p.strip_rows * p.strip_pitch;
-  float* chan = reinterpret_cast<float*>(strip + 2 * ((strip_elems + 7) & ~7));   // scale, shift, slope
+  const int strip_buf = (strip_elems + 7) & ~7;
+  float* chan = reinterpret_cast<float*>(strip + 4 * strip_buf);   // scale, shift, slope
   uint64_t* bars = reinterpret_cast<uint64_t*>(chan + 192);
   uint64_t* full = bars;                         // [kStemAStages]
   uint64_t* empty = bars + kStemAStages;         // [kStemAStages]
   uint64_t* tfull = bars + 2 * kStemAStages;     // [2]
   uint64_t* tempty = tfull + 2;                  // [2]
   uint64_t* wbar = tempty + 2;                   // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-  int* tile_iy0 = reinterpret_cast<int*>(wbar + 2);   // [tiles_per_frame <= 64] first input row of a tile's strip
+  uint64_t* sfull = wbar + 1;                    // [4] strip slot filled (2 loader warps)
+  uint64_t* sempty = sfull + 4;                  // [4] strip slot consumed (4 builder warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 4);
+  int* tile_iy0 = reinterpret_cast<int*>(sempty + 5);   // [tiles_per_frame <= 64] first input row of a tile's strip
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,8 +89,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < kStemAStages; ++s) {
-        mbar_init(&full[s], 8);      // one elected arrive per producer warp
+        mbar_init(&full[s], 4);      // one elected arrive per builder warp of the owning group
         mbar_init(&empty[s], 1);
+        mbar_init(&sfull[s], 2);
+        mbar_init(&sempty[s], 4);
       }
       mbar_init(&tfull[0], 1);
       mbar_init(&tfull[1], 1);
@@ -94,71 +110,104 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 5) {
-    // =============================================================== producers: build operand A
-    // Strip fill: lane <-> group of 4 input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global
-    // load), warp <-> strip rows rsub, rsub+8(, rsub+16).  Loads for stage s+1 are issued before stage s is
-    // built and are only touched (converted, stored) one iteration later, so their latency is hidden.
-    const int pt = threadIdx.x - 5 * 32;          // 0..255
-    const int arow = pt & 127;                    // A-tile row (conv pixel within the tile)
-    const int half = pt >> 7;                     // chunks [4*half, 4*half+4) of the 8 x 16 B row
-    const int grp = pt & 31;
-    const int rsub = pt >> 5;
+  if (warp >= 7) {
+    // =============================================================== builders: operand A from the staged strip
+    // Two groups of 4 warps alternate pipeline stages (group g owns stages s = g, g+2, ...), so two A tiles are
+    // in flight; thread <-> A-tile row (conv pixel), 8 chunks of 16 B: chunk kh = 8 consecutive input pixels of
+    // window row kh (chunk 7 = zero padding of K).
+    const int bt = threadIdx.x - 7 * 32;          // 0..255
+    const int group = bt >> 7;
+    const int arow = bt & 127;
+    const int SP = p.strip_pitch;
+    StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
+    if (group == 1) cur.advance();
+    int cached_tile = -1, cached_frame = -1;
+    uint32_t arel = 0;
+    bool avalid = false;
+    for (uint32_t s = group; cur.frame < p.frames; s += 2) {
+      const int slot = s & 3;
+      const uint32_t ph = (s >> 2) & 1;
+      if (cur.tile != cached_tile || cur.frame != cached_frame) {
+        cached_tile = cur.tile; cached_frame = cur.frame;
+        const int m = cur.tile * 128 + arow;
+        avalid = m < p.Mf;
+        const int yy = m / p.Wo, xx = m - yy * p.Wo;
+        arel = (uint32_t)((2 * yy - 3 - tile_iy0[cur.tile]) * SP + 2 * xx) >> 1;   // uint32 index into the strip
+      }
+      const uint32_t* srow = reinterpret_cast<const uint32_t*>(strip + slot * strip_buf) + arel;
+      mbar_wait(&sfull[slot], ph);
+      uint4 v[8];
+#pragma unroll
+      for (int kh = 0; kh < 7; ++kh) {
+        v[kh] = make_uint4(0u, 0u, 0u, 0u);
+        if (avalid) {
+          const uint32_t* sp = srow + kh * (SP >> 1);
+          v[kh].x = sp[0]; v[kh].y = sp[1]; v[kh].z = sp[2]; v[kh].w = sp[3];
+        }
+      }
+      v[7] = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty[slot]);          // strip slot consumed (values are in registers)
+      mbar_wait(&empty[slot], ph ^ 1);
+      uint8_t* dst_row = smA + slot * kStemABytes + arow * 128;
+#pragma unroll
+      for (int kh = 0; kh < 8; ++kh) *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v[kh];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[slot]);
+      cur.advance();
+      cur.advance();
+    }
+  } else if (warp >= 5) {
+    // =============================================================== loaders: global -> bf16 strip ring
+    // lane <-> group of 4 input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global load),
+    // warp lw <-> strip rows lw, lw+2, ...  Loads of stage s+1 are issued before stage s is converted, and the
+    // loaders run up to 4 stages ahead of the builders, so global latency is off the critical path.
+    const int lw = warp - 5;
+    const int grp = lane;
     const int ix0 = 4 * grp - 4;
     const bool col_ok = ix0 >= 0 && ix0 < p.W;            // whole group inside the image (W % 4 == 0)
     const bool grp_ok = grp <= p.W / 4 + 2;               // group touches the strip at all
     const int SP = p.strip_pitch;
-    const int strip_buf = (strip_elems + 7) & ~7;
     const size_t frame_elems = (size_t)p.Hraw * p.Wraw;
     const int col_off = (kU8 ? p.dh * p.Wraw + p.dw : 0) + ix0;
-    int stage = 0;
-    uint32_t phase = 0;
-    int sbuf = 0;
     typename std::conditional<kU8, uint32_t, float4>::type raw[kIters];
     uint32_t vmask = 0;
 
-    // request the strip rows of (frame fidx = b*T + t, temporal tap kt, tile)
-    auto issue = [&](int fidx, int t, int tile, int kt) {
-      const int tt = t + kt - 2;
+    auto issue = [&](const StemCursor& c) {
+      const int tt = c.ft + c.kt - 2;
       vmask = 0;
       if (!(col_ok && tt >= 0 && tt < p.T)) return;
-      const int iy0 = tile_iy0[tile];
-      if constexpr (kU8) {
-        const uint8_t* src = static_cast<const uint8_t*>(p.x) + (size_t)(fidx + kt - 2) * frame_elems + col_off;
+      const int iy0 = tile_iy0[c.tile];
+      const size_t fo = (size_t)(c.frame + c.kt - 2) * frame_elems + col_off;
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-          const int iy = iy0 + rsub + 8 * i;
-          if (rsub + 8 * i < p.strip_rows && (unsigned)iy < (unsigned)p.H) {
-            raw[i] = __ldg(reinterpret_cast<const uint32_t*>(src + iy * p.Wraw));
-            vmask |= 1u << i;
+      for (int i = 0; i < kIters; ++i) {
+        const int r = lw + 2 * i;
+        const int iy = iy0 + r;
+        if (r < p.strip_rows && (unsigned)iy < (unsigned)p.H) {
+          if constexpr (kU8) {
+            raw[i] = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.x) + fo + iy * p.Wraw));
+          } else {
+            raw[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + fo + iy * p.Wraw));
           }
-        }
-      } else {
-        const float* src = static_cast<const float*>(p.x) + (size_t)(fidx + kt - 2) * frame_elems + col_off;
-#pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-          const int iy = iy0 + rsub + 8 * i;
-          if (rsub + 8 * i < p.strip_rows && (unsigned)iy < (unsigned)p.H) {
-            raw[i] = __ldg(reinterpret_cast<const float4*>(src + iy * p.Wraw));
-            vmask |= 1u << i;
-          }
+          vmask |= 1u << i;
         }
       }
     };
 
-    int frame = blockIdx.x, tile = 0, kt = 0;
-    int ft = frame % p.T;
-    if (frame < p.frames) issue(frame, ft, 0, 0);
-    const uint8_t* dst_swz = nullptr;             // this thread's A row inside a stage (+ stage offset later)
-    uint32_t arel = 0;
-    bool avalid = false;
-    while (frame < p.frames) {
-      // 1. park the prefetched strip rows in shared memory (bf16); strip column c = ix + 3
-      __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip) + sbuf * strip_buf;
+    StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
+    cur.ft = cur.frame % p.T;
+    if (cur.frame < p.frames) issue(cur);
+    for (uint32_t s = 0; cur.frame < p.frames; ++s) {
+      const int slot = s & 3;
+      const uint32_t ph = (s >> 2) & 1;
+      mbar_wait(&sempty[slot], ph ^ 1);
+      __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip + slot * strip_buf);
       if (grp_ok) {
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
-          if (rsub + 8 * i < p.strip_rows) {
+          const int r = lw + 2 * i;
+          if (r < p.strip_rows) {
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
             if (vmask & (1u << i)) {
               if constexpr (kU8) {
@@ -171,57 +220,19 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
                 v0 = raw[i].x; v1 = raw[i].y; v2 = raw[i].z; v3 = raw[i].w;
               }
             }
-            __nv_bfloat16* row = sb + (rsub + 8 * i) * SP + 4 * grp;   // c = 4*grp - 1 + j
+            __nv_bfloat16* row = sb + r * SP + 4 * grp;   // strip column c = ix + 3 = 4*grp - 1 + j
             if (grp > 0) row[-1] = __float2bfloat16_rn(v0);
             *reinterpret_cast<uint32_t*>(row) = pack_bf16x2(v1, v2);
             row[2] = __float2bfloat16_rn(v3);
           }
         }
       }
-      // 2. start fetching the next stage's strip
-      int nframe = frame, ntile = tile, nkt = kt + 1, nt = ft;
-      if (nkt == 5) {
-        nkt = 0;
-        if (++ntile == p.tiles_per_frame) {
-          ntile = 0;
-          nframe += gridDim.x;
-          nt = nframe % p.T;
-        }
-      }
-      if (nframe < p.frames) issue(nframe, nt, ntile, nkt);
-      named_bar_sync(1, kProducerThreads);
-      // 3. build this thread's half row of A: chunk kh = 8 consecutive input pixels of window row kh
-      if (kt == 0) {
-        const int m = tile * 128 + arow;
-        avalid = m < p.Mf;
-        const int yy = m / p.Wo, xx = m - yy * p.Wo;
-        arel = (uint32_t)((2 * yy - 3 - tile_iy0[tile]) * SP + 2 * xx) >> 1;   // uint32 index into the strip
-      }
-      mbar_wait(&empty[stage], phase ^ 1);
-      {
-        uint8_t* dst_row = smA + stage * kStemABytes + arow * 128;
-        const uint32_t* srow = reinterpret_cast<const uint32_t*>(sb) + arel + half * 4 * (SP >> 1);
-        uint4 v[4];
-#pragma unroll
-        for (int cidx = 0; cidx < 4; ++cidx) {
-          v[cidx] = make_uint4(0u, 0u, 0u, 0u);
-          if (avalid && (half == 0 || cidx < 3)) {
-            const uint32_t* sp = srow + cidx * (SP >> 1);
-            v[cidx].x = sp[0]; v[cidx].y = sp[1]; v[cidx].z = sp[2]; v[cidx].w = sp[3];
-          }
-        }
-#pragma unroll
-        for (int cidx = 0; cidx < 4; ++cidx)
-          *reinterpret_cast<uint4*>(dst_row + (((half * 4 + cidx) ^ (arow & 7)) << 4)) = v[cidx];
-      }
-      fence_proxy_async_smem();
+      cur.advance();
+      if (cur.kt == 0 && cur.tile == 0) cur.ft = cur.frame % p.T;
+      if (cur.frame < p.frames) issue(cur);                 // next stage's loads fly while builders work
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
-      if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
-      sbuf ^= 1;
-      frame = nframe; tile = ntile; kt = nkt; ft = nt;
+      if (lane == 0) mbar_arrive(&sfull[slot]);
     }
-    (void)dst_swz;
   } else if (warp == 4) {
     // =============================================================== MMA issuer
     if (lane == 0) {
@@ -381,14 +392,14 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   p.ring_rows = rr;
   p.strip_rows = 2 * span + 7;
   p.strip_pitch = W + 12;
-  DL_CHECK_ARG(p.strip_rows <= 8 * kStripItersMax && W / 4 + 2 < 32, "stem: needs 32 <= W <= 116");
+  DL_CHECK_ARG(p.strip_rows <= kStripRowsMax && W / 4 + 2 < 32, "stem: needs 32 <= W <= 116");
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.y = static_cast<uint16_t*>(y);
   p.frames = B * T;
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
-                      2 * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 16 * 8 + 16 + 64 * 4;
+                      4 * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 24 * 8 + 16 + 64 * 4;
   DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
   CUtensorMap mapW;
@@ -397,10 +408,10 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.frames < grid) grid = p.frames;
-  const int iters = p.strip_rows <= 16 ? 2 : 3;
+  const bool small = p.strip_rows <= 14;      // rows per loader warp: 7 (GRID 88x88) or 12
   void (*kern)(const CUtensorMap, const StemParams) =
-      is_u8 ? (iters == 2 ? stem_conv3d_kernel<true, 2> : stem_conv3d_kernel<true, 3>)
-            : (iters == 2 ? stem_conv3d_kernel<false, 2> : stem_conv3d_kernel<false, 3>);
+      is_u8 ? (small ? stem_conv3d_kernel<true, 7> : stem_conv3d_kernel<true, 12>)
+            : (small ? stem_conv3d_kernel<false, 7> : stem_conv3d_kernel<false, 12>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
   kern<<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
