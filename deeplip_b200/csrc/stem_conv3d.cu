@@ -20,7 +20,8 @@ namespace dl {
 constexpr int kStemAStages = 4;
 constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 64 K (bf16)
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
-constexpr int kStemThreads = 15 * 32;               // 4 epilogue + 1 MMA + 2 loader + 8 builder warps
+constexpr int kStemThreads = 16 * 32;               // 4 epilogue + 1 MMA + 3 loader + 8 builder warps
+constexpr int kLoaders = 3;                         // loader warps == strip ring slots
 constexpr int kStripRowsMax = 24;                   // loader warp lw fills strip rows lw, lw+2, ...
 
 struct StemParams {
@@ -91,7 +92,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       for (int s = 0; s < kStemAStages; ++s) {
         mbar_init(&full[s], 4);      // one elected arrive per builder warp of the owning group
         mbar_init(&empty[s], 1);
-        mbar_init(&sfull[s], 2);
+        mbar_init(&sfull[s], 1);
         mbar_init(&sempty[s], 4);
       }
       mbar_init(&tfull[0], 1);
@@ -110,12 +111,12 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 7) {
+  if (warp >= 8) {
     // =============================================================== builders: operand A from the staged strip
     // Two groups of 4 warps alternate pipeline stages (group g owns stages s = g, g+2, ...), so two A tiles are
     // in flight; thread <-> A-tile row (conv pixel), 8 chunks of 16 B: chunk kh = 8 consecutive input pixels of
     // window row kh (chunk 7 = zero padding of K).
-    const int bt = threadIdx.x - 7 * 32;          // 0..255
+    const int bt = threadIdx.x - 8 * 32;          // 0..255
     const int group = bt >> 7;
     const int arow = bt & 127;
     const int SP = p.strip_pitch;
@@ -124,6 +125,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     int cached_tile = -1, cached_frame = -1;
     uint32_t arel = 0;
     bool avalid = false;
+    uint32_t sslot = group, sph = 0;              // strip ring position of stage s: s % kLoaders, (s / kLoaders) & 1
     for (uint32_t s = group; cur.frame < p.frames; s += 2) {
       const int slot = s & 3;
       const uint32_t ph = (s >> 2) & 1;
@@ -134,8 +136,8 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
         const int yy = m / p.Wo, xx = m - yy * p.Wo;
         arel = (uint32_t)((2 * yy - 3 - tile_iy0[cur.tile]) * SP + 2 * xx) >> 1;   // uint32 index into the strip
       }
-      const uint32_t* srow = reinterpret_cast<const uint32_t*>(strip + slot * strip_buf) + arel;
-      mbar_wait(&sfull[slot], ph);
+      const uint32_t* srow = reinterpret_cast<const uint32_t*>(strip + sslot * strip_buf) + arel;
+      mbar_wait(&sfull[sslot], sph);
       uint4 v[8];
 #pragma unroll
       for (int kh = 0; kh < 7; ++kh) {
@@ -147,7 +149,9 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       }
       v[7] = make_uint4(0u, 0u, 0u, 0u);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sempty[slot]);          // strip slot consumed (values are in registers)
+      if (lane == 0) mbar_arrive(&sempty[sslot]);         // strip slot consumed (values are in registers)
+      sslot += 2;
+      if (sslot >= kLoaders) { sslot -= kLoaders; sph ^= 1; }
       mbar_wait(&empty[slot], ph ^ 1);
       uint8_t* dst_row = smA + slot * kStemABytes + arow * 128;
 #pragma unroll
@@ -160,9 +164,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     }
   } else if (warp >= 5) {
     // =============================================================== loaders: global -> bf16 strip ring
-    // lane <-> group of 4 input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global load),
-    // warp lw <-> strip rows lw, lw+2, ...  Loads of stage s+1 are issued before stage s is converted, and the
-    // loaders run up to 4 stages ahead of the builders, so global latency is off the critical path.
+    // Three loader warps; warp lw owns strip slot lw and pipeline stages s = lw, lw+3, ...  Lane <-> group of 4
+    // input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global load per strip row).  The loads of a
+    // warp's next stage are issued before it converts the current one, so ~6 stages of global loads are in
+    // flight per CTA and their latency never reaches the builders.
     const int lw = warp - 5;
     const int grp = lane;
     const int ix0 = 4 * grp - 4;
@@ -181,43 +186,40 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       const int iy0 = tile_iy0[c.tile];
       const size_t fo = (size_t)(c.frame + c.kt - 2) * frame_elems + col_off;
 #pragma unroll
-      for (int i = 0; i < kIters; ++i) {
-        const int r = lw + 2 * i;
+      for (int r = 0; r < kIters; ++r) {
         const int iy = iy0 + r;
         if (r < p.strip_rows && (unsigned)iy < (unsigned)p.H) {
           if constexpr (kU8) {
-            raw[i] = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.x) + fo + iy * p.Wraw));
+            raw[r] = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.x) + fo + iy * p.Wraw));
           } else {
-            raw[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + fo + iy * p.Wraw));
+            raw[r] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + fo + iy * p.Wraw));
           }
-          vmask |= 1u << i;
+          vmask |= 1u << r;
         }
       }
     };
 
     StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
+    for (int i = 0; i < lw; ++i) cur.advance();
     cur.ft = cur.frame % p.T;
     if (cur.frame < p.frames) issue(cur);
-    for (uint32_t s = 0; cur.frame < p.frames; ++s) {
-      const int slot = s & 3;
-      const uint32_t ph = (s >> 2) & 1;
-      mbar_wait(&sempty[slot], ph ^ 1);
-      __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip + slot * strip_buf);
+    __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip + lw * strip_buf);
+    for (uint32_t it = 0; cur.frame < p.frames; ++it) {
+      mbar_wait(&sempty[lw], (it & 1) ^ 1);
       if (grp_ok) {
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-          const int r = lw + 2 * i;
+        for (int r = 0; r < kIters; ++r) {
           if (r < p.strip_rows) {
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-            if (vmask & (1u << i)) {
+            if (vmask & (1u << r)) {
               if constexpr (kU8) {
-                const uint32_t u = raw[i];
+                const uint32_t u = raw[r];
                 v0 = fmaf((float)(u & 0xffu), p.u8_scale, p.u8_bias);
                 v1 = fmaf((float)((u >> 8) & 0xffu), p.u8_scale, p.u8_bias);
                 v2 = fmaf((float)((u >> 16) & 0xffu), p.u8_scale, p.u8_bias);
                 v3 = fmaf((float)(u >> 24), p.u8_scale, p.u8_bias);
               } else {
-                v0 = raw[i].x; v1 = raw[i].y; v2 = raw[i].z; v3 = raw[i].w;
+                v0 = raw[r].x; v1 = raw[r].y; v2 = raw[r].z; v3 = raw[r].w;
               }
             }
             __nv_bfloat16* row = sb + r * SP + 4 * grp;   // strip column c = ix + 3 = 4*grp - 1 + j
@@ -227,11 +229,12 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
           }
         }
       }
-      cur.advance();
-      if (cur.kt == 0 && cur.tile == 0) cur.ft = cur.frame % p.T;
-      if (cur.frame < p.frames) issue(cur);                 // next stage's loads fly while builders work
+      const int prev_frame = cur.frame;
+      cur.advance(); cur.advance(); cur.advance();
+      if (cur.frame != prev_frame) cur.ft = cur.frame % p.T;
+      if (cur.frame < p.frames) issue(cur);                 // next own stage's loads fly while builders work
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[slot]);
+      if (lane == 0) mbar_arrive(&sfull[lw]);
     }
   } else if (warp == 4) {
     // =============================================================== MMA issuer
@@ -408,10 +411,10 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.frames < grid) grid = p.frames;
-  const bool small = p.strip_rows <= 14;      // rows per loader warp: 7 (GRID 88x88) or 12
+  const bool small = p.strip_rows <= 13;      // strip rows per stage: 13 (GRID 88x88) or up to 24
   void (*kern)(const CUtensorMap, const StemParams) =
-      is_u8 ? (small ? stem_conv3d_kernel<true, 7> : stem_conv3d_kernel<true, 12>)
-            : (small ? stem_conv3d_kernel<false, 7> : stem_conv3d_kernel<false, 12>);
+      is_u8 ? (small ? stem_conv3d_kernel<true, 13> : stem_conv3d_kernel<true, 24>)
+            : (small ? stem_conv3d_kernel<false, 13> : stem_conv3d_kernel<false, 24>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
   kern<<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
