@@ -1,0 +1,256 @@
+// 3x3 / stride 1 / pad 1 convolution, 64 -> 64 channels (ResNet layer1, models/video_models/resnet.py:56-69) with
+// operand reuse in shared memory.
+//
+// The generic implicit-GEMM kernel (igemm_conv.cu) fetches one [128 px x 64 ch] im2col box per filter tap, i.e.
+// every activation crosses L2 -> SM nine times; with only 64 output channels per tile that makes layer1
+// L2-bandwidth bound (measured ~10 TB/s, 445 TFLOP/s).  Here ONE TMA box -- an 18-row x 16-pixel halo patch --
+// feeds all nine taps: the A operand of tap (r, s) is simply a shifted view of the patch, expressed through the
+// UMMA shared-memory descriptor (start + (16 r + s) * 128 B, 2048 B between 8-pixel row groups), and the whole
+// 64 x 576 weight matrix stays resident in shared memory.  L2 traffic per output tile drops from 216 KB to 36 KB.
+//
+// Layout contract ("stacked rows"): activations are (N, img_rows, W, 64) bf16 with img_rows >= H + 1 and rows
+// H .. img_rows-1 of every image all zero.  Stacked row R = n * img_rows + y; the zero row is at once the bottom
+// padding of image n and the top padding of image n + 1, so a tile may span images.  Left / right padding comes
+// from TMA out-of-bounds zero fill.  An output tile is 16 stacked rows x 8 columns (M = 128); column groups of a
+// row start at 0, 8, ..., W - 8 (the last one may overlap its neighbour; duplicates are not written).  The kernel
+// never writes the padding rows of y: they must be zero when y is used as an input again.
+#include "dl_host.cuh"
+#include "dl_ptx.cuh"
+
+namespace dl {
+
+constexpr int kHaloPatchRows = 18, kHaloPatchCols = 16;
+constexpr int kHaloPatchBytes = kHaloPatchRows * kHaloPatchCols * 128;   // 36 864
+constexpr int kHaloStages = 4;
+constexpr int kHaloWBytes = 9 * 64 * 64 * 2;                             // 73 728 resident weights
+constexpr int kHaloThreads = 320;
+constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 3 * 64 * 4 + 16 * 8 + 16 + 1024;
+
+struct HaloParams {
+  int rows_total, img_rows, H, W;
+  int num_groups, total_tiles;
+  int base_offset_mode;
+  const float* scale;
+  const float* shift;
+  const float* slope;
+  const uint16_t* residual;
+  uint16_t* y;
+};
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+                    const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* patches = smem;
+  uint8_t* wres = smem + kHaloStages * kHaloPatchBytes;
+  float* prm = reinterpret_cast<float*>(wres + kHaloWBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 192);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kHaloStages;
+  uint64_t* tfull = bars + 2 * kHaloStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kHaloStages; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(&tfull[0], 1);
+      mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], 256);
+      mbar_init(&tempty[1], 256);
+      mbar_init(wfull, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<128>(tmem_slot);
+  }
+  for (int c = threadIdx.x; c < 64; c += kHaloThreads) {
+    prm[c] = p.scale[c];
+    prm[64 + c] = p.shift[c];
+    prm[128 + c] = p.slope[c];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, kHaloWBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &mapW, wfull, tap * 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int rt = tile / p.num_groups;
+        const int g = tile - rt * p.num_groups;
+        const int x0 = min(8 * g, p.W - 8);
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], kHaloPatchBytes);
+        tma_load_3d(patches + stage * kHaloPatchBytes, &mapX, &full[stage], 0, x0 - 1, rt * 16 - 1);
+        if (++stage == kHaloStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      mbar_wait(wfull, 0);
+      const uint32_t wbase = smem_u32(wres);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * 64;
+        const uint32_t pbase = smem_u32(patches + stage * kHaloPatchBytes);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, s = tap - 3 * r;
+          // rows of the A view: output pixel (rr, xx) reads patch pixel (rr + r, xx + s); pitch 16 px = 2048 B
+          const uint32_t a0 = pbase + (uint32_t)(r * kHaloPatchCols + s) * 128u;
+          const uint32_t bo = p.base_offset_mode ? (uint32_t)s : 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = umma_desc_sw128_kmajor_ex(a0 + 32u * k, 2048u, bo);
+            const uint64_t bdesc = umma_desc_sw128_kmajor(wbase + tap * 8192u + 32u * k);
+            umma_bf16(d, adesc, bdesc, idesc, (tap | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[acc]);
+        if (++stage == kHaloStages) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int chunk = (warp - 2) >> 2;          // 32-channel half handled by this warp
+    const bool has_res = p.residual != nullptr;
+    const int m = quarter * 32 + lane;          // accumulator row == TMEM lane
+    const int rr = m >> 3, xx = m & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int rt = tile / p.num_groups;
+      const int g = tile - rt * p.num_groups;
+      const int x0 = min(8 * g, p.W - 8);
+      const int R = rt * 16 + rr;
+      const int x = x0 + xx;
+      const bool ok = R < p.rows_total && (R % p.img_rows) < p.H && x >= 8 * g;
+      const size_t off = ((size_t)R * p.W + x) * 64 + chunk * 32;
+      uint4 res[4];
+      if (has_res && ok) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) res[q] = __ldg(rp + q);
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      uint32_t acc_r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 64 + chunk * 32, acc_r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      const float4* sc = reinterpret_cast<const float4*>(prm + chunk * 32);
+      const float4* sh = reinterpret_cast<const float4*>(prm + 64 + chunk * 32);
+      const float4* sl = reinterpret_cast<const float4*>(prm + 128 + chunk * 32);
+      uint4 o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 s4 = sc[2 * q + h], h4 = sh[2 * q + h];
+          v[4 * h + 0] = fmaf(__uint_as_float(acc_r[8 * q + 4 * h + 0]), s4.x, h4.x);
+          v[4 * h + 1] = fmaf(__uint_as_float(acc_r[8 * q + 4 * h + 1]), s4.y, h4.y);
+          v[4 * h + 2] = fmaf(__uint_as_float(acc_r[8 * q + 4 * h + 2]), s4.z, h4.z);
+          v[4 * h + 3] = fmaf(__uint_as_float(acc_r[8 * q + 4 * h + 3]), s4.w, h4.w);
+        }
+        if (has_res && ok) {
+          const uint4 rv = res[q];
+          v[0] += bf16_lo(rv.x); v[1] += bf16_hi(rv.x); v[2] += bf16_lo(rv.y); v[3] += bf16_hi(rv.y);
+          v[4] += bf16_lo(rv.z); v[5] += bf16_hi(rv.z); v[6] += bf16_lo(rv.w); v[7] += bf16_hi(rv.w);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 l4 = sl[2 * q + h];
+          v[4 * h + 0] = v[4 * h + 0] > 0.f ? v[4 * h + 0] : v[4 * h + 0] * l4.x;
+          v[4 * h + 1] = v[4 * h + 1] > 0.f ? v[4 * h + 1] : v[4 * h + 1] * l4.y;
+          v[4 * h + 2] = v[4 * h + 2] > 0.f ? v[4 * h + 2] : v[4 * h + 2] * l4.z;
+          v[4 * h + 3] = v[4 * h + 3] > 0.f ? v[4 * h + 3] : v[4 * h + 3] * l4.w;
+        }
+        o[q].x = pack_bf16x2(v[0], v[1]); o[q].y = pack_bf16x2(v[2], v[3]);
+        o[q].z = pack_bf16x2(v[4], v[5]); o[q].w = pack_bf16x2(v[6], v[7]);
+      }
+      if (ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.y + off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = o[q];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+}  // namespace dl
+
+extern "C" int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
+                                        const float* slope, const void* residual, void* y, int N, int H, int W,
+                                        int img_rows, void* stream) {
+  using namespace dl;
+  DL_CHECK_ARG(x && w_packed && scale && shift && slope && y, "conv3x3_halo: null pointer");
+  DL_CHECK_ARG(N > 0 && H > 0 && W >= 8 && img_rows >= H + 1, "conv3x3_halo: need W >= 8 and img_rows >= H + 1");
+  DL_CHECK_ARG((long long)N * img_rows < (1ll << 31) / 16, "conv3x3_halo: too many rows");
+  int st = require_sm100();
+  if (st != DL_OK) return st;
+  static bool configured = false;
+  static int bo_mode = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    if (e != cudaSuccess) return fail(DL_ERR_CUDA, "conv3x3_halo smem attribute: %s", cudaGetErrorString(e));
+    const char* env = getenv("DL_HALO_BASE_OFFSET");
+    bo_mode = env ? atoi(env) : 0;
+    configured = true;
+  }
+  HaloParams p;
+  p.rows_total = N * img_rows; p.img_rows = img_rows; p.H = H; p.W = W;
+  p.num_groups = (W + 7) / 8;
+  p.total_tiles = ((p.rows_total + 15) / 16) * p.num_groups;
+  p.base_offset_mode = bo_mode;
+  p.scale = scale; p.shift = shift; p.slope = slope;
+  p.residual = static_cast<const uint16_t*>(residual);
+  p.y = static_cast<uint16_t*>(y);
+  CUtensorMap mapX, mapW;
+  st = make_tiled_3d_bf16(&mapX, x, (uint64_t)p.rows_total, (uint64_t)W, 64, kHaloPatchRows, kHaloPatchCols, 64);
+  if (st != DL_OK) return st;
+  st = make_tiled_2d_bf16(&mapW, w_packed, 64, 576, 576, 64, 64);
+  if (st != DL_OK) return st;
+  int grid = device_sm_count();
+  if (grid <= 0) grid = 148;
+  if (p.total_tiles < grid) grid = p.total_tiles;
+  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(mapX, mapW, p);
+  return check_launch("conv3x3_halo_kernel");
+}

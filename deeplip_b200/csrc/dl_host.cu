@@ -101,13 +101,31 @@ int make_tiled_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return DL_OK;
 }
 
-int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int R, int S,
+int make_tiled_3d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t C,
+                       uint32_t box_rows, uint32_t box_cols, uint32_t box_c) {
+  int st = load_driver();
+  if (st != DL_OK) return st;
+  cuuint64_t dims[3] = {C, cols, rows};
+  cuuint64_t strides[2] = {C * 2, cols * C * 2};
+  cuuint32_t box[3] = {box_c, box_cols, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DL_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d): rows=%llu cols=%llu C=%llu", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)C);
+  return DL_OK;
+}
+
+int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int img_rows,
+                          int R, int S,
                           int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                           uint32_t channels, uint32_t pixels) {
   int st = load_driver();
   if (st != DL_OK) return st;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)img_rows * W * ldx * 2};
   // Bounding box of the filter's top-left anchor: starts at -pad and stops so that the last tap
   // (offset (S-1)*dil) still lies within the padded image.
   int lower[2] = {-pad_w, -pad_h};
@@ -122,7 +140,7 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
   // Drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (a flag in the
   // second descriptor word that must be clear); same remedy as NVIDIA's own conv templates apply.
   if (g_driver_version <= 13010) {
-    uint64_t bytes = (uint64_t)N * H * W * ldx * 2;
+    uint64_t bytes = (uint64_t)N * img_rows * W * ldx * 2;
     if (bytes < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
   }
   return DL_OK;

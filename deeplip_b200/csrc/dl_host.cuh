@@ -19,9 +19,14 @@ int require_sm100();                          // DL_OK or DL_ERR_UNSUPPORTED
 int make_tiled_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                        uint32_t box_rows, uint32_t box_cols);
 
+// 3-D tiled map over a (rows, cols, C) 16-bit tensor (C contiguous): box = (box_c, box_cols, box_rows).
+int make_tiled_3d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t C,
+                       uint32_t box_rows, uint32_t box_cols, uint32_t box_c);
+
 // im2col map over an NHWC 16-bit activation tensor (pitch ldx elements per pixel): loads
 // `pixels` output positions x `channels` channels per request, 128-byte swizzle, zero OOB fill.
-int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int R, int S,
+int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int img_rows,
+                          int R, int S,
                           int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                           uint32_t channels, uint32_t pixels);
 

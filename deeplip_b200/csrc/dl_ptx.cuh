@@ -47,11 +47,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a trap (launch error), never as a hung GPU box.
+// Bounded wait: a protocol bug must surface as a trap (launch error) within ~2 s, never as a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { asm volatile("trap;"); }
+    if (clock64() - t0 > 4000000000ll) { asm volatile("trap;"); }
   }
 }
 
@@ -186,4 +187,26 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+}  // namespace dl
+
+namespace dl {
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// General K-major 128B-swizzle descriptor: explicit stride between 8-row groups and swizzle-phase base offset
+// (for operand views whose start is not 1024-byte aligned).
+__device__ __forceinline__ uint64_t umma_desc_sw128_kmajor_ex(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 }  // namespace dl

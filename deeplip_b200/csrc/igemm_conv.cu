@@ -389,7 +389,9 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   const long long Ktot = (long long)d->R * d->S * p.cchunks * 64;
 
   CUtensorMap mapA, mapB;
-  st = make_im2col_nhwc_bf16(&mapA, x, d->N, d->H, d->W, d->C, d->ldx, d->R, d->S, d->stride_h, d->stride_w, d->pad_h,
+  const int img_rows = d->img_rows > 0 ? d->img_rows : d->H;
+  DL_CHECK_ARG(img_rows >= d->H, "conv_igemm: img_rows < H");
+  st = make_im2col_nhwc_bf16(&mapA, x, d->N, d->H, d->W, d->C, d->ldx, img_rows, d->R, d->S, d->stride_h, d->stride_w, d->pad_h,
                              d->pad_w, d->dil_h, d->dil_w, 64, 128);
   if (st != DL_OK) return st;
   st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot, (uint32_t)block_n, 64);

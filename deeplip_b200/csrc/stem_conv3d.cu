@@ -21,7 +21,8 @@ constexpr int kStemAStages = 4;
 constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 64 K (bf16)
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
 constexpr int kStemThreads = 16 * 32;               // 4 epilogue + 1 MMA + 3 loader + 8 builder warps
-constexpr int kLoaders = 3;                         // loader warps == strip ring slots
+constexpr int kLoaders = 3;                         // loader warps
+constexpr int kStripSlots = 6;                      // strip ring: slot s % 6 -> one producer warp (s % 3), one consumer group (s % 2)
 constexpr int kStripRowsMax = 24;                   // loader warp lw fills strip rows lw, lw+2, ...
 
 struct StemParams {
@@ -36,6 +37,7 @@ struct StemParams {
   const float* slope;
   uint16_t* y;
   int frames;
+  int out_img_rows;     // row pitch of one output frame (>= Hp)
 };
 
 // (frame, tile, temporal tap) of a pipeline stage; every role walks the same sequence.
@@ -64,20 +66,20 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   uint8_t* smB = smA + kStemAStages * kStemABytes;               // 40 KB
   uint8_t* ring = smB + kStemBBytes;                             // ring_rows x Wo x 128 B
   const int ring_bytes = p.ring_rows * p.Wo * 128;
-  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // 4 x strip_rows x strip_pitch bf16
+  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // kStripSlots x strip_rows x strip_pitch bf16
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const int strip_buf = (strip_elems + 7) & ~7;
-  float* chan = reinterpret_cast<float*>(strip + 4 * strip_buf);   // scale, shift, slope
+  float* chan = reinterpret_cast<float*>(strip + kStripSlots * strip_buf);   // scale, shift, slope
   uint64_t* bars = reinterpret_cast<uint64_t*>(chan + 192);
   uint64_t* full = bars;                         // [kStemAStages]
   uint64_t* empty = bars + kStemAStages;         // [kStemAStages]
   uint64_t* tfull = bars + 2 * kStemAStages;     // [2]
   uint64_t* tempty = tfull + 2;                  // [2]
   uint64_t* wbar = tempty + 2;                   // [1]
-  uint64_t* sfull = wbar + 1;                    // [4] strip slot filled (2 loader warps)
-  uint64_t* sempty = sfull + 4;                  // [4] strip slot consumed (4 builder warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 4);
-  int* tile_iy0 = reinterpret_cast<int*>(sempty + 5);   // [tiles_per_frame <= 64] first input row of a tile's strip
+  uint64_t* sfull = wbar + 1;                    // [kStripSlots] strip slot filled (its loader warp)
+  uint64_t* sempty = sfull + kStripSlots;        // [kStripSlots] strip slot consumed (4 builder warps of one group)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + kStripSlots);
+  int* tile_iy0 = reinterpret_cast<int*>(sempty + kStripSlots + 1);   // [tiles_per_frame <= 64] first input row of a tile's strip
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,6 +94,8 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       for (int s = 0; s < kStemAStages; ++s) {
         mbar_init(&full[s], 4);      // one elected arrive per builder warp of the owning group
         mbar_init(&empty[s], 1);
+      }
+      for (int s = 0; s < kStripSlots; ++s) {
         mbar_init(&sfull[s], 1);
         mbar_init(&sempty[s], 4);
       }
@@ -125,7 +129,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     int cached_tile = -1, cached_frame = -1;
     uint32_t arel = 0;
     bool avalid = false;
-    uint32_t sslot = group, sph = 0;              // strip ring position of stage s: s % kLoaders, (s / kLoaders) & 1
+    uint32_t sslot = group, sph = 0;              // strip ring position of stage s: s % kStripSlots, (s / kStripSlots) & 1
     for (uint32_t s = group; cur.frame < p.frames; s += 2) {
       const int slot = s & 3;
       const uint32_t ph = (s >> 2) & 1;
@@ -151,7 +155,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sempty[sslot]);         // strip slot consumed (values are in registers)
       sslot += 2;
-      if (sslot >= kLoaders) { sslot -= kLoaders; sph ^= 1; }
+      if (sslot >= kStripSlots) { sslot -= kStripSlots; sph ^= 1; }
       mbar_wait(&empty[slot], ph ^ 1);
       uint8_t* dst_row = smA + slot * kStemABytes + arow * 128;
 #pragma unroll
@@ -164,7 +168,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     }
   } else if (warp >= 5) {
     // =============================================================== loaders: global -> bf16 strip ring
-    // Three loader warps; warp lw owns strip slot lw and pipeline stages s = lw, lw+3, ...  Lane <-> group of 4
+    // Three loader warps; warp lw owns pipeline stages s = lw, lw+3, ... (strip slots lw and lw+3).  Lane <-> group of 4
     // input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global load per strip row).  The loads of a
     // warp's next stage are issued before it converts the current one, so ~6 stages of global loads are in
     // flight per CTA and their latency never reaches the builders.
@@ -203,9 +207,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     for (int i = 0; i < lw; ++i) cur.advance();
     cur.ft = cur.frame % p.T;
     if (cur.frame < p.frames) issue(cur);
-    __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip + lw * strip_buf);
     for (uint32_t it = 0; cur.frame < p.frames; ++it) {
-      mbar_wait(&sempty[lw], (it & 1) ^ 1);
+      const int slot = lw + kLoaders * (it & 1);            // stage s = lw + 3*it  ->  slot s % 6
+      __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip + slot * strip_buf);
+      mbar_wait(&sempty[slot], ((it >> 1) & 1) ^ 1);
       if (grp_ok) {
 #pragma unroll
         for (int r = 0; r < kIters; ++r) {
@@ -234,7 +239,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       if (cur.frame != prev_frame) cur.ft = cur.frame % p.T;
       if (cur.frame < p.frames) issue(cur);                 // next own stage's loads fly while builders work
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[lw]);
+      if (lane == 0) mbar_arrive(&sfull[slot]);
     }
   } else if (warp == 4) {
     // =============================================================== MMA issuer
@@ -277,7 +282,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
     const int row_bytes = p.Wo * 128;
     for (int frame = blockIdx.x; frame < p.frames; frame += gridDim.x) {
       int py_done = 0;
-      uint16_t* yframe = p.y + (size_t)frame * p.Hp * p.Wp * 64;
+      uint16_t* yframe = p.y + (size_t)frame * p.out_img_rows * p.Wp * 64;
       for (int tile = 0; tile < p.tiles_per_frame; ++tile) {
         const int m = tile * 128 + et;
         mbar_wait(&tfull[acc], acc_phase);
@@ -364,7 +369,8 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
 
 extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
                                             float mean, float std, const void* w_packed, const float* scale,
-                                            const float* shift, const float* slope, void* y, void* stream) {
+                                            const float* shift, const float* slope, void* y, int out_img_rows,
+                                            void* stream) {
   using namespace dl;
   DL_CHECK_ARG(x && w_packed && scale && shift && slope && y, "stem: null pointer");
   DL_CHECK_ARG(B > 0 && T > 0, "stem: empty batch");
@@ -399,10 +405,12 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.y = static_cast<uint16_t*>(y);
   p.frames = B * T;
+  p.out_img_rows = out_img_rows > 0 ? out_img_rows : p.Hp;
+  DL_CHECK_ARG(p.out_img_rows >= p.Hp, "stem: out_img_rows < H/4");
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
-                      4 * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 24 * 8 + 16 + 64 * 4;
+                      kStripSlots * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 32 * 8 + 16 + 64 * 4;
   DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
   CUtensorMap mapW;

@@ -62,8 +62,9 @@ def nct_to_ntc_bf16(x, ld=None):
 
 
 # ------------------------------------------------------------------ K2
-def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std=0.165):
-    """x: (B,T,H,W) f32 normalised frames, or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T, H/4, W/4, 64) bf16."""
+def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std=0.165, out=None):
+    """x: (B,T,H,W) f32 normalised frames, or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T, H/4, W/4, 64) bf16.
+    out: optional pre-zeroed (B*T, rows >= H/4, W/4, 64) buffer in the stacked-rows layout."""
     _need_cuda(x, w_packed, scale, shift, slope)
     x = x.contiguous()
     B, T = x.shape[0], x.shape[1]
@@ -75,10 +76,15 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
         x = x.float()
         H, W = x.shape[2], x.shape[3]
         Hraw, Wraw, is_u8 = H, W, 0
-    y = torch.empty((B * T, H // 4, W // 4, 64), device=x.device, dtype=torch.bfloat16)
+    if out is None:
+        y = torch.empty((B * T, H // 4, W // 4, 64), device=x.device, dtype=torch.bfloat16)
+    else:
+        y = out
+        assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.shape[0] == B * T and \
+            y.shape[1] >= H // 4 and y.shape[2] == W // 4 and y.shape[3] == 64
     st = _lib.lib().dl_stem_conv3d_bn_prelu_pool(_ptr(x), is_u8, B, T, H, W, Hraw, Wraw, float(mean), float(std),
                                                  _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope), _ptr(y),
-                                                 _stream())
+                                                 y.shape[1], _stream())
     _lib.check(st, 'dl_stem_conv3d_bn_prelu_pool')
     return y
 
@@ -86,11 +92,13 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
 # ------------------------------------------------------------------ K3 / K5 / K7
 def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=(1, 1), scale=None, shift=None,
                slope=None, residual=None, want_bf16=True, want_f32=False, scale2=None, shift2=None,
-               f32_slope=1.0):
-    """x: (N,H,W,ldx) bf16 channels-last.  Returns (y_bf16 (N,P,Q,Cout) | None, y_f32 (N*P*Q,Cout) | None)."""
+               f32_slope=1.0, H=None):
+    """x: (N,H,W,ldx) bf16 channels-last -- or (N,img_rows,W,ldx) stacked rows with the true height passed as H.
+    Returns (y_bf16 (N,P,Q,Cout) | None, y_f32 (N*P*Q,Cout) | None)."""
     _need_cuda(x, w_packed, scale, shift, slope, residual, scale2, shift2)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
-    N, H, W, ldx = x.shape
+    N, img_rows, W, ldx = x.shape
+    H = H or img_rows
     P = (H + 2 * pad[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
     Q = (W + 2 * pad[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
     y = torch.empty((N, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
@@ -98,12 +106,26 @@ def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.numel() == y.numel()
     d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], Cout, Cout,
-                 float(f32_slope))
+                 float(f32_slope), img_rows)
     st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
                                        _ptr(residual), _ptr(y), _ptr(yf), _ptr(scale2), _ptr(shift2),
                                        C.byref(d), _stream())
     _lib.check(st, 'dl_conv_igemm_bf16')
     return y, yf
+
+
+def conv3x3_halo(x, w_packed, scale, shift, slope, H, out, residual=None):
+    """3x3 s1 p1 64->64 conv on stacked-rows activations: x, out, residual (N, img_rows >= H+1, W, 64) bf16 with
+    zero padding rows; `out` is a caller-owned buffer whose padding rows are already zero."""
+    _need_cuda(x, w_packed, scale, shift, slope, residual, out)
+    for t in (x, out, residual):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == x.shape)
+    N, img_rows, W, Cc = x.shape
+    assert Cc == 64
+    st = _lib.lib().dl_conv3x3_c64_halo_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
+                                             _ptr(residual), _ptr(out), N, H, W, img_rows, _stream())
+    _lib.check(st, 'dl_conv3x3_c64_halo_bf16')
+    return out
 
 
 # ------------------------------------------------------------------ K4 / K6

@@ -79,6 +79,13 @@ class Lipreading(nn.Module):
         if self.training:
             raise RuntimeError('deeplip_b200.Lipreading is inference-only: call .eval() (BN uses running stats)')
         pk = self._packed()
+        B, T = x.shape[0], x.shape[1]
+        H, W = (88, 88) if x.dtype == torch.uint8 else (x.shape[2], x.shape[3])
+        if self.trunk.halo_enabled(W // 4):
+            # stem writes straight into the stacked-rows layout layer1's halo kernel consumes
+            buf = self.trunk.stacked_buffers(B * T, H // 4, W // 4, x.device, 2 * len(self.trunk.layer1) + 1)[-1]
+            ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], out=buf)
+            return self.trunk.forward_nhwc(buf, stacked_H=H // 4)
         y = ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'])
         return self.trunk.forward_nhwc(y)
 

@@ -6,10 +6,14 @@ forward runs dl_conv_igemm_bf16 (tcgen05 implicit GEMM, BN/PReLU/residual fused)
 bf16 activations.  Inference (eval) only.
 """
 import math
+import os
 import torch
 import torch.nn as nn
 
 from .. import ops, packing
+
+# layer1 (64 -> 64, 3x3, stride 1) runs on the halo-reuse kernel (dl_conv3x3_c64_halo_bf16) unless disabled
+USE_HALO = os.environ.get('DL_USE_HALO', '1') != '0'
 
 
 def conv3x3(in_planes, out_planes, stride=1):
@@ -70,16 +74,30 @@ class BasicBlock(nn.Module):
             self._pk = pk
         return self._pk
 
-    def forward_nhwc(self, x):
-        """x: (N,H,W,inplanes) bf16 -> (N,P,Q,planes) bf16  (reference forward :56-69)."""
+    @property
+    def halo_ok(self):
+        return self.stride == 1 and self.inplanes == 64 and self.planes == 64 and self.downsample is None
+
+    def forward_stacked(self, x, H, mid, out):
+        """Stacked-rows layout (N, >=H+1, W, 64): both convs on the halo-reuse kernel; mid/out are
+        caller-owned buffers whose padding rows are zero."""
+        pk = self._packed()
+        ops.conv3x3_halo(x, pk['w1'], pk['s1'], pk['h1'], pk['a1'], H, out=mid)
+        ops.conv3x3_halo(mid, pk['w2'], pk['s2'], pk['h2'], pk['a2'], H, out=out, residual=x)
+        return out
+
+    def forward_nhwc(self, x, H=None):
+        """x: (N,H,W,inplanes) bf16 -> (N,P,Q,planes) bf16  (reference forward :56-69).  With H given, x is in
+        the stacked-rows layout (N, img_rows > H, W, C); only blocks with a downsample branch accept that."""
         pk = self._packed()
         st = (self.stride, self.stride)
         out, _ = ops.conv_igemm(x, pk['w1'], self.inplanes, self.planes, 3, 3, st, (1, 1), (1, 1),
-                                pk['s1'], pk['h1'], pk['a1'])
+                                pk['s1'], pk['h1'], pk['a1'], H=H)
         if self.downsample is not None:
             res, _ = ops.conv_igemm(x, pk['wd'], self.inplanes, self.planes, 1, 1, st, (0, 0), (1, 1),
-                                    pk['sd'], pk['hd'], pk['ad'])
+                                    pk['sd'], pk['hd'], pk['ad'], H=H)
         else:
+            assert H is None, 'identity residual needs the dense layout'
             res = x
         out, _ = ops.conv_igemm(out, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1),
                                 pk['s2'], pk['h2'], pk['a2'], residual=res)
@@ -143,11 +161,39 @@ class ResNet(nn.Module):
         self.invalidate()
         return out
 
-    def forward_nhwc(self, x):
-        """(N,H,W,64) bf16 -> (N,P,Q,512) bf16, before the global average pool."""
-        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
-            for blk in layer:
+    def halo_enabled(self, W):
+        return USE_HALO and W >= 8 and all(b.halo_ok for b in self.layer1) and self.layer2[0].downsample is not None
+
+    def stacked_buffers(self, N, H, W, device, count):
+        """Persistent zero-initialised (N, H+1, W, 64) activation buffers (padding rows are never written)."""
+        key = (N, H, W, str(device), count)
+        if getattr(self, '_stk_key', None) != key:
+            self._stk = [torch.zeros((N, H + 1, W, 64), device=device, dtype=torch.bfloat16) for _ in range(count)]
+            self._stk_key = key
+        return self._stk
+
+    def forward_nhwc(self, x, stacked_H=None):
+        """(N,H,W,64) bf16 -- or stacked rows (N,H+1,W,64) with stacked_H=H -- -> (N,P,Q,512) bf16, before the
+        global average pool."""
+        N, rows, W, _ = x.shape
+        H = stacked_H or rows
+        if self.halo_enabled(W):
+            nb = len(self.layer1)
+            bufs = self.stacked_buffers(N, H, W, x.device, 2 * nb + 1)
+            if stacked_H is None:
+                bufs[-1][:, :H].copy_(x)
+                x = bufs[-1]
+            for i, blk in enumerate(self.layer1):
+                x = blk.forward_stacked(x, H, bufs[2 * i], bufs[2 * i + 1])
+            x = self.layer2[0].forward_nhwc(x, H=H)
+            rest = list(self.layer2)[1:]
+        else:
+            assert stacked_H is None
+            for blk in self.layer1:
                 x = blk.forward_nhwc(x)
+            rest = list(self.layer2)
+        for blk in rest + list(self.layer3) + list(self.layer4):
+            x = blk.forward_nhwc(x)
         return x
 
     def forward(self, x):

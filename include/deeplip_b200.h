@@ -59,11 +59,14 @@ int dl_nct_to_ntc_bf16(const float* x, int B, int C, int T, void* y, int ldc, vo
  *     (B, T, Hraw, Wraw) with the reference preprocessing fused into the load (u8 == 1):
  *     x/255 -> centre crop to HxW -> (x-mean)/std  (models/video_models/dataloaders.py:19-24).
  *     w_packed: (64, 320) bf16 = [cout][kt][kh*8+kw] zero padded (see deeplip_b200/packing.py).
- *     y: (B*T, H/4, W/4, 64) bf16 channels-last.
+ *     y: (B*T, out_img_rows, W/4, 64) bf16 channels-last; out_img_rows >= H/4 is the row pitch of one
+ *     frame (0 = H/4).  Rows H/4 .. out_img_rows-1 are not written ("stacked rows" layout of
+ *     dl_conv3x3_c64_halo_bf16: the caller keeps them zero).
  */
 int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
                                  float mean, float std, const void* w_packed, const float* scale,
-                                 const float* shift, const float* slope, void* y, void* stream);
+                                 const float* shift, const float* slope, void* y, int out_img_rows,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3/K5/K7  implicit-GEMM convolution on tcgen05 tensor cores (TMA im2col operand A, TMA tiled
@@ -87,11 +90,23 @@ typedef struct dl_conv_desc {
   int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   int ldy, ldf;
   float f32_slope;   /* leaky slope applied to the f32 side output (1.0f = none) */
+  int img_rows;      /* row pitch of one input image (>= H; 0 = H): input may be in the stacked-rows layout */
 } dl_conv_desc;
 
 int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
                        const float* slope, const void* residual, void* y, float* y_f32, const float* scale2,
                        const float* shift2, const dl_conv_desc* desc, void* stream);
+
+/* 3x3 / stride 1 / pad 1, 64 -> 64 channel convolution with shared-memory operand reuse (one halo patch
+ * feeds all nine taps, weights resident): the ResNet layer1 BasicBlock convs (resnet.py:56-69) at a ninth
+ * of the L2 traffic of the generic kernel.  Same fused epilogue (scale, shift, residual, slope).
+ * x, y, residual: (N, img_rows, W, 64) bf16 "stacked rows": img_rows >= H + 1 and rows H .. img_rows-1 of
+ * every image are zero in x (they act as vertical padding); the kernel never writes those rows of y.
+ * w_packed: (64, 576) bf16 as for dl_conv_igemm_bf16.  W >= 8.
+ */
+int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
+                             const float* slope, const void* residual, void* y, int N, int H, int W,
+                             int img_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  per-frame global average pool + masked temporal mean.  Replaces AdaptiveAvgPool2d(1)

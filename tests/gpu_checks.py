@@ -64,6 +64,36 @@ def conv_case(N, H, W, C, Cout, R, S, stride=1, pad=0, dil=(1, 1), residual=Fals
     return out
 
 
+def halo_case(N=5, H=22, W=22, residual=True, seed=0):
+    """dl_conv3x3_c64_halo_bf16 on the stacked-rows layout vs F.conv2d."""
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(N, H, W, 64, generator=g))
+    w = bf16r(torch.randn(64, 64, 3, 3, generator=g) / 24.0)
+    scale = torch.rand(64, generator=g) + 0.5
+    shift = torch.randn(64, generator=g) * 0.2
+    slope = torch.rand(64, generator=g) * 0.5
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
+    res = bf16r(torch.randn(N, H, W, 64, generator=g)) if residual else None
+    if residual:
+        ref = ref + res.permute(0, 3, 1, 2)
+    ref = torch.where(ref > 0, ref, ref * slope[None, :, None, None]).permute(0, 2, 3, 1)
+
+    def stack(t):
+        o = torch.zeros(N, H + 1, W, 64)
+        o[:, :H] = t
+        return o.to(DEV).to(torch.bfloat16)
+    out = torch.zeros(N, H + 1, W, 64, device=DEV, dtype=torch.bfloat16)
+    ops.conv3x3_halo(stack(x), packing.pack_conv_weight(w.to(DEV)), scale.to(DEV), shift.to(DEV), slope.to(DEV), H,
+                     out=out, residual=None if res is None else stack(res))
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    m = {'rel': rel_err(got[:, :H], ref), 'pad_abs': float(got[:, H:].abs().max())}
+    d = (got[:, :H] - ref).abs()
+    m['worst'] = [int(v) for v in np.unravel_index(int(d.argmax()), d.shape)]
+    assert m['rel'] < 1.5e-2 and m['pad_abs'] == 0.0, m
+    return m
+
+
 def _pad_last(t, n):
     if t.shape[-1] == n:
         return t

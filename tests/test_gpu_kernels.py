@@ -17,6 +17,11 @@ def test_conv_igemm(name):
     G.conv_case(**G.CONV_CASES[name])
 
 
+@pytest.mark.parametrize('kw', [dict(), dict(N=3, H=8, W=40, residual=False), dict(N=1, H=3, W=8), dict(N=300)])
+def test_conv3x3_halo(kw):
+    G.halo_case(**kw)
+
+
 def test_conv_igemm_rejects_bad_shapes():
     from deeplip_b200 import ops
     x = torch.zeros(1, 4, 4, 12, device='cuda', dtype=torch.bfloat16)          # ldx not a multiple of 8

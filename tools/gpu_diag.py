@@ -35,6 +35,9 @@ run('frontend_logfbank60', G.frontend_case, feat_type='logfbank', n_feat=60)
 run('frontend_ragged', G.frontend_case, B=3, nsamp=20000, lengths=[20000, 12345, 300])
 for k, kw in G.CONV_CASES.items():
     run('conv_' + k, G.conv_case, **kw)
+run('halo_22', G.halo_case)
+run('halo_8x40_nores', G.halo_case, N=3, H=8, W=40, residual=False)
+run('halo_big', G.halo_case, N=300, H=22, W=22)
 run('attn_pool', G.attn_pool_case)
 run('stem_f32_small', G.stem_case, B=1, T=3, H=32, W=32)
 run('stem_f32', G.stem_case)
