@@ -29,7 +29,6 @@ constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 3 * 64 *
 struct HaloParams {
   int rows_total, img_rows, H, W;
   int num_groups, total_tiles;
-  int base_offset_mode;
   const float* scale;
   const float* shift;
   const float* slope;
@@ -122,7 +121,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
           const int r = tap / 3, s = tap - 3 * r;
           // rows of the A view: output pixel (rr, xx) reads patch pixel (rr + r, xx + s); pitch 16 px = 2048 B
           const uint32_t a0 = pbase + (uint32_t)(r * kHaloPatchCols + s) * 128u;
-          const uint32_t bo = p.base_offset_mode ? (uint32_t)s : 0u;
+          // The 128B swizzle is a function of the absolute shared-memory address bits (verified on B200: a view that
+          // starts s pixels into the row needs NO descriptor base offset; setting one scrambles the operand).
+          const uint32_t bo = 0u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adesc = umma_desc_sw128_kmajor_ex(a0 + 32u * k, 2048u, bo);
@@ -227,19 +228,15 @@ extern "C" int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, con
   int st = require_sm100();
   if (st != DL_OK) return st;
   static bool configured = false;
-  static int bo_mode = 0;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "conv3x3_halo smem attribute: %s", cudaGetErrorString(e));
-    const char* env = getenv("DL_HALO_BASE_OFFSET");
-    bo_mode = env ? atoi(env) : 0;
     configured = true;
   }
   HaloParams p;
   p.rows_total = N * img_rows; p.img_rows = img_rows; p.H = H; p.W = W;
   p.num_groups = (W + 7) / 8;
   p.total_tiles = ((p.rows_total + 15) / 16) * p.num_groups;
-  p.base_offset_mode = bo_mode;
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.residual = static_cast<const uint16_t*>(residual);
   p.y = static_cast<uint16_t*>(y);
