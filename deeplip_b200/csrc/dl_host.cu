@@ -118,6 +118,24 @@ int make_tiled_3d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return DL_OK;
 }
 
+int make_tiled_4d_bf16_noswizzle(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t d2,
+                                 uint64_t d3, uint32_t box_cols, uint32_t box_rows) {
+  int st = load_driver();
+  if (st != DL_OK) return st;
+  cuuint64_t dims[4] = {cols, rows, d2, d3};
+  cuuint64_t strides[3] = {cols * 2, rows * cols * 2, d2 * rows * cols * 2};
+  cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DL_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d): cols=%llu rows=%llu d2=%llu d3=%llu box=%ux%u",
+                (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)d2,
+                (unsigned long long)d3, box_cols, box_rows);
+  return DL_OK;
+}
+
 int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int img_rows,
                           int R, int S,
                           int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,

@@ -23,6 +23,10 @@ int make_tiled_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64
 int make_tiled_3d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t C,
                        uint32_t box_rows, uint32_t box_cols, uint32_t box_c);
 
+// 4-D tiled map, no swizzle, over a dense (d3, d2, rows, cols) 16-bit tensor; box = (box_cols, box_rows, 1, 1).
+int make_tiled_4d_bf16_noswizzle(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t d2,
+                                 uint64_t d3, uint32_t box_cols, uint32_t box_rows);
+
 // im2col map over an NHWC 16-bit activation tensor (pitch ldx elements per pixel): loads
 // `pixels` output positions x `channels` channels per request, 128-byte swizzle, zero OOB fill.
 int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int img_rows,

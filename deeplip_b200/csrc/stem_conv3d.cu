@@ -11,7 +11,6 @@
 // bf16 conv rows in a shared-memory ring and max-pool completed rows straight to global memory.
 //
 // Roofline: tensor pipe; algorithmic work 2*Ho*Wo*64*245 flop per frame (DESIGN.md "Kernels").
-#include <type_traits>
 #include "dl_host.cuh"
 #include "dl_ptx.cuh"
 
@@ -20,18 +19,15 @@ namespace dl {
 constexpr int kStemAStages = 4;
 constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 64 K (bf16)
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
-constexpr int kStemThreads = 16 * 32;               // 4 epilogue + 1 MMA + 3 loader + 8 builder warps
-constexpr int kLoaders = 3;                         // loader warps
-constexpr int kStripSlots = 6;                      // strip ring: slot s % 6 -> one producer warp (s % 3), one consumer group (s % 2)
-constexpr int kStripRowsMax = 24;                   // loader warp lw fills strip rows lw, lw+2, ...
+constexpr int kStemThreads = 14 * 32;               // 4 epilogue + 1 MMA + 1 TMA + 8 builder warps
+constexpr int kStripSlots = 6;                      // strip ring: slot s % 6 -> consumer group s % 2
+constexpr int kStripRowsMax = 24;                   // strip rows per stage (TMA box height)
 
 struct StemParams {
-  const void* x;
-  int B, T, H, W, Hraw, Wraw, dh, dw;
-  float u8_scale, u8_bias;                          // (u/255 - mean)/std == u * u8_scale + u8_bias
+  int B, T, H, W;
   int Ho, Wo, Hp, Wp, Mf, tiles_per_frame;
   int ring_rows;        // power of two
-  int strip_rows, strip_pitch;                      // pitch = W + 12 elements (cols c = ix + 3, c in [0, W+8))
+  int strip_rows, strip_pitch;                      // pitch = roundup8(W + 8) elements (cols c = ix + 3)
   const float* scale;
   const float* shift;
   const float* slope;
@@ -56,9 +52,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <bool kU8, int kIters>
 __global__ void __launch_bounds__(kStemThreads, 1)
-stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p) {
+stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
+                   const StemParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // round up inside the shared window (pointer arithmetic on the __shared__ symbol keeps LDS/STS addressing)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -68,7 +64,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   const int ring_bytes = p.ring_rows * p.Wo * 128;
   uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // kStripSlots x strip_rows x strip_pitch bf16
   const int strip_elems = p.strip_rows * p.strip_pitch;
-  const int strip_buf = (strip_elems + 7) & ~7;
+  const int strip_buf = (strip_elems + 63) & ~63;
   float* chan = reinterpret_cast<float*>(strip + kStripSlots * strip_buf);   // scale, shift, slope
   uint64_t* bars = reinterpret_cast<uint64_t*>(chan + 192);
   uint64_t* full = bars;                         // [kStemAStages]
@@ -96,7 +92,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
         mbar_init(&empty[s], 1);
       }
       for (int s = 0; s < kStripSlots; ++s) {
-        mbar_init(&sfull[s], 1);
+        mbar_init(&sfull[s], 1);      // the producer's expect_tx arrive
         mbar_init(&sempty[s], 4);
       }
       mbar_init(&tfull[0], 1);
@@ -106,6 +102,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       mbar_init(wbar, 1);
       fence_mbar_init();
       tma_prefetch_desc(&mapW);
+      tma_prefetch_desc(&mapX);
     }
     __syncwarp();
     tmem_alloc<128>(tmem_slot);
@@ -115,12 +112,12 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8) {
+  if (warp >= 6) {
     // =============================================================== builders: operand A from the staged strip
     // Two groups of 4 warps alternate pipeline stages (group g owns stages s = g, g+2, ...), so two A tiles are
     // in flight; thread <-> A-tile row (conv pixel), 8 chunks of 16 B: chunk kh = 8 consecutive input pixels of
     // window row kh (chunk 7 = zero padding of K).
-    const int bt = threadIdx.x - 8 * 32;          // 0..255
+    const int bt = threadIdx.x - 6 * 32;          // 0..255
     const int group = bt >> 7;
     const int arow = bt & 127;
     const int SP = p.strip_pitch;
@@ -166,80 +163,24 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
       cur.advance();
       cur.advance();
     }
-  } else if (warp >= 5) {
-    // =============================================================== loaders: global -> bf16 strip ring
-    // Three loader warps; warp lw owns pipeline stages s = lw, lw+3, ... (strip slots lw and lw+3).  Lane <-> group of 4
-    // input columns ix0 = 4*lane-4 .. +3 (one aligned 4-byte / 16-byte global load per strip row).  The loads of a
-    // warp's next stage are issued before it converts the current one, so ~6 stages of global loads are in
-    // flight per CTA and their latency never reaches the builders.
-    const int lw = warp - 5;
-    const int grp = lane;
-    const int ix0 = 4 * grp - 4;
-    const bool col_ok = ix0 >= 0 && ix0 < p.W;            // whole group inside the image (W % 4 == 0)
-    const bool grp_ok = grp <= p.W / 4 + 2;               // group touches the strip at all
-    const int SP = p.strip_pitch;
-    const size_t frame_elems = (size_t)p.Hraw * p.Wraw;
-    const int col_off = (kU8 ? p.dh * p.Wraw + p.dw : 0) + ix0;
-    typename std::conditional<kU8, uint32_t, float4>::type raw[kIters];
-    uint32_t vmask = 0;
-
-    auto issue = [&](const StemCursor& c) {
-      const int tt = c.ft + c.kt - 2;
-      vmask = 0;
-      if (!(col_ok && tt >= 0 && tt < p.T)) return;
-      const int iy0 = tile_iy0[c.tile];
-      const size_t fo = (size_t)(c.frame + c.kt - 2) * frame_elems + col_off;
-#pragma unroll
-      for (int r = 0; r < kIters; ++r) {
-        const int iy = iy0 + r;
-        if (r < p.strip_rows && (unsigned)iy < (unsigned)p.H) {
-          if constexpr (kU8) {
-            raw[r] = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.x) + fo + iy * p.Wraw));
-          } else {
-            raw[r] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + fo + iy * p.Wraw));
-          }
-          vmask |= 1u << r;
-        }
+  } else if (warp == 5) {
+    // =============================================================== strip producer: one thread, TMA only
+    // The input was normalised / zero-bordered once by stem_prepass_kernel into (B, T, H+8, pitch) bf16, so the
+    // strip of a stage is a plain 2-D box of that tensor: rows iy0 .. iy0+strip_rows-1 of frame t+kt-2 (a frame
+    // index outside [0,T) is out of bounds in the T dimension -> the TMA unit zero-fills it: Conv3d's temporal pad).
+    if (lane == 0) {
+      StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
+      int fb = cur.frame / p.T, ft = cur.frame - fb * p.T;
+      int last_frame = cur.frame;
+      const uint32_t strip_bytes = (uint32_t)strip_elems * 2u;
+      uint32_t slot = 0, ph = 0;
+      for (; cur.frame < p.frames; cur.advance()) {
+        if (cur.frame != last_frame) { last_frame = cur.frame; fb = cur.frame / p.T; ft = cur.frame - fb * p.T; }
+        mbar_wait(&sempty[slot], ph ^ 1);
+        mbar_expect_tx(&sfull[slot], strip_bytes);
+        tma_load_4d(strip + slot * strip_buf, &mapX, &sfull[slot], 0, tile_iy0[cur.tile] + 3, ft + cur.kt - 2, fb);
+        if (++slot == kStripSlots) { slot = 0; ph ^= 1; }
       }
-    };
-
-    StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
-    for (int i = 0; i < lw; ++i) cur.advance();
-    cur.ft = cur.frame % p.T;
-    if (cur.frame < p.frames) issue(cur);
-    for (uint32_t it = 0; cur.frame < p.frames; ++it) {
-      const int slot = lw + kLoaders * (it & 1);            // stage s = lw + 3*it  ->  slot s % 6
-      __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(strip + slot * strip_buf);
-      mbar_wait(&sempty[slot], ((it >> 1) & 1) ^ 1);
-      if (grp_ok) {
-#pragma unroll
-        for (int r = 0; r < kIters; ++r) {
-          if (r < p.strip_rows) {
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-            if (vmask & (1u << r)) {
-              if constexpr (kU8) {
-                const uint32_t u = raw[r];
-                v0 = fmaf((float)(u & 0xffu), p.u8_scale, p.u8_bias);
-                v1 = fmaf((float)((u >> 8) & 0xffu), p.u8_scale, p.u8_bias);
-                v2 = fmaf((float)((u >> 16) & 0xffu), p.u8_scale, p.u8_bias);
-                v3 = fmaf((float)(u >> 24), p.u8_scale, p.u8_bias);
-              } else {
-                v0 = raw[r].x; v1 = raw[r].y; v2 = raw[r].z; v3 = raw[r].w;
-              }
-            }
-            __nv_bfloat16* row = sb + r * SP + 4 * grp;   // strip column c = ix + 3 = 4*grp - 1 + j
-            if (grp > 0) row[-1] = __float2bfloat16_rn(v0);
-            *reinterpret_cast<uint32_t*>(row) = pack_bf16x2(v1, v2);
-            row[2] = __float2bfloat16_rn(v3);
-          }
-        }
-      }
-      const int prev_frame = cur.frame;
-      cur.advance(); cur.advance(); cur.advance();
-      if (cur.frame != prev_frame) cur.ft = cur.frame % p.T;
-      if (cur.frame < p.frames) issue(cur);                 // next own stage's loads fly while builders work
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[slot]);
     }
   } else if (warp == 4) {
     // =============================================================== MMA issuer
@@ -299,15 +240,19 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
         if (m < p.Mf) {
           const int yy = m / p.Wo, xx = m - yy * p.Wo;
           uint8_t* dst = ring + (yy & ring_mask) * row_bytes + xx * 128;
+          const float4* c4 = reinterpret_cast<const float4*>(chan);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = ch * 8 + i;
-              const float a = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]);
-              const float z = fmaf(a, chan[c], chan[64 + c]);
-              v[i] = z > 0.f ? z : z * chan[128 + c];
+            for (int h = 0; h < 2; ++h) {
+              const float4 sc = c4[2 * ch + h], sh = c4[16 + 2 * ch + h], sl = c4[32 + 2 * ch + h];
+              const int c = ch * 8 + 4 * h;
+              float z;
+              z = fmaf(__uint_as_float(c < 32 ? r0[c] : r1[c - 32]), sc.x, sh.x);         v[4 * h + 0] = z > 0.f ? z : z * sl.x;
+              z = fmaf(__uint_as_float(c < 32 ? r0[c + 1] : r1[c - 31]), sc.y, sh.y);     v[4 * h + 1] = z > 0.f ? z : z * sl.y;
+              z = fmaf(__uint_as_float(c < 32 ? r0[c + 2] : r1[c - 30]), sc.z, sh.z);     v[4 * h + 2] = z > 0.f ? z : z * sl.z;
+              z = fmaf(__uint_as_float(c < 32 ? r0[c + 3] : r1[c - 29]), sc.w, sh.w);     v[4 * h + 3] = z > 0.f ? z : z * sl.w;
             }
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -320,36 +265,40 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
         const int m_end = min((tile + 1) * 128, p.Mf);
         const int rows_complete = m_end / p.Wo;               // conv rows 0 .. rows_complete-1 are final
         const int py_ready = rows_complete / 2;               // needs conv row 2*py+1 <= rows_complete-1
-        const int items = (py_ready - py_done) * p.Wp * 8;
-        for (int it = et; it < items; it += 128) {
-          const int ch = it & 7;
-          const int pix = it >> 3;
-          const int pyo = pix / p.Wp, px = pix - pyo * p.Wp;
-          const int py = py_done + pyo;
-          __nv_bfloat162 best[4];
-          bool first = true;
+        for (int py = py_done; py < py_ready; ++py) {
+          const int cy0 = max(2 * py - 1, 0);                  // clamped rows/cols repeat an element: max unchanged
+          const uint8_t* r0p = ring + (cy0 & ring_mask) * row_bytes;
+          const uint8_t* r1p = ring + ((2 * py) & ring_mask) * row_bytes;
+          const uint8_t* r2p = ring + ((2 * py + 1) & ring_mask) * row_bytes;
+          for (int it = et; it < p.Wp * 8; it += 128) {
+            const int ch = it & 7, px = it >> 3;
+            const int cx1 = 2 * px, cx2 = cx1 + 1, cx0 = max(cx1 - 1, 0);
+            const int o0 = cx0 * 128 + ((ch ^ (cx0 & 7)) << 4);
+            const int o1 = cx1 * 128 + ((ch ^ (cx1 & 7)) << 4);
+            const int o2 = cx2 * 128 + ((ch ^ (cx2 & 7)) << 4);
+            uint4 v[9];
+            v[0] = *reinterpret_cast<const uint4*>(r0p + o0); v[1] = *reinterpret_cast<const uint4*>(r0p + o1);
+            v[2] = *reinterpret_cast<const uint4*>(r0p + o2); v[3] = *reinterpret_cast<const uint4*>(r1p + o0);
+            v[4] = *reinterpret_cast<const uint4*>(r1p + o1); v[5] = *reinterpret_cast<const uint4*>(r1p + o2);
+            v[6] = *reinterpret_cast<const uint4*>(r2p + o0); v[7] = *reinterpret_cast<const uint4*>(r2p + o1);
+            v[8] = *reinterpret_cast<const uint4*>(r2p + o2);
+            __nv_bfloat162 best[4];
 #pragma unroll
-          for (int dy = -1; dy <= 1; ++dy) {
-            const int cy = 2 * py + dy;
-            if (cy < 0) continue;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-              const int cx = 2 * px + dx;
-              if (cx < 0) continue;
-              const uint4 v = *reinterpret_cast<const uint4*>(ring + (cy & ring_mask) * row_bytes + cx * 128 +
-                                                              ((ch ^ (cx & 7)) << 4));
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-              if (first) {
-                best[0] = h[0]; best[1] = h[1]; best[2] = h[2]; best[3] = h[3];
-                first = false;
-              } else {
-                best[0] = __hmax2(best[0], h[0]); best[1] = __hmax2(best[1], h[1]);
-                best[2] = __hmax2(best[2], h[2]); best[3] = __hmax2(best[3], h[3]);
-              }
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat162 m01 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[0])[q],
+                                           reinterpret_cast<const __nv_bfloat162*>(&v[1])[q]);
+              __nv_bfloat162 m23 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[2])[q],
+                                           reinterpret_cast<const __nv_bfloat162*>(&v[3])[q]);
+              __nv_bfloat162 m45 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[4])[q],
+                                           reinterpret_cast<const __nv_bfloat162*>(&v[5])[q]);
+              __nv_bfloat162 m67 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[6])[q],
+                                           reinterpret_cast<const __nv_bfloat162*>(&v[7])[q]);
+              best[q] = __hmax2(__hmax2(__hmax2(m01, m23), __hmax2(m45, m67)),
+                                reinterpret_cast<const __nv_bfloat162*>(&v[8])[q]);
             }
+            *reinterpret_cast<uint4*>(yframe + ((size_t)py * p.Wp + px) * 64 + ch * 8) =
+                *reinterpret_cast<const uint4*>(best);
           }
-          *reinterpret_cast<uint4*>(yframe + ((size_t)py * p.Wp + px) * 64 + ch * 8) =
-              *reinterpret_cast<const uint4*>(best);
         }
         py_done = py_ready;
         named_bar_sync(2, 128);
@@ -365,16 +314,57 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const StemParams p)
   }
 }
 
+// Pre-pass (HBM-bound, ~0.03 ms per 64 utterances): uint8 crops (x/255, centre crop, (x-mean)/std fused;
+// models/video_models/dataloaders.py:19-24) or normalised f32 frames -> zero-bordered bf16 frames
+// xp (B*T, H+8, pitch): row iy+3, column ix+3.  One thread writes 8 consecutive columns (16 B).
+__global__ void stem_prepass_kernel(const void* __restrict__ x, int is_u8, int frames, int H, int W, int Hraw,
+                                    int Wraw, int dh, int dw, float u8_scale, float u8_bias, int rows, int pitch,
+                                    uint16_t* __restrict__ xp) {
+  const int groups = pitch >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)frames * rows * groups) return;
+  const int g = (int)(idx % groups);
+  const long long t = idx / groups;
+  const int row = (int)(t % rows);
+  const long long f = t / rows;
+  const int iy = row - 3;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ix = g * 8 + j - 3;
+    float val = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (is_u8) {
+        const uint8_t u = __ldg(static_cast<const uint8_t*>(x) + ((size_t)f * Hraw + (iy + dh)) * Wraw + (ix + dw));
+        val = fmaf((float)u, u8_scale, u8_bias);
+      } else {
+        val = __ldg(static_cast<const float*>(x) + ((size_t)f * H + iy) * W + ix);
+      }
+    }
+    v[j] = val;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(xp + ((size_t)f * rows + row) * pitch + g * 8) = o;
+}
+
 }  // namespace dl
+
+extern "C" long long dl_stem_workspace_bytes(int B, int T, int H, int W) {
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0) return 0;
+  const long long pitch = (W + 8 + 7) / 8 * 8;
+  return (long long)B * T * (H + 8) * pitch * 2;
+}
 
 extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
                                             float mean, float std, const void* w_packed, const float* scale,
                                             const float* shift, const float* slope, void* y, int out_img_rows,
-                                            void* stream) {
+                                            void* workspace, void* stream) {
   using namespace dl;
-  DL_CHECK_ARG(x && w_packed && scale && shift && slope && y, "stem: null pointer");
+  DL_CHECK_ARG(x && w_packed && scale && shift && slope && y && workspace, "stem: null pointer");
   DL_CHECK_ARG(B > 0 && T > 0, "stem: empty batch");
-  DL_CHECK_ARG(H >= 8 && W >= 32 && H % 4 == 0 && W % 4 == 0 && W <= 116, "stem: H, W must be multiples of 4, 32 <= W <= 116");
+  DL_CHECK_ARG(H >= 8 && W >= 32 && H % 4 == 0 && W % 4 == 0 && W <= 120, "stem: H, W must be multiples of 4, 32 <= W <= 120");
   if (is_u8) {
     DL_CHECK_ARG(Hraw >= H && Wraw >= W && std != 0.f, "stem: raw crop smaller than the centre crop");
   }
@@ -382,16 +372,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   if (st != DL_OK) return st;
 
   StemParams p;
-  p.x = x;
-  p.B = B; p.T = T; p.H = H; p.W = W; p.Hraw = Hraw; p.Wraw = Wraw;
-  // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
-  p.dh = is_u8 ? (Hraw - H) / 2 : 0;
-  p.dw = is_u8 ? (Wraw - W) / 2 : 0;
-  p.u8_scale = is_u8 ? 1.0f / (255.0f * std) : 1.0f;
-  p.u8_bias = is_u8 ? -mean / std : 0.0f;
-  if (is_u8) {
-    DL_CHECK_ARG(Wraw % 4 == 0 && p.dw % 4 == 0, "stem: u8 crops need Wraw and the crop offset to be multiples of 4");
-  }
+  p.B = B; p.T = T; p.H = H; p.W = W;
   p.Ho = H / 2; p.Wo = W / 2; p.Hp = H / 4; p.Wp = W / 4;
   p.Mf = p.Ho * p.Wo;
   p.tiles_per_frame = (p.Mf + 127) / 128;
@@ -400,31 +381,48 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   while (rr < span + 6) rr <<= 1;
   p.ring_rows = rr;
   p.strip_rows = 2 * span + 7;
-  p.strip_pitch = W + 12;
-  DL_CHECK_ARG(p.strip_rows <= kStripRowsMax && W / 4 + 2 < 32, "stem: needs 32 <= W <= 116");
+  p.strip_pitch = (W + 8 + 7) / 8 * 8;
+  DL_CHECK_ARG(p.strip_rows <= kStripRowsMax, "stem: frame too narrow (strip of %d rows)", p.strip_rows);
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.y = static_cast<uint16_t*>(y);
   p.frames = B * T;
   p.out_img_rows = out_img_rows > 0 ? out_img_rows : p.Hp;
   DL_CHECK_ARG(p.out_img_rows >= p.Hp, "stem: out_img_rows < H/4");
+  DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
+
+  cudaStream_t cs = (cudaStream_t)stream;
+  // ---- pre-pass: normalise + zero-border into the caller's workspace
+  const int rows = H + 8, pitch = p.strip_pitch;
+  // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
+  const int dh = is_u8 ? (Hraw - H) / 2 : 0, dw = is_u8 ? (Wraw - W) / 2 : 0;
+  {
+    const long long n = (long long)p.frames * rows * (pitch / 8);
+    stem_prepass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
+        x, is_u8, p.frames, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f,
+        rows, pitch, static_cast<uint16_t*>(workspace));
+    st = check_launch("stem_prepass_kernel");
+    if (st != DL_OK) return st;
+  }
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
-                      kStripSlots * (size_t)((strip_elems + 7) & ~7) * 2 + 192 * 4 + 32 * 8 + 16 + 64 * 4;
-  DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
+                      kStripSlots * (size_t)((strip_elems + 63) & ~63) * 2 + 192 * 4 + 32 * 8 + 16 + 64 * 4;
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
-  CUtensorMap mapW;
+  CUtensorMap mapW, mapX;
   st = make_tiled_2d_bf16(&mapW, w_packed, 64, 320, 320, 64, 64);
+  if (st != DL_OK) return st;
+  st = make_tiled_4d_bf16_noswizzle(&mapX, workspace, (uint64_t)pitch, (uint64_t)rows, (uint64_t)T, (uint64_t)B,
+                                    (uint32_t)pitch, (uint32_t)p.strip_rows);
   if (st != DL_OK) return st;
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.frames < grid) grid = p.frames;
-  const bool small = p.strip_rows <= 13;      // strip rows per stage: 13 (GRID 88x88) or up to 24
-  void (*kern)(const CUtensorMap, const StemParams) =
-      is_u8 ? (small ? stem_conv3d_kernel<true, 13> : stem_conv3d_kernel<true, 24>)
-            : (small ? stem_conv3d_kernel<false, 13> : stem_conv3d_kernel<false, 24>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
-  kern<<<grid, kStemThreads, smem, (cudaStream_t)stream>>>(mapW, p);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  stem_conv3d_kernel<<<grid, kStemThreads, smem, cs>>>(mapW, mapX, p);
   return check_launch("stem_conv3d_kernel");
 }

@@ -24,6 +24,20 @@ def _need_cuda(*ts):
             raise RuntimeError('deeplip_b200 ops need CUDA tensors (there is no CPU fallback)')
 
 
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    """Per-device scratch the C ABI asks the caller to own (grown on demand, reused across calls on the
+    same stream)."""
+    key = str(device)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
 def ceil_to(x, m):
     return (x + m - 1) // m * m
 
@@ -82,9 +96,10 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
         y = out
         assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.shape[0] == B * T and \
             y.shape[1] >= H // 4 and y.shape[2] == W // 4 and y.shape[3] == 64
+    ws = _workspace(x.device, _lib.lib().dl_stem_workspace_bytes(B, T, H, W))
     st = _lib.lib().dl_stem_conv3d_bn_prelu_pool(_ptr(x), is_u8, B, T, H, W, Hraw, Wraw, float(mean), float(std),
                                                  _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope), _ptr(y),
-                                                 y.shape[1], _stream())
+                                                 y.shape[1], _ptr(ws), _stream())
     _lib.check(st, 'dl_stem_conv3d_bn_prelu_pool')
     return y
 
