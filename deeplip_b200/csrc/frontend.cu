@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
                                                               const int32_t* __restrict__ lengths, int nsamp, int T,
                                                               FrontendTables tb, float* __restrict__ feat) {
   __shared__ float2 buf[8][kNfft];
+  __shared__ float2 tw[kNfft / 2];        // twiddles staged in shared memory: lanes index them divergently, which the
+                                          // constant cache would serialise 32-fold
   __shared__ float logmel[8][kMaxFilt];
   __shared__ float dctm[kMaxFilt * 26];   // DCT rows (ncep x 26 filters), mfcc only
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -38,6 +40,7 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
   const int t = blockIdx.x * 8 + warp;
   const int F = tb.ncep;
 
+  for (int i = threadIdx.x; i < kNfft / 2; i += 256) tw[i] = c_twiddle[i];
   if (tb.kind == 0) {
     // scipy dct(type=2, norm='ortho') rows with the cepstral lifter (L=22) folded in
     const int nf = tb.nfilt;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
     for (int i = lane; i < kNfft / 2; i += 32) {
       const int grp = i >> st, pos = i & (half - 1);
       const int i0 = (grp << (st + 1)) + pos, i1 = i0 + half;
-      const float2 w = c_twiddle[pos << (8 - st)];
+      const float2 w = tw[pos << (8 - st)];
       const float2 a = z[i0], c = z[i1];
       const float2 m = make_float2(c.x * w.x - c.y * w.y, c.x * w.y + c.y * w.x);
       z[i0] = make_float2(a.x + m.x, a.y + m.y);
