@@ -228,12 +228,11 @@ def run_ours(args, rank, world, local):
     for i in range(2):
         step(i, from_host=True)
     ms_e2e, _ = timed(args.steps, from_host=True)
-    if rank == 0 and args.steps * (ms + ms_e2e) / args.steps < 1500:      # keep the GPU busy >= ~1 s for the sampler
-        t_end = time.time() + 1.0
-        i = 0
-        while time.time() < t_end:
-            step(i); i += 1
-        torch.cuda.synchronize()
+    # keep every GPU busy for ~1 s more so the clock sampler sees the loaded state (same count on all ranks:
+    # step() contains the collective)
+    for i in range(max(0, int(1000.0 / max(ms / args.steps, 0.05)) - 2 * args.steps)):
+        step(i)
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     e2e = args.steps * n_total / (ms_e2e / 1e3)
     h2d = B * (T_FRAMES * RAW_HW * RAW_HW + NSAMP * 4)
