@@ -63,6 +63,62 @@ class AVExtractor:
         return self.fuse(xv, em)
 
 
+class HostPipeline:
+    """End-to-end extraction from pinned HOST buffers with the H2D copy of batch i+1 overlapped with the
+    kernels of batch i (copy stream + events, two device staging slots) and the D2H of the fused
+    embeddings issued asynchronously into pinned memory.  This is the call a user with data on the host
+    makes; the reference does one blocking `.to(device)` per clip (train_fusion.py:388, 399)."""
+
+    def __init__(self, extractor, device='cuda', slots=2):
+        self.ex = extractor
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = slots
+        self._stage = [None] * slots
+        self._ready = [torch.cuda.Event() for _ in range(slots)]
+        self._free = [torch.cuda.Event() for _ in range(slots)]
+
+    def _upload(self, k, wav_h, vid_h):
+        slot = k % self.slots
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._free[slot])          # kernels that read this slot are done
+            st = self._stage[slot]
+            if st is None or st[0].shape != wav_h.shape or st[1].shape != vid_h.shape or st[1].dtype != vid_h.dtype:
+                st = (torch.empty(wav_h.shape, dtype=wav_h.dtype, device=self.device),
+                      torch.empty(vid_h.shape, dtype=vid_h.dtype, device=self.device))
+                self._stage[slot] = st
+            st[0].copy_(wav_h, non_blocking=True)
+            st[1].copy_(vid_h, non_blocking=True)
+            self._ready[slot].record(self.copy_stream)
+
+    def run(self, batches, post=None):
+        """batches: sequence of (wav_host (B,nsamp) f32 pinned, video_host (B,T,H,W) u8/f32 pinned).
+        Returns the list of fused embeddings as pinned host tensors (valid after the final synchronize,
+        which this method performs)."""
+        batches = list(batches)
+        main = torch.cuda.current_stream(self.device)
+        for ev in self._free:
+            ev.record(main)
+        outs = []
+        if batches:
+            self._upload(0, *batches[0])
+        for k in range(len(batches)):
+            slot = k % self.slots
+            if k + 1 < len(batches):
+                self._upload(k + 1, *batches[k + 1])
+            main.wait_event(self._ready[slot])
+            wav_d, vid_d = self._stage[slot]
+            emb = self.ex.extract(wav_d, vid_d)
+            self._free[slot].record(main)
+            if post is not None:
+                emb = post(emb)
+            h = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
+            h.copy_(emb, non_blocking=True)
+            outs.append(h)
+        torch.cuda.synchronize(self.device)
+        return outs
+
+
 def build_models(device='cuda', audio_arch='etdnn', pooling='statistic', seed=1, randomize=True):
     """Random-init (seeded) audio + video drop-in models in eval mode, as bench/tests use them."""
     from . import synth

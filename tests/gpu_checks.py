@@ -460,5 +460,11 @@ def pipeline_case(B=4, T=8, nsamp=24000, seed=1):
     alone = ex.extract(torch.from_numpy(wav2[1:2, :nsamp - 5000]).to(DEV), raw_f[1:2, :T - 3].contiguous().to(DEV))
     torch.cuda.synchronize()
     out['ragged_abs'] = float((rag[1] - alone[0]).abs().max())
+    # host pipeline (pinned host buffers, H2D overlapped with compute) == direct device call
+    from deeplip_b200.pipeline import HostPipeline
+    hw, hv = torch.from_numpy(wav).pin_memory(), torch.from_numpy(raw).pin_memory()
+    outs = HostPipeline(ex, DEV).run([(hw, hv), (hw, hv), (hw, hv)])
+    out['host_pipeline_abs'] = max(float((o.to(DEV) - got).abs().max()) for o in outs)
+    assert out['host_pipeline_abs'] == 0.0, out
     assert out['emb_cos_min'] > 0.999 and out['score_abs'] < 1e-3 and out['ragged_abs'] < 1e-5, out
     return out
