@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libdeeplip_b200.so')
-SOURCES = ['dl_host.cu', 'igemm_conv.cu', 'conv3x3_halo.cu', 'stem_conv3d.cu', 'frontend.cu', 'pool_fuse_score.cu']
+SOURCES = ['dl_host.cu', 'igemm_conv.cu', 'igemm2_conv.cu', 'conv3x3_halo.cu', 'stem_conv3d.cu', 'frontend.cu', 'pool_fuse_score.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

@@ -19,6 +19,7 @@ struct FrontendTables {
   int ncep;                  // number of coefficients written (F)
   int kind;                  // 0 mfcc, 1 fbank, 2 logfbank
   int bins[kMaxFilt + 2];    // FFT-bin edges of the triangular filters
+  float inv_width[kMaxFilt + 1];   // 1 / (bins[j+1] - bins[j])
 };
 
 __constant__ float2 c_twiddle[kNfft / 2];   // exp(-2 pi i k / 512)
@@ -106,8 +107,9 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
   for (int j = lane; j < tb.nfilt; j += 32) {
     const int b0 = tb.bins[j], b1 = tb.bins[j + 1], b2 = tb.bins[j + 2];
     float s = 0.f;
-    for (int i = b0; i < b1; ++i) s = fmaf(z[i].x, (float)(i - b0) / (float)(b1 - b0), s);
-    for (int i = b1; i < b2; ++i) s = fmaf(z[i].x, (float)(b2 - i) / (float)(b2 - b1), s);
+    const float up = tb.inv_width[j], dn = tb.inv_width[j + 1];
+    for (int i = b0; i < b1; ++i) s = fmaf(z[i].x, (float)(i - b0) * up, s);
+    for (int i = b1; i < b2; ++i) s = fmaf(z[i].x, (float)(b2 - i) * dn, s);
     if (s == 0.f) s = 2.220446049250313e-16f;
     logmel[warp][j] = (tb.kind == 1) ? s : logf(s);
   }
@@ -199,6 +201,10 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
   for (int i = 0; i < nfilt + 2; ++i) {
     const double mel = lo + (hi - lo) * (double)i / (double)(nfilt + 1);
     tb.bins[i] = (int)floor((kNfft + 1) * mel2hz(mel) / 16000.0);
+  }
+  for (int i = 0; i < nfilt + 1; ++i) {
+    const int w = tb.bins[i + 1] - tb.bins[i];
+    tb.inv_width[i] = w > 0 ? 1.0f / (float)w : 0.0f;
   }
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid((T + 7) / 8, B);

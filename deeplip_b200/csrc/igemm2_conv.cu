@@ -1,0 +1,211 @@
+// Implicit-GEMM convolution on CTA pairs (tcgen05 cta_group::2): two SMs of one TPC compute a 256-row x BLOCK_N
+// tile together.  Each CTA TMA-im2col-loads its own 128 output pixels of operand A and only HALF of the weight
+// tile (operand B); the leader CTA issues one M=256 tcgen05.mma that reads A and the B halves from both CTAs'
+// shared memory and writes each CTA's 128 accumulator rows into its own tensor memory.
+//
+// Why: measured on B200 the tensor pipe's shared-memory operand fetch sustains ~60 B/cycle/SM; a single-CTA
+// 128 x 256 x 16 MMA needs 12 KB (A 4 KB + B 8 KB) -> ~190 cycles against a 128-cycle math floor (67 %), and the
+// 128 x 128 tile only reaches 50 %.  Halving B per SM brings N=256 to the math floor and N=128 to 67 %.
+//
+// Same TMA im2col producer / TMEM double buffering / fused epilogue as igemm_conv.cu; barriers of the pair:
+//   full[s]   (leader)      : 2 arrivals (each CTA's producer) + all TMA bytes of both CTAs
+//   empty[s]  (both)        : tcgen05.commit multicast
+//   tfull[a]  (both)        : tcgen05.commit multicast
+//   tempty[a] (leader)      : 512 arrivals (epilogue threads of both CTAs, the peer's via the cluster window)
+#include <cuda_runtime.h>
+#include "igemm_common.cuh"
+
+namespace dl {
+
+template <int BLOCK_N>
+struct Igemm2Cfg {
+  static constexpr int A_BYTES = 128 * 64 * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int PARAM_BYTES = 3 * kMaxCout * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+  static constexpr int THREADS = 320;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const IgemmParams p) {
+  using Cfg = Igemm2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* prm = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::PARAM_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int pair = (int)cluster_id_x();
+  const int num_pairs = (int)num_clusters_x();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full[s], 2);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(&tfull[0], 1);
+      mbar_init(&tfull[1], 1);
+      mbar_init(&tempty[0], 512);
+      mbar_init(&tempty[1], 512);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  if (p.y != nullptr) {
+    for (int c = threadIdx.x; c < p.Cout; c += Cfg::THREADS) {
+      prm[c] = p.scale[c];
+      prm[kMaxCout + c] = p.shift[c];
+      prm[2 * kMaxCout + c] = p.slope[c];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // super tiles: (pair of consecutive m blocks) x n block
+  const int num_m_pairs = (p.num_m_blocks + 1) >> 1;
+  const int total = num_m_pairs * p.num_n_blocks;
+  const int num_kb = p.R * p.S * p.cchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < total; t += num_pairs) {
+        const int mp = t / p.num_n_blocks;
+        const int n_blk = t - mp * p.num_n_blocks;
+        const int m0 = (2 * mp + (int)rank) * 128;
+        const int img = m0 / p.PQ;
+        const int rem = m0 - img * p.PQ;
+        const int pp = rem / p.Q;
+        const int qq = rem - pp * p.Q;
+        const int w0 = qq * p.stride_w - p.pad_w;
+        const int h0 = pp * p.stride_h - p.pad_h;
+        int kb = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              const uint32_t lbar = mapa_shared(smem_u32(&full[stage]), 0);       // the leader's barrier
+              if (rank == 0) mbar_expect_tx_cluster(lbar, 2u * Cfg::STAGE_BYTES);
+              else mbar_arrive_cluster(lbar);
+              tma2_load_im2col_4d(sa, &mapA, lbar, cc * 64, w0, h0, img, (uint16_t)(s * p.dil_w),
+                                  (uint16_t)(r * p.dil_h));
+              tma2_load_2d(sa + Cfg::A_BYTES, &mapB, lbar, kb * 64, n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < total; t += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128_kmajor(sa);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma2_commit_both(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_both(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const bool has_res = p.residual != nullptr;
+    const bool fast = p.y != nullptr && p.yf == nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < total; t += num_pairs) {
+      const int mp = t / p.num_n_blocks;
+      const int n_blk = t - mp * p.num_n_blocks;
+      const long long row = (long long)(2 * mp + (int)rank) * 128 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int cbase = n_blk * BLOCK_N;
+      uint4 res[4];
+      igemm_prefetch_residual(p, row, row_ok, cbase, chunk0, has_res, res);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      igemm_epilogue_tile<BLOCK_N>(p, prm, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
+                                   res);
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));     // the leader's MMA thread waits on this
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // nobody leaves (or frees TMEM) while the peer may still touch this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, cudaStream_t stream) {
+  using Cfg = Igemm2Cfg<BLOCK_N>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(DL_ERR_CUDA, "igemm2 smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int super_tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
+  int pairs = device_sm_count() / 2;
+  if (pairs <= 0) pairs = 74;
+  if (super_tiles < pairs) pairs = super_tiles;
+  igemm2_conv_kernel<BLOCK_N><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+  return check_launch("igemm2_conv_kernel");
+}
+
+// Called by dl_conv_igemm_bf16 (igemm_conv.cu) for wide, large-M problems.
+int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
+                      cudaStream_t stream) {
+  return block_n == 128 ? launch_igemm2<128>(mapA, mapB, p, stream) : launch_igemm2<256>(mapA, mapB, p, stream);
+}
+
+}  // namespace dl

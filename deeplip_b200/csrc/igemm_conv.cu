@@ -14,30 +14,11 @@
 //                              side output) -- overlapped with the next tile's MMAs.
 //
 // Roofline: tensor pipe.  Algorithmic work = 2 * M * Cout * R*S*C flop per launch (DESIGN.md "Kernels").
-#include "dl_host.cuh"
-#include "dl_ptx.cuh"
+#include "igemm_common.cuh"
 
 namespace dl {
 
-struct IgemmParams {
-  int M, P, Q, PQ;
-  int Cout;
-  int cchunks, R, S;
-  int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
-  int num_m_blocks, num_n_blocks;
-  int ldy, ldf;
-  float f32_slope;
-  const float* scale;
-  const float* shift;
-  const float* slope;
-  const float* scale2;
-  const float* shift2;
-  const uint16_t* residual;
-  uint16_t* y;
-  float* yf;
-};
 
-constexpr int kMaxCout = 2048;   // per-channel epilogue parameters staged in shared memory
 
 constexpr int kResidentBBytes = 72 * 1024;   // whole packed weight matrix kept in shared memory when it fits
 
@@ -198,112 +179,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       // residual of this warp's first chunk: requested BEFORE waiting for the accumulator so the L2 round trip
       // overlaps the tile's MMAs
       uint4 res[4];
-      {
-        const int c0 = cbase + chunk0 * 32;
-        if (has_res && row_ok && c0 + 32 <= p.Cout) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) res[g] = __ldg(rp + g);
-        }
-      }
+      igemm_prefetch_residual(p, row, row_ok, cbase, chunk0, has_res, res);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int j = chunk0; j < BLOCK_N / 32; j += 2) {
-        const int c0 = cbase + j * 32;
-        if (c0 >= p.Cout) break;
-        uint32_t acc_r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + j * 32, acc_r);
-        const bool full_chunk = c0 + 32 <= p.Cout;
-        if (fast && full_chunk) {
-          // ---- straight-line path: parameters from shared memory, residual already in registers
-          uint4 res_cur[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) res_cur[g] = res[g];
-          if (has_res && row_ok && j + 2 < BLOCK_N / 32 && c0 + 96 <= p.Cout) {     // prefetch the next chunk's
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c0 + 64);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) res[g] = __ldg(rp + g);
-          }
-          tmem_ld_wait();
-          const float4* sc = reinterpret_cast<const float4*>(prm + c0);
-          const float4* sh = reinterpret_cast<const float4*>(prm + kMaxCout + c0);
-          const float4* sl = reinterpret_cast<const float4*>(prm + 2 * kMaxCout + c0);
-          uint4 o[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float v[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 s4 = sc[2 * g + h], h4 = sh[2 * g + h];
-              v[4 * h + 0] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 0]), s4.x, h4.x);
-              v[4 * h + 1] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 1]), s4.y, h4.y);
-              v[4 * h + 2] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 2]), s4.z, h4.z);
-              v[4 * h + 3] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 3]), s4.w, h4.w);
-            }
-            if (has_res) {
-              const uint4 rr = res_cur[g];
-              v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-              v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 l4 = sl[2 * g + h];
-              v[4 * h + 0] = v[4 * h + 0] > 0.f ? v[4 * h + 0] : v[4 * h + 0] * l4.x;
-              v[4 * h + 1] = v[4 * h + 1] > 0.f ? v[4 * h + 1] : v[4 * h + 1] * l4.y;
-              v[4 * h + 2] = v[4 * h + 2] > 0.f ? v[4 * h + 2] : v[4 * h + 2] * l4.z;
-              v[4 * h + 3] = v[4 * h + 3] > 0.f ? v[4 * h + 3] : v[4 * h + 3] * l4.w;
-            }
-            o[g].x = pack_bf16x2(v[0], v[1]); o[g].y = pack_bf16x2(v[2], v[3]);
-            o[g].z = pack_bf16x2(v[4], v[5]); o[g].w = pack_bf16x2(v[6], v[7]);
-          }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.y + row * p.ldy + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) dst[g] = o[g];
-          }
-        } else {
-          // ---- general path: partial chunk and / or fp32 side output (heads, attention logits)
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int c = c0 + g * 8;
-              if (c >= p.Cout) continue;
-              float a[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(acc_r[g * 8 + i]);
-              if (p.yf != nullptr) {
-                float o[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  o[i] = p.scale2 != nullptr ? fmaf(a[i], __ldg(p.scale2 + c + i), __ldg(p.shift2 + c + i)) : a[i];
-                  o[i] = o[i] > 0.f ? o[i] : o[i] * p.f32_slope;
-                }
-                float4* dst = reinterpret_cast<float4*>(p.yf + row * p.ldf + c);
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-              }
-              if (p.y != nullptr) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaf(a[i], prm[c + i], prm[kMaxCout + c + i]);
-                if (has_res) {
-                  const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c));
-                  v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                  v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * prm[2 * kMaxCout + c + i];
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(p.y + row * p.ldy + c) = o;
-              }
-            }
-          }
-        }
-      }
+      igemm_epilogue_tile<BLOCK_N>(p, prm, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
+                                   res);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       acc ^= 1;
@@ -338,6 +218,9 @@ static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
   igemm_conv_kernel<BLOCK_N, kResB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
   return check_launch("igemm_conv_kernel");
 }
+
+int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
+                      cudaStream_t stream);   // igemm2_conv.cu
 
 }  // namespace dl
 
@@ -394,12 +277,21 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   st = make_im2col_nhwc_bf16(&mapA, x, d->N, d->H, d->W, d->C, d->ldx, img_rows, d->R, d->S, d->stride_h, d->stride_w, d->pad_h,
                              d->pad_w, d->dil_h, d->dil_w, 64, 128);
   if (st != DL_OK) return st;
-  st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot, (uint32_t)block_n, 64);
+  const long long num_kb = (long long)d->R * d->S * p.cchunks;
+  const bool resident = p.num_n_blocks == 1 && num_kb * block_n * 128 <= kResidentBBytes;
+  // CTA pairs (cta_group::2) for wide tiles on problems large enough to fill the chip twice over
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* env = getenv("DL_USE_2CTA");
+    use_pair = (env == nullptr || atoi(env) != 0) ? 1 : 0;
+  }
+  const bool pair = use_pair && block_n >= 128 && !resident && p.num_m_blocks >= 256;
+  st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot,
+                          (uint32_t)(pair ? block_n / 2 : block_n), 64);
   if (st != DL_OK) return st;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const long long num_kb = (long long)d->R * d->S * p.cchunks;
-  const bool resident = p.num_n_blocks == 1 && num_kb * block_n * 128 <= kResidentBBytes;
+  if (pair) return launch_igemm_pair(mapA, mapB, p, block_n, s);
   switch (block_n) {
     case 64: return resident ? launch_igemm<64, true>(mapA, mapB, p, s) : launch_igemm<64, false>(mapA, mapB, p, s);
     case 128: return resident ? launch_igemm<128, true>(mapA, mapB, p, s) : launch_igemm<128, false>(mapA, mapB, p, s);

@@ -140,26 +140,26 @@ __global__ void attn_logits_kernel(const float* __restrict__ hf, int rows, int H
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-frame spatial mean, then mean over the valid frames of each utterance.  One block per utterance
-// and 64-channel... (C/8 threads cover the channels; thread groups stride over frames).
+// Per-frame spatial mean, then mean over the valid frames of each utterance.  Block = (utterance, 64-channel
+// slab): 8 channel-threads (8 channels = 16 B each) x 32 frame groups; deterministic smem reduction.
 __global__ void __launch_bounds__(256) frame_pool_kernel(const uint16_t* __restrict__ x, int T, int HW, int C,
                                                          const int32_t* __restrict__ lengths,
                                                          float* __restrict__ frame_feats,
                                                          float* __restrict__ utt_mean) {
-  extern __shared__ float sm[];   // groups x C partial sums
+  __shared__ float sm[32][64];
   const int b = blockIdx.x;
-  const int tpg = C / 8;                       // threads per group (one thread = 8 channels)
-  const int groups = blockDim.x / tpg;
-  const int g = threadIdx.x / tpg, ct = threadIdx.x % tpg;
+  const int cb = blockIdx.y * 64;
+  const int ct = threadIdx.x & 7, g = threadIdx.x >> 3;
+  const int c = cb + ct * 8;
   int len = lengths ? lengths[b] : T;
   len = max(1, min(len, T));
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const float inv_hw = 1.f / (float)HW;
-  if (g < groups) {
-    for (int t = g; t < T; t += groups) {
-      const uint16_t* xf = x + ((size_t)(b * T + t) * HW) * C + ct * 8;
+  if (c < C) {
+    for (int t = g; t < T; t += 32) {
+      const uint16_t* xf = x + ((size_t)(b * T + t) * HW) * C + c;
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int px = 0; px < HW; ++px) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(xf + (size_t)px * C));
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) frame_pool_kernel(const uint16_t* __restr
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] *= inv_hw;
       if (frame_feats) {
-        float4* o = reinterpret_cast<float4*>(frame_feats + ((size_t)b * T + t) * C + ct * 8);
+        float4* o = reinterpret_cast<float4*>(frame_feats + ((size_t)b * T + t) * C + c);
         o[0] = make_float4(f[0], f[1], f[2], f[3]);
         o[1] = make_float4(f[4], f[5], f[6], f[7]);
       }
@@ -178,16 +178,14 @@ __global__ void __launch_bounds__(256) frame_pool_kernel(const uint16_t* __restr
         for (int i = 0; i < 8; ++i) acc[i] += f[i];
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sm[g * C + ct * 8 + i] = acc[i];
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[g][ct * 8 + i] = acc[i];
   __syncthreads();
-  if (utt_mean) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = 0.f;
-      for (int gg = 0; gg < groups; ++gg) s += sm[gg * C + c];
-      utt_mean[(size_t)b * C + c] = s / (float)len;
-    }
+  if (utt_mean && threadIdx.x < 64 && cb + threadIdx.x < C) {
+    float s = 0.f;
+    for (int gg = 0; gg < 32; ++gg) s += sm[gg][threadIdx.x];
+    utt_mean[(size_t)b * C + cb + threadIdx.x] = s / (float)len;
   }
 }
 
@@ -420,12 +418,9 @@ extern "C" int dl_frame_pool_temporal_mean(const void* x, int B, int T, int HW, 
                                            float* frame_feats, float* utt_mean, void* stream) {
   DL_CHECK_ARG(x && (frame_feats || utt_mean), "frame_pool: null pointer");
   DL_CHECK_ARG(B > 0 && T > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 2048, "frame_pool: bad shape");
-  const int tpg = C / 8;
-  int threads = (256 / tpg) * tpg;
-  if (threads == 0) threads = tpg;
-  const int groups = threads / tpg;
-  frame_pool_kernel<<<B, threads, groups * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const uint16_t*)x, T, HW, C, lengths, frame_feats, utt_mean);
+  dim3 grid(B, (C + 63) / 64);
+  frame_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, T, HW, C, lengths, frame_feats,
+                                                            utt_mean);
   return check_launch("frame_pool_kernel");
 }
 

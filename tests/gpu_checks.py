@@ -116,6 +116,9 @@ CONV_CASES = {
     'tdnn_k1_512_1500': dict(N=2, H=1, W=130, C=512, Cout=1500, R=1, S=1),
     'fc_3000_512': dict(N=5, H=1, W=1, C=3000, Cout=512, R=1, S=1, f32=True),
     'many_tiles': dict(N=64, H=22, W=22, C=64, Cout=64, R=3, S=3, stride=1, pad=1, residual=True),
+    'pair_128': dict(N=300, H=11, W=11, C=128, Cout=128, R=3, S=3, stride=1, pad=1, residual=True),
+    'pair_256_s2': dict(N=1101, H=11, W=11, C=128, Cout=256, R=3, S=3, stride=2, pad=1),
+    'pair_512_odd': dict(N=3700, H=3, W=3, C=256, Cout=512, R=3, S=3, stride=1, pad=1, residual=True),
 }
 
 
