@@ -11,7 +11,7 @@
 //   full[s]   (leader)      : 2 arrivals (each CTA's producer) + all TMA bytes of both CTAs
 //   empty[s]  (both)        : tcgen05.commit multicast
 //   tfull[a]  (both)        : tcgen05.commit multicast
-//   tempty[a] (leader)      : 512 arrivals (epilogue threads of both CTAs, the peer's via the cluster window)
+//   tempty[a] (leader)      : 16 arrivals (one per epilogue warp of both CTAs, the peer's via the cluster window)
 #include <cuda_runtime.h>
 #include "igemm_common.cuh"
 
@@ -64,8 +64,8 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
       mbar_init(&tfull[0], 1);
       mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], 512);
-      mbar_init(&tempty[1], 512);
+      mbar_init(&tempty[0], 16);
+      mbar_init(&tempty[1], 16);
       fence_mbar_init();
     }
     __syncwarp();
@@ -168,7 +168,8 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       igemm_epilogue_tile<BLOCK_N>(p, prm, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
                                    res);
       tc_fence_before();
-      mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));     // the leader's MMA thread waits on this
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // the leader's MMA thread waits
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
