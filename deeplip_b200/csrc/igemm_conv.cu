@@ -285,7 +285,7 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
     const char* env = getenv("DL_USE_2CTA");
     use_pair = (env == nullptr || atoi(env) != 0) ? 1 : 0;
   }
-  const bool pair = use_pair && block_n >= 128 && !resident && p.num_m_blocks >= 256;
+  const bool pair = use_pair && block_n >= 128 && !resident && p.num_m_blocks >= 128;
   st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot,
                           (uint32_t)(pair ? block_n / 2 : block_n), 64);
   if (st != DL_OK) return st;
