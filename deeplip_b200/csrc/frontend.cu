@@ -26,7 +26,7 @@ __constant__ float2 c_twiddle[kNfft / 2];   // exp(-2 pi i k / 512)
 
 __device__ __forceinline__ int bitrev9(int v) { return __brev((unsigned)v) >> 23; }
 
-// grid (ceil(T/8), B); block 256 = 8 warps, one frame per warp.  Writes raw (pre-CMVN) features to
+// grid (ceil(T/16), B); block 256 = 8 warps, two frames per warp (two-for-one real FFT).  Writes raw (pre-CMVN) features to
 // feat (B, F, T) f32.
 __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __restrict__ wav,
                                                               const int32_t* __restrict__ lengths, int nsamp, int T,
@@ -35,10 +35,11 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
   __shared__ float2 tw[kNfft / 2];        // twiddles staged in shared memory: lanes index them divergently, which the
                                           // constant cache would serialise 32-fold
   __shared__ float logmel[8][kMaxFilt];
+  __shared__ float logmel2[8][kMaxFilt];
   __shared__ float dctm[kMaxFilt * 26];   // DCT rows (ncep x 26 filters), mfcc only
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int t = blockIdx.x * 8 + warp;
+  const int t0 = (blockIdx.x * 8 + warp) * 2;       // this warp transforms frames t0 and t0+1 with ONE complex FFT
   const int F = tb.ncep;
 
   for (int i = threadIdx.x; i < kNfft / 2; i += 256) tw[i] = c_twiddle[i];
@@ -56,25 +57,36 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
 
   const int len = lengths ? min(lengths[b], nsamp) : nsamp;
   const int nfr = len <= kFrameLen ? 1 : 1 + (len - kFrameLen + kFrameStep - 1) / kFrameStep;
-  if (t >= T) return;
-  float* out = feat + (size_t)b * F * T + t;
-  if (t >= nfr) {   // padding frame of a ragged batch
-    for (int f = lane; f < F; f += 32) out[(size_t)f * T] = 0.f;
+  if (t0 >= T) return;
+  const bool has2 = t0 + 1 < T;
+  float* out = feat + (size_t)b * F * T + t0;
+  if (t0 >= nfr) {   // padding frames of a ragged batch
+    for (int f = lane; f < F; f += 32) {
+      out[(size_t)f * T] = 0.f;
+      if (has2) out[(size_t)f * T + 1] = 0.f;
+    }
     return;
   }
 
-  // ---- load + pre-emphasis + zero pad to 512, bit-reversed for the in-place DIT FFT
+  // ---- load + pre-emphasis + zero pad to 512, bit-reversed for the in-place DIT FFT.
+  // Two real frames ride one complex transform: z = x1 + i x2  =>  X1[k] = (Z[k] + conj Z[N-k]) / 2,
+  // X2[k] = (Z[k] - conj Z[N-k]) / (2i).
   const float* x = wav + (size_t)b * nsamp;
-  const int s0 = t * kFrameStep;
+  const int s0 = t0 * kFrameStep;
+  const bool live2 = t0 + 1 < nfr;
   float2* z = buf[warp];
   for (int i = lane; i < kNfft; i += 32) {
-    float v = 0.f;
-    const int s = s0 + i;
-    if (i < kFrameLen && s < len) {
-      const float cur = __ldg(x + s);
-      v = (s == 0) ? cur : cur - kPreemph * __ldg(x + s - 1);
+    float v1 = 0.f, v2 = 0.f;
+    if (i < kFrameLen) {
+      const int s = s0 + i;
+      if (s < len) {
+        const float cur = __ldg(x + s);
+        v1 = (s == 0) ? cur : cur - kPreemph * __ldg(x + s - 1);
+      }
+      const int s2 = s + kFrameStep;
+      if (live2 && s2 < len) v2 = __ldg(x + s2) - kPreemph * __ldg(x + s2 - 1);
     }
-    z[bitrev9(i)] = make_float2(v, 0.f);
+    z[bitrev9(i)] = make_float2(v1, v2);
   }
   __syncwarp();
   // ---- 9 radix-2 stages
@@ -92,37 +104,68 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
     }
     __syncwarp();
   }
-  // ---- power spectrum (257 bins) in place (x component), total energy
-  float e = 0.f;
-  for (int k = lane; k <= kNfft / 2; k += 32) {
-    const float2 c = z[k];
-    const float pw = (c.x * c.x + c.y * c.y) * (1.f / (float)kNfft);
-    e += pw;
-    z[k].x = pw;
+  // ---- split the two spectra; power (257 bins) of frame 1 / frame 2 into z[k].x / z[k].y; total energies
+  float e1 = 0.f, e2 = 0.f;
+  const float inv_n = 1.f / (float)kNfft;
+  for (int k = lane + 1; k < kNfft / 2; k += 32) {
+    const float2 a = z[k], c = z[kNfft - k];
+    const float x1r = 0.5f * (a.x + c.x), x1i = 0.5f * (a.y - c.y);
+    const float x2r = 0.5f * (a.y + c.y), x2i = 0.5f * (c.x - a.x);
+    const float p1 = (x1r * x1r + x1i * x1i) * inv_n, p2 = (x2r * x2r + x2i * x2i) * inv_n;
+    e1 += p1; e2 += p2;
+    z[k] = make_float2(p1, p2);
   }
-  e = warp_sum(e);
-  if (e == 0.f) e = 2.220446049250313e-16f;
+  if (lane == 0) {
+    const float2 a = z[0], c = z[kNfft / 2];
+    const float p10 = a.x * a.x * inv_n, p20 = a.y * a.y * inv_n;
+    const float p1n = c.x * c.x * inv_n, p2n = c.y * c.y * inv_n;
+    e1 += p10 + p1n; e2 += p20 + p2n;
+    z[0] = make_float2(p10, p20);
+    z[kNfft / 2] = make_float2(p1n, p2n);
+  }
+  e1 = warp_sum(e1); e2 = warp_sum(e2);
+  if (e1 == 0.f) e1 = 2.220446049250313e-16f;
+  if (e2 == 0.f) e2 = 2.220446049250313e-16f;
   __syncwarp();
-  // ---- mel filterbank: lane j <-> filter j (two passes when nfilt > 32)
+  // ---- mel filterbank: lane j <-> filter j (two passes when nfilt > 32), both frames at once
+  float* lm1 = logmel[warp];
+  float* lm2 = logmel2[warp];
   for (int j = lane; j < tb.nfilt; j += 32) {
     const int b0 = tb.bins[j], b1 = tb.bins[j + 1], b2 = tb.bins[j + 2];
-    float s = 0.f;
+    float s1 = 0.f, s2 = 0.f;
     const float up = tb.inv_width[j], dn = tb.inv_width[j + 1];
-    for (int i = b0; i < b1; ++i) s = fmaf(z[i].x, (float)(i - b0) * up, s);
-    for (int i = b1; i < b2; ++i) s = fmaf(z[i].x, (float)(b2 - i) * dn, s);
-    if (s == 0.f) s = 2.220446049250313e-16f;
-    logmel[warp][j] = (tb.kind == 1) ? s : logf(s);
+    for (int i = b0; i < b1; ++i) {
+      const float w = (float)(i - b0) * up;
+      const float2 pw = z[i];
+      s1 = fmaf(pw.x, w, s1); s2 = fmaf(pw.y, w, s2);
+    }
+    for (int i = b1; i < b2; ++i) {
+      const float w = (float)(b2 - i) * dn;
+      const float2 pw = z[i];
+      s1 = fmaf(pw.x, w, s1); s2 = fmaf(pw.y, w, s2);
+    }
+    if (s1 == 0.f) s1 = 2.220446049250313e-16f;
+    if (s2 == 0.f) s2 = 2.220446049250313e-16f;
+    lm1[j] = (tb.kind == 1) ? s1 : logf(s1);
+    lm2[j] = (tb.kind == 1) ? s2 : logf(s2);
   }
   __syncwarp();
   if (tb.kind == 0) {
     for (int n = lane; n < F; n += 32) {
-      float c = 0.f;
-      for (int j = 0; j < tb.nfilt; ++j) c = fmaf(dctm[n * tb.nfilt + j], logmel[warp][j], c);
-      if (n == 0) c = logf(e);          // appendEnergy=True
-      out[(size_t)n * T] = c;
+      float c1 = 0.f, c2 = 0.f;
+      for (int j = 0; j < tb.nfilt; ++j) {
+        const float d = dctm[n * tb.nfilt + j];
+        c1 = fmaf(d, lm1[j], c1); c2 = fmaf(d, lm2[j], c2);
+      }
+      if (n == 0) { c1 = logf(e1); c2 = logf(e2); }          // appendEnergy=True
+      out[(size_t)n * T] = c1;
+      if (has2) out[(size_t)n * T + 1] = live2 ? c2 : 0.f;
     }
   } else {
-    for (int f = lane; f < F; f += 32) out[(size_t)f * T] = logmel[warp][f];
+    for (int f = lane; f < F; f += 32) {
+      out[(size_t)f * T] = lm1[f];
+      if (has2) out[(size_t)f * T + 1] = live2 ? lm2[f] : 0.f;
+    }
   }
 }
 
@@ -207,7 +250,7 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
     tb.inv_width[i] = w > 0 ? 1.0f / (float)w : 0.0f;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((T + 7) / 8, B);
+  dim3 grid((T + 15) / 16, B);
   frontend_frames_kernel<<<grid, 256, 0, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
   st = check_launch("frontend_frames_kernel");
   if (st != DL_OK) return st;
