@@ -278,9 +278,16 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     trunk_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
     trunk_tflops = GFLOP_TRUNK_PER_UTT * B / trunk_ms          # GFLOP / ms == TFLOP/s
-    roofline = {'kernel': 'igemm_conv_kernel + conv3x3_halo_kernel (the 19 ResNet-18 trunk conv launches of one step)', 'bound': 'tensor',
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_trunk_traffic.json')
+    if os.path.exists(tpath) and B == 64:          # dram bytes per launch from the committed ncu capture
+        tj = json.load(open(tpath))
+        traffic = tj['trunk_dram_bytes_per_step'] / tj['trunk_conv_launches']
+    roofline = {'kernel': 'igemm_conv / igemm2_conv / conv3x3_halo kernels (the 19 ResNet-18 trunk conv launches of one step)',
+                'bound': 'tensor',
                 'achieved': trunk_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': trunk_tflops / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'frac': trunk_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
+                'traffic_note': 'avg DRAM bytes per trunk launch (ncu dram__bytes_read+write, profiles/r1_step_traffic.txt)',
                 'peak_src': peaks['src'] + ' (sustained bf16 cuBLAS)', 'launches': 19,
                 'avg_launch_ms': trunk_ms / 19, 'flop_per_launch': GFLOP_TRUNK_PER_UTT * B * 1e9 / 19}
     # stem + audio, for the record

@@ -235,7 +235,8 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   DL_CHECK_ARG((scale2 == nullptr) == (shift2 == nullptr), "conv_igemm: scale2/shift2 must come together");
   DL_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->Cout > 0, "conv_igemm: empty shape");
   DL_CHECK_ARG(d->ldx % 8 == 0 && d->ldx >= d->C, "conv_igemm: ldx must be >= C and a multiple of 8");
-  DL_CHECK_ARG(d->Cout % 8 == 0 && d->Cout <= kMaxCout, "conv_igemm: Cout must be a multiple of 8, at most %d", kMaxCout);
+  DL_CHECK_ARG(d->Cout % 8 == 0, "conv_igemm: Cout must be a multiple of 8 (pad the packed weights)");
+  DL_CHECK_ARG(!y || d->Cout <= kMaxCout, "conv_igemm: the bf16 epilogue stages at most %d channels", kMaxCout);
   DL_CHECK_ARG(!y || (d->ldy % 8 == 0 && d->ldy >= d->Cout), "conv_igemm: ldy must be >= Cout, multiple of 8");
   DL_CHECK_ARG(!y_f32 || (d->ldf % 4 == 0 && d->ldf >= d->Cout), "conv_igemm: ldf must be >= Cout, multiple of 4");
   DL_CHECK_ARG(d->R >= 1 && d->S >= 1 && d->stride_h >= 1 && d->stride_w >= 1 && d->dil_h >= 1 && d->dil_w >= 1 &&

@@ -418,10 +418,13 @@ def scoring_full_case(tmpdir, kind='grid'):
                                  torch.from_numpy(enrol).to(DEV)).cpu().numpy()
     idx = torch.arange(len(tl.utts), dtype=torch.int32, device=DEV)
     self_s = ops.cosine_score_trials(torch.from_numpy(emb).to(DEV), idx, idx).cpu().numpy()
+    dense = U.score_trials_dense(emb, tl).cpu().numpy()
     out = {'n_utts': len(tl.utts), 'score_abs': float(np.abs(s - ref).max()), 'eer': float(eer_g),
+           'dense_abs': float(np.abs(dense - ref).max()),
            'eer_abs_diff': float(abs(eer_g - eer_r)), 'swap_abs': float(np.abs(s - sw).max()),
            'self_abs': float(np.abs(self_s - 1).max())}
     assert out['score_abs'] < 1e-5 and out['eer_abs_diff'] < 5e-4 and out['swap_abs'] == 0.0 and out['self_abs'] < 1e-6, out
+    assert out['dense_abs'] < 1e-3, out          # bf16 operands: within north_star's per-trial tolerance
     assert 0.005 < out['eer'] < 0.45, out        # the synthetic list must not be degenerate
     return out
 
