@@ -181,6 +181,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           res[q] = *reinterpret_cast<const uint4*>(rrow + (((chunk * 4 + q) ^ (m & 7)) << 4));
+        // The slot is refilled by TMA (async proxy) as soon as all warps have arrived: the generic-proxy reads above
+        // must be PERFORMED first.  Without this fence the arrive overtakes the loads (seen on B200 as ~5 % of
+        // launches with corrupted tiles).
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&rempty[rs]);
         rs ^= 1;

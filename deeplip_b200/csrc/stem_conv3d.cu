@@ -149,17 +149,21 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
         }
       }
       v[7] = make_uint4(0u, 0u, 0u, 0u);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sempty[sslot]);         // strip slot consumed (values are in registers)
-      sslot += 2;
-      if (sslot >= kStripSlots) { sslot -= kStripSlots; sph ^= 1; }
       mbar_wait(&empty[slot], ph ^ 1);
       uint8_t* dst_row = smA + slot * kStemABytes + arow * 128;
 #pragma unroll
       for (int kh = 0; kh < 8; ++kh) *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v[kh];
+      // one proxy fence covers both hand-offs: the A tile written above becomes visible to the tensor core (async
+      // proxy), and the strip reads are performed before TMA may refill the slot (an arrive issued right after the
+      // loads can overtake them)
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[slot]);
+      if (lane == 0) {
+        mbar_arrive(&sempty[sslot]);
+        mbar_arrive(&full[slot]);
+      }
+      sslot += 2;
+      if (sslot >= kStripSlots) { sslot -= kStripSlots; sph ^= 1; }
       cur.advance();
       cur.advance();
     }

@@ -474,3 +474,22 @@ def pipeline_case(B=4, T=8, nsamp=24000, seed=1):
     assert out['host_pipeline_abs'] == 0.0, out
     assert out['emb_cos_min'] > 0.999 and out['score_abs'] < 1e-3 and out['ragged_abs'] < 1e-5, out
     return out
+
+
+def determinism_case(B=8, T=10, reps=25, seed=1):
+    """Bitwise run-to-run determinism of the video path under back-to-back launches (no host sync in
+    between).  Guards the smem hand-offs between generic-proxy readers and TMA refills: a missing proxy
+    fence showed up as ~5 % of launches with a few corrupted tiles, invisible to tolerance-based parity."""
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    audio, video = build_models(DEV, seed=seed)
+    ex = AVExtractor(audio, video)
+    spk = list(range(B))
+    raw = torch.from_numpy(synth.lip_crops_u8(spk, T=T, seed=seed)).to(DEV)
+    wav = torch.from_numpy(synth.speech_like_audio(spk, nsamp=16000, seed=seed)).to(DEV)
+    maps = [video.trunk_maps(raw).clone() for _ in range(reps)]
+    embs = [ex.extract(wav, raw).clone() for _ in range(reps)]
+    torch.cuda.synchronize()
+    out = {'maps_mismatch': sum(int(not torch.equal(maps[0], m)) for m in maps[1:]),
+           'emb_mismatch': sum(int(not torch.equal(embs[0], e)) for e in embs[1:])}
+    assert out['maps_mismatch'] == 0 and out['emb_mismatch'] == 0, out
+    return out

@@ -44,6 +44,10 @@ def test_av_pipeline_and_ragged_batch():
     G.pipeline_case()
 
 
+def test_bitwise_determinism_back_to_back():
+    G.determinism_case()
+
+
 def test_modules_are_inference_only_and_fail_loudly_on_cpu():
     from deeplip_b200 import ops
     with pytest.raises(RuntimeError, match='no CPU fallback'):
