@@ -59,6 +59,8 @@ def lib():
         l.dl_version.restype = C.c_int
         l.dl_last_error.restype = C.c_char_p
         l.dl_launch_count.restype = C.c_longlong
+        l.dl_set_option.argtypes = [C.c_char_p, _i]
+        l.dl_set_option.restype = C.c_int
         l.dl_stem_workspace_bytes.restype = C.c_longlong
         l.dl_stem_workspace_bytes.argtypes = [_i, _i, _i, _i]
         _lib = l
@@ -68,6 +70,10 @@ def lib():
 def check(status, what):
     if status != DL_OK:
         raise RuntimeError('deeplip_b200.%s failed (%d): %s' % (what, status, lib().dl_last_error().decode()))
+
+
+def set_option(name, value):
+    check(lib().dl_set_option(name.encode(), int(value)), 'dl_set_option')
 
 
 def launch_count():

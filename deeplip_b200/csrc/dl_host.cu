@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 
 namespace dl {
@@ -166,7 +167,19 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 
 }  // namespace dl
 
+namespace dl {
+static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1};
+int opt_pair() { return g_opt_pair.load(std::memory_order_relaxed); }
+int opt_pair_resident() { return g_opt_pair_resident.load(std::memory_order_relaxed); }
+}  // namespace dl
+
 extern "C" {
+int dl_set_option(const char* name, int value) {
+  if (!name) return DL_ERR_INVALID;
+  if (!strcmp(name, "pair")) { dl::g_opt_pair.store(value); return DL_OK; }
+  if (!strcmp(name, "pair_resident")) { dl::g_opt_pair_resident.store(value); return DL_OK; }
+  return dl::fail(DL_ERR_INVALID, "unknown option '%s'", name);
+}
 int dl_version(void) { return 100; }
 const char* dl_last_error(void) { return dl::g_err; }
 long long dl_launch_count(void) { return dl::g_launches.load(); }

@@ -12,7 +12,9 @@ int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);          // cudaGetLastError -> DL_OK / DL_ERR_CUDA
 int device_sm_count();
-int require_sm100();                          // DL_OK or DL_ERR_UNSUPPORTED
+int require_sm100();
+int opt_pair();            // tuning switches (dl_set_option): CTA-pair kernels on / off
+int opt_pair_resident();   // resident weight-half variant of the pair kernel on / off                          // DL_OK or DL_ERR_UNSUPPORTED
 
 // 2-D tiled map over a row-major (rows, cols) 16-bit matrix with row pitch `ld` elements;
 // box = (box_cols, box_rows), 128-byte swizzle.

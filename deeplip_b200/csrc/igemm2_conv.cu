@@ -17,34 +17,43 @@
 
 namespace dl {
 
-template <int BLOCK_N>
+constexpr int kPairResidentBBytes = 144 * 1024;   // this CTA's half of the whole weight matrix, kept in smem
+constexpr int kPairResidentMaxCout = 512;
+
+// kResB: single N block and the CTA's weight half (all K blocks) fits in shared memory -> loaded once per CTA,
+// the stages carry operand A only.  Removes the weight re-reads that keep layer2 (11x11 maps) L2-bound.
+template <int BLOCK_N, bool kResB>
 struct Igemm2Cfg {
   static constexpr int A_BYTES = 128 * 64 * 2;
-  static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of the weight tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BLOCK_N == 256 ? 6 : 8;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of one weight K block
+  static constexpr int STAGE_BYTES = kResB ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int STAGES = kResB ? 4 : (BLOCK_N == 256 ? 6 : 8);
+  static constexpr int BRES_BYTES = kResB ? kPairResidentBBytes : 0;
+  static constexpr int PSTRIDE = kResB ? kPairResidentMaxCout : kMaxCout;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int PARAM_BYTES = 3 * kMaxCout * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+  static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
+  static constexpr int PARAM_BYTES = 3 * PSTRIDE * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
   static constexpr int THREADS = 320;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kResB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const IgemmParams p) {
-  using Cfg = Igemm2Cfg<BLOCK_N>;
+  using Cfg = Igemm2Cfg<BLOCK_N, kResB>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* prm = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::PARAM_BYTES);
+  uint8_t* bres = smem + STAGES * Cfg::STAGE_BYTES;            // resident weight half (kResB only)
+  float* prm = reinterpret_cast<float*>(bres + Cfg::BRES_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bres + Cfg::BRES_BYTES + Cfg::PARAM_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bfull = bars + 2 * STAGES + 4;                     // leader: both weight halves landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,6 +75,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       mbar_init(&tfull[1], 1);
       mbar_init(&tempty[0], 16);
       mbar_init(&tempty[1], 16);
+      mbar_init(bfull, 2);
       fence_mbar_init();
     }
     __syncwarp();
@@ -74,8 +84,8 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (p.y != nullptr) {
     for (int c = threadIdx.x; c < p.Cout; c += Cfg::THREADS) {
       prm[c] = p.scale[c];
-      prm[kMaxCout + c] = p.shift[c];
-      prm[2 * kMaxCout + c] = p.slope[c];
+      prm[Cfg::PSTRIDE + c] = p.shift[c];
+      prm[2 * Cfg::PSTRIDE + c] = p.slope[c];
     }
   }
   tc_fence_before();
@@ -91,6 +101,13 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
+      if (kResB) {                       // whole weight half of this CTA, credited to the leader's barrier
+        const uint32_t bb = mapa_shared(smem_u32(bfull), 0);
+        if (rank == 0) mbar_expect_tx_cluster(bb, 2u * (uint32_t)num_kb * Cfg::B_BYTES);
+        else mbar_arrive_cluster(bb);
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma2_load_2d(bres + kb * Cfg::B_BYTES, &mapB, bb, kb * 64, (int)rank * (BLOCK_N / 2));
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < total; t += num_pairs) {
@@ -114,7 +131,8 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               else mbar_arrive_cluster(lbar);
               tma2_load_im2col_4d(sa, &mapA, lbar, cc * 64, w0, h0, img, (uint16_t)(s * p.dil_w),
                                   (uint16_t)(r * p.dil_h));
-              tma2_load_2d(sa + Cfg::A_BYTES, &mapB, lbar, kb * 64, n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              if (!kResB)
+                tma2_load_2d(sa + Cfg::A_BYTES, &mapB, lbar, kb * 64, n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -124,6 +142,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   } else if (warp == 1) {
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      if (kResB) mbar_wait(bfull, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -137,7 +156,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128_kmajor(sa);
-          const uint64_t bdesc = umma_desc_sw128_kmajor(sa + Cfg::A_BYTES);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(kResB ? smem_u32(bres) + kb * Cfg::B_BYTES : sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma2_commit_both(&empty[stage]);
@@ -165,7 +184,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       igemm_prefetch_residual(p, row, row_ok, cbase, chunk0, has_res, res);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      igemm_epilogue_tile<BLOCK_N>(p, prm, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
+      igemm_epilogue_tile<BLOCK_N>(p, prm, Cfg::PSTRIDE, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
                                    res);
       tc_fence_before();
       __syncwarp();
@@ -184,13 +203,13 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kResB>
 static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, cudaStream_t stream) {
-  using Cfg = Igemm2Cfg<BLOCK_N>;
+  using Cfg = Igemm2Cfg<BLOCK_N, kResB>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N, kResB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "igemm2 smem attribute: %s", cudaGetErrorString(e));
     configured = true;
@@ -199,14 +218,18 @@ static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const
   int pairs = device_sm_count() / 2;
   if (pairs <= 0) pairs = 74;
   if (super_tiles < pairs) pairs = super_tiles;
-  igemm2_conv_kernel<BLOCK_N><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+  igemm2_conv_kernel<BLOCK_N, kResB><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
   return check_launch("igemm2_conv_kernel");
 }
 
 // Called by dl_conv_igemm_bf16 (igemm_conv.cu) for wide, large-M problems.
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
                       cudaStream_t stream) {
-  return block_n == 128 ? launch_igemm2<128>(mapA, mapB, p, stream) : launch_igemm2<256>(mapA, mapB, p, stream);
+  const long long num_kb = (long long)p.R * p.S * p.cchunks;
+  const bool res = opt_pair_resident() && p.num_n_blocks == 1 && num_kb * (block_n / 2) * 128 <= kPairResidentBBytes &&
+                   p.Cout <= kPairResidentMaxCout;
+  if (block_n == 128) return res ? launch_igemm2<128, true>(mapA, mapB, p, stream) : launch_igemm2<128, false>(mapA, mapB, p, stream);
+  return res ? launch_igemm2<256, true>(mapA, mapB, p, stream) : launch_igemm2<256, false>(mapA, mapB, p, stream);
 }
 
 }  // namespace dl

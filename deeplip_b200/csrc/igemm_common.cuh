@@ -40,11 +40,13 @@ __device__ __forceinline__ void igemm_prefetch_residual(const IgemmParams& p, lo
 }
 
 // Epilogue of one tile for one warp: TMEM lane quarter `quarter`, 32-column chunks chunk0, chunk0+2, ...
-// tmem_acc = TMEM address of the accumulator stage (column of channel cbase, lane 0).
+// tmem_acc = TMEM address of the accumulator stage (column of channel cbase, lane 0); prm = scale | shift | slope
+// arrays in shared memory, pstride floats apart.
 template <int BLOCK_N>
-__device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const float* prm, uint32_t tmem_acc,
-                                                    long long row, bool row_ok, int cbase, int quarter, int chunk0,
-                                                    bool has_res, bool fast, uint4 (&res)[4]) {
+__device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const float* prm, int pstride,
+                                                    uint32_t tmem_acc, long long row, bool row_ok, int cbase,
+                                                    int quarter, int chunk0, bool has_res, bool fast,
+                                                    uint4 (&res)[4]) {
 #pragma unroll 1
   for (int j = chunk0; j < BLOCK_N / 32; j += 2) {
     const int c0 = cbase + j * 32;
@@ -64,8 +66,8 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const 
       }
       tmem_ld_wait();
       const float4* sc = reinterpret_cast<const float4*>(prm + c0);
-      const float4* sh = reinterpret_cast<const float4*>(prm + kMaxCout + c0);
-      const float4* sl = reinterpret_cast<const float4*>(prm + 2 * kMaxCout + c0);
+      const float4* sh = reinterpret_cast<const float4*>(prm + pstride + c0);
+      const float4* sl = reinterpret_cast<const float4*>(prm + 2 * pstride + c0);
       uint4 o[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -124,14 +126,14 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const 
           if (p.y != nullptr) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaf(a[i], prm[c + i], prm[kMaxCout + c + i]);
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(a[i], prm[c + i], prm[pstride + c + i]);
             if (has_res) {
               const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c));
               v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
               v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * prm[2 * kMaxCout + c + i];
+            for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * prm[2 * pstride + c + i];
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);

@@ -182,7 +182,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       igemm_prefetch_residual(p, row, row_ok, cbase, chunk0, has_res, res);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      igemm_epilogue_tile<BLOCK_N>(p, prm, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
+      igemm_epilogue_tile<BLOCK_N>(p, prm, kMaxCout, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
                                    res);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -281,12 +281,7 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   const long long num_kb = (long long)d->R * d->S * p.cchunks;
   const bool resident = p.num_n_blocks == 1 && num_kb * block_n * 128 <= kResidentBBytes;
   // CTA pairs (cta_group::2) for wide tiles on problems large enough to fill the chip twice over
-  static int use_pair = -1;
-  if (use_pair < 0) {
-    const char* env = getenv("DL_USE_2CTA");
-    use_pair = (env == nullptr || atoi(env) != 0) ? 1 : 0;
-  }
-  const bool pair = use_pair && block_n >= 128 && !resident && p.num_m_blocks >= 128;
+  const bool pair = opt_pair() && block_n >= 128 && !resident && p.num_m_blocks >= 128;
   st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot,
                           (uint32_t)(pair ? block_n / 2 : block_n), 64);
   if (st != DL_OK) return st;

@@ -63,22 +63,34 @@ __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restri
   for (int i = 0; i < 8; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
   int n = 0;
   if (c0 < C) {
-    for (int t = warp; t < len; t += 8) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * ldx + c0));
-      float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                    bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
-      if (kAttn) {
-        const float w = alpha[t];
+    // 4 time steps (4 independent 16-byte loads) in flight per lane: the kernel is pure streaming
+    for (int tb = warp; tb < len; tb += 32) {
+      uint4 v4[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a0[i] = fmaf(w, f[i], a0[i]); a1[i] = fmaf(w * f[i], f[i], a1[i]); }
-      } else {
-        ++n;
-        const float rn = 1.f / (float)n;
+      for (int u = 0; u < 4; ++u) {
+        const int t = tb + 8 * u;
+        if (t < len) v4[u] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * ldx + c0));
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float d = f[i] - a0[i];
-          a0[i] += d * rn;
-          a1[i] = fmaf(d, f[i] - a0[i], a1[i]);
+      for (int u = 0; u < 4; ++u) {
+        const int t = tb + 8 * u;
+        if (t >= len) break;
+        const uint4 v = v4[u];
+        float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                      bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+        if (kAttn) {
+          const float w = alpha[t];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a0[i] = fmaf(w, f[i], a0[i]); a1[i] = fmaf(w * f[i], f[i], a1[i]); }
+        } else {
+          ++n;
+          const float rn = 1.f / (float)n;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d = f[i] - a0[i];
+            a0[i] += d * rn;
+            a1[i] = fmaf(d, f[i] - a0[i], a1[i]);
+          }
         }
       }
     }
@@ -306,6 +318,7 @@ __device__ __forceinline__ void pair_dot(const float* __restrict__ a, const floa
   if ((D & 3) == 0) {
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll 8
     for (int i = lane; i < D / 4; i += 32) {
       const float4 u = __ldg(a4 + i), w = __ldg(b4 + i);
       d = fmaf(u.x, w.x, d); d = fmaf(u.y, w.y, d); d = fmaf(u.z, w.z, d); d = fmaf(u.w, w.w, d);

@@ -31,6 +31,9 @@ extern "C" {
 
 int dl_version(void);
 const char* dl_last_error(void);
+/* Tuning switches for A/B measurements: "pair" (CTA-pair igemm kernels, default 1), "pair_resident"
+ * (smem-resident weight half in the pair kernel, default 1).  Results are identical either way. */
+int dl_set_option(const char* name, int value);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long dl_launch_count(void);
 

@@ -7,6 +7,10 @@ import bench
 from deeplip_b200.pipeline import AVExtractor, build_models
 B = int(os.environ.get('B', '64'))
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+from deeplip_b200 import _lib
+for k in ('pair', 'pair_resident'):
+    if os.environ.get('DL_OPT_' + k.upper()) is not None:
+        _lib.set_option(k, int(os.environ['DL_OPT_' + k.upper()]))
 audio, video = build_models('cuda', seed=1)
 ex = AVExtractor(audio, video)
 raw, wav = bench.synth_batch(B, seed=1)
