@@ -107,7 +107,7 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
 # ------------------------------------------------------------------ K3 / K5 / K7
 def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=(1, 1), scale=None, shift=None,
                slope=None, residual=None, want_bf16=True, want_f32=False, scale2=None, shift2=None,
-               f32_slope=1.0, H=None):
+               f32_slope=1.0, H=None, out=None, out_channel_offset=0):
     """x: (N,H,W,ldx) bf16 channels-last -- or (N,img_rows,W,ldx) stacked rows with the true height passed as H.
     Returns (y_bf16 (N,P,Q,Cout) | None, y_f32 (N*P*Q,Cout) | None)."""
     _need_cuda(x, w_packed, scale, shift, slope, residual, scale2, shift2)
@@ -116,15 +116,23 @@ def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=
     H = H or img_rows
     P = (H + 2 * pad[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
     Q = (W + 2 * pad[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
-    y = torch.empty((N, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    ldy = Cout
+    y_ptr = None
+    if out is not None:          # write Cout channels into a slice of a wider channels-last buffer (concat for free)
+        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape[:3] == (N, P, Q)
+        assert out_channel_offset % 8 == 0 and out_channel_offset + Cout <= out.shape[3] and residual is None
+        y, ldy = out, out.shape[3]
+        y_ptr = C.c_void_p(out.data_ptr() + 2 * out_channel_offset)
+    else:
+        y = torch.empty((N, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     yf = torch.empty((N * P * Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.numel() == y.numel()
-    d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], Cout, Cout,
+    d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ldy, Cout,
                  float(f32_slope), img_rows)
     st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
-                                       _ptr(residual), _ptr(y), _ptr(yf), _ptr(scale2), _ptr(shift2),
-                                       C.byref(d), _stream())
+                                       _ptr(residual), y_ptr if y_ptr is not None else _ptr(y), _ptr(yf),
+                                       _ptr(scale2), _ptr(shift2), C.byref(d), _stream())
     _lib.check(st, 'dl_conv_igemm_bf16')
     return y, yf
 

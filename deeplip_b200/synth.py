@@ -89,6 +89,36 @@ def make_video_state_dict(seed=SEED, randomize=True, relu_type='prelu'):
     return sd
 
 
+def make_tcn_state_dict(num_classes=500, hidden=256, ksizes=(3, 5, 7), layers=4, in_dim=512, seed=SEED,
+                        randomize=True):
+    """MS-TCN head keys of Lipreading (models/video_models/tcn.py:62-140, model.py:20-37):
+    tcn.mb_ms_tcn.network.{i}.cbcr{0,1}_{k}.{conv,batchnorm,non_lin}, .downsample, .relu_final, tcn.tcn_output."""
+    rng = np.random.default_rng(seed + 3000)
+    sd = {}
+    nk = len(ksizes)
+    width = hidden * nk
+    for i in range(layers):
+        cin = in_dim if i == 0 else width
+        p = 'tcn.mb_ms_tcn.network.%d.' % i
+        for stage, c_in in ((0, cin), (1, width)):
+            for k_idx, k in enumerate(ksizes):
+                q = p + 'cbcr%d_%d.' % (stage, k_idx)
+                bound = 1.0 / math.sqrt(c_in * k)
+                sd[q + 'conv.weight'] = _t(rng.uniform(-bound, bound, (hidden, c_in, k)) * math.sqrt(3.0))
+                sd[q + 'conv.bias'] = _t(rng.uniform(-bound, bound, hidden))
+                _bn(sd, q + 'batchnorm', hidden, rng, randomize)
+                _prelu(sd, q + 'non_lin.weight', hidden, rng, randomize)
+        if cin // nk != width:
+            bound = 1.0 / math.sqrt(cin)
+            sd[p + 'downsample.weight'] = _t(rng.uniform(-bound, bound, (width, cin, 1)))
+            sd[p + 'downsample.bias'] = _t(rng.uniform(-bound, bound, width))
+        _prelu(sd, p + 'relu_final.weight', width, rng, randomize)
+    bound = 1.0 / math.sqrt(width)
+    sd['tcn.tcn_output.weight'] = _t(rng.uniform(-bound, bound, (num_classes, width)))
+    sd['tcn.tcn_output.bias'] = _t(rng.uniform(-bound, bound, num_classes))
+    return sd
+
+
 def make_audio_state_dict(opts, seed=SEED, randomize=True):
     rng = np.random.default_rng(seed + 1000)
     o = opts[opts['arch']]

@@ -10,6 +10,7 @@ import torch.nn as nn
 
 from .. import ops, packing
 from .resnet import ResNet, BasicBlock
+from .tcn import MultiscaleMultibranchTCN
 
 
 def threeD_to_2D_tensor(x):
@@ -26,9 +27,16 @@ class Lipreading(nn.Module):
         if backbone_type != 'resnet':
             # conf/video_config.json:2 and conf/fusion_config.yaml:75 both select 'resnet'
             raise NotImplementedError("only backbone_type='resnet' is on the B200 hot path (SURVEY 2)")
+        self.tcn = None
         if not extract_feats:
-            raise NotImplementedError('the MS-TCN classification head (extract_feats=False) is outside the '
-                                      'extraction hot path (SURVEY 8(f) N3); construct with extract_feats=True')
+            if len(tcn_options['kernel_size']) == 1:
+                raise NotImplementedError('the single-branch TCN is not configured by the reference '
+                                          '(tcn_kernel_size: [3, 5, 7]); only the multi-scale head is built')
+            self.tcn = MultiscaleMultibranchTCN(
+                input_size=512,
+                num_channels=[hidden_dim * len(tcn_options['kernel_size']) * tcn_options['width_mult']] * tcn_options['num_layers'],
+                num_classes=num_classes, tcn_options=tcn_options, dropout=tcn_options['dropout'],
+                relu_type=relu_type, dwpw=tcn_options['dwpw'])
         self.frontend_nout = 64
         self.backend_out = 512
         self.trunk = ResNet(BasicBlock, [2, 2, 2, 2], relu_type=relu_type)
@@ -45,7 +53,7 @@ class Lipreading(nn.Module):
         sd = {}
         for k, v in state_dict.items():
             k = k[7:] if k.startswith('module.') else k
-            if k.startswith('tcn.'):
+            if k.startswith('tcn.') and self.tcn is None:
                 continue
             sd[k] = v
         out = super().load_state_dict(sd, strict=strict, **kw)
@@ -55,6 +63,8 @@ class Lipreading(nn.Module):
     def invalidate(self):
         self._pk = None
         self.trunk.invalidate()
+        if getattr(self, 'tcn', None) is not None:
+            self.tcn.invalidate()
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
@@ -94,7 +104,9 @@ class Lipreading(nn.Module):
         assert C == 1
         y = self.trunk_maps(x[:, 0])
         feats, _ = ops.frame_pool_temporal_mean(y, B, T, want_frames=True, want_mean=False)
-        return feats                      # (B, T, 512); lengths unused when extract_feats (model.py:105)
+        if self.extract_feats:
+            return feats                  # (B, T, 512); lengths unused when extract_feats (model.py:105)
+        return self.tcn(feats, lengths, B)
 
     def utterance_embedding(self, x, lengths=None):
         """Fused form of train_fusion.py:400: mean over the (valid) frames of each clip -> (B,512).

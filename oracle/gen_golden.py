@@ -37,6 +37,23 @@ def video_case():
                         stem_sample=stem[0, ::8, 0, ::3, ::3].numpy())
 
 
+def video_tcn_case():
+    """Lipreading(extract_feats=False): trunk + MS-TCN head -> logits."""
+    from models.video_models.model import Lipreading
+    from models.video_models.dataloaders import get_preprocessing_pipelines
+    sd = synth.make_video_state_dict(seed=1, randomize=True)
+    sd.update(synth.make_tcn_state_dict(num_classes=62, seed=1, randomize=True))
+    m = Lipreading(relu_type='prelu', backbone_type='resnet', num_classes=62, extract_feats=False,
+                   tcn_options=synth.TCN_OPTIONS).eval()
+    m.load_state_dict(sd)
+    crops = synth.lip_crops_u8([3, 7], T=12, seed=2)
+    pre = get_preprocessing_pipelines()['test']
+    x = np.stack([pre(c).astype(np.float32) for c in crops])
+    with torch.no_grad():
+        y = m(torch.from_numpy(x)[:, None], lengths=[12, 9])
+    np.savez_compressed(os.path.join(OUT, 'video_tcn_small.npz'), logits=y.numpy())
+
+
 def audio_case():
     from models.audio_models.tdnn import SpeakerEmbNet
     out = {}
@@ -105,6 +122,6 @@ def scoring_case():
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(1)
-    video_case(); audio_case(); fusion_case(); scoring_case()
+    video_case(); video_tcn_case(); audio_case(); fusion_case(); scoring_case()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -157,6 +157,37 @@ def lipreading_features(sd, x):
     return x.view(B, Tn, x.size(1))
 
 
+def ms_tcn_logits(sd, feats, lengths, ksizes=(3, 5, 7), layers=4):
+    """MS-TCN head, models/video_models/tcn.py:28-140 + model.py:20-37 (eval mode, dwpw=False):
+    per block two sets of {Conv1d(k, dilation 2^i, padding (k-1)2^i) -> BN -> symmetric chomp -> PReLU}
+    branches concatenated, + 1x1-conv skip, PReLU; then the masked temporal mean (`_average_batch`) and Linear.
+    feats: (B,T,512) -> (B,num_classes)."""
+    sd = _strip(sd)
+    x = feats.transpose(1, 2)                                   # (B,C,T), model.py:35
+    for i in range(layers):
+        d = 2 ** i
+        p = 'tcn.mb_ms_tcn.network.%d.' % i
+
+        def branches(inp, stage):
+            outs = []
+            for k_idx, k in enumerate(ksizes):
+                q = p + 'cbcr%d_%d.' % (stage, k_idx)
+                pad = (k - 1) * d
+                o = F.conv1d(inp, sd[q + 'conv.weight'], sd[q + 'conv.bias'], dilation=d, padding=pad)
+                o = _bn(o, sd, q + 'batchnorm')
+                if pad:
+                    o = o[:, :, pad // 2:-(pad // 2)]          # Chomp1d(symm_chomp=True), tcn.py:22-23
+                outs.append(F.prelu(o, sd[q + 'non_lin.weight']))
+            return torch.cat(outs, 1)
+        out1 = branches(branches(x, 0), 1)
+        res = x
+        if p + 'downsample.weight' in sd:
+            res = F.conv1d(x, sd[p + 'downsample.weight'], sd[p + 'downsample.bias'])
+        x = F.prelu(out1 + res, sd[p + 'relu_final.weight'])
+    pooled = torch.stack([x[b, :, :int(l)].mean(dim=1) for b, l in enumerate(lengths)], 0)   # model.py:16-17
+    return F.linear(pooled, sd['tcn.tcn_output.weight'], sd['tcn.tcn_output.bias'])
+
+
 def temporal_mean(feats, lengths=None):
     """train_fusion.py:400 (mean over frames of one clip); batched form
     models/video_models/model.py:16-17 averages the first len_i frames."""

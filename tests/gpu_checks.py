@@ -493,3 +493,28 @@ def determinism_case(B=8, T=10, reps=25, seed=1):
            'emb_mismatch': sum(int(not torch.equal(embs[0], e)) for e in embs[1:])}
     assert out['maps_mismatch'] == 0 and out['emb_mismatch'] == 0, out
     return out
+
+
+def video_tcn_case(B=2, T=12, seed=1):
+    """Lipreading(extract_feats=False) drop-in (trunk + MS-TCN head) vs the oracle and the reference golden."""
+    import os
+    from deeplip_b200.video_models.model import Lipreading
+    sd = synth.make_video_state_dict(seed=1, randomize=True)
+    sd.update(synth.make_tcn_state_dict(num_classes=62, seed=1, randomize=True))
+    m = Lipreading(relu_type='prelu', backbone_type='resnet', num_classes=62, extract_feats=False,
+                   tcn_options=synth.TCN_OPTIONS)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    raw = torch.from_numpy(synth.lip_crops_u8([3, 7], T=12, seed=2))
+    x = torch.stack([models_ref.video_preprocess(r) for r in raw])
+    lengths = [12, 9]
+    with torch.no_grad():
+        ref = models_ref.ms_tcn_logits(sd, models_ref.lipreading_features(sd, x[:, None]), lengths)
+        got = m(x[:, None].to(DEV), lengths=lengths)
+    torch.cuda.synchronize()
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'video_tcn_small.npz'))['logits']
+    out = {'cos_vs_oracle': float(cosine_rows(got, ref).min()), 'rel_vs_oracle': rel_err(got, ref),
+           'cos_vs_reference_golden': float(cosine_rows(got, torch.from_numpy(gold)).min()),
+           'argmax_equal': bool((got.argmax(1).cpu() == ref.argmax(1)).all())}
+    assert out['cos_vs_oracle'] > 0.999 and out['cos_vs_reference_golden'] > 0.999 and out['argmax_equal'], out
+    return out

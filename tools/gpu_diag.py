@@ -44,6 +44,7 @@ run('stem_f32', G.stem_case)
 run('stem_u8', G.stem_case, u8=True)
 run('video_model', G.video_model_case)
 run('video_golden', G.video_golden_case)
+run('video_tcn', G.video_tcn_case)
 run('audio_model_etdnn', G.audio_model_case)
 run('audio_model_tdnn_attn', G.audio_model_case, arch='tdnn', pooling='attentive_statistic')
 run('audio_golden', G.audio_golden_case)
