@@ -105,6 +105,38 @@ def load_embeddings(root, utts):
     return np.stack([np.load(os.path.join(root, utt_to_relpath(u))).reshape(-1) for u in utts]).astype(np.float32)
 
 
+def save_embedding_table(path, utts, emb):
+    """Packed hand-off: ONE (N_utt, D) float32 .npy + a sidecar utterance list, instead of
+    one file per utterance.  `path` without extension; writes <path>.npy and <path>.utts.txt."""
+    emb = emb.detach().cpu().numpy() if torch.is_tensor(emb) else np.asarray(emb)
+    assert emb.ndim == 2 and emb.shape[0] == len(utts)
+    os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+    np.save(path + '.npy', np.ascontiguousarray(emb, dtype=np.float32))
+    with open(path + '.utts.txt', 'w') as f:
+        f.write('\n'.join(utts) + '\n')
+
+
+def load_embedding_table(path, utts=None):
+    """Inverse of save_embedding_table; with `utts` given, rows are returned in that order (a KeyError names a
+    missing utterance)."""
+    emb = np.load(path + '.npy')
+    with open(path + '.utts.txt') as f:
+        have = [l.rstrip('\n') for l in f if l.strip()]
+    assert emb.shape[0] == len(have), 'table / utterance list length mismatch'
+    if utts is None:
+        return have, emb
+    index = {u: i for i, u in enumerate(have)}
+    return list(utts), emb[[index[u] for u in utts]]
+
+
+def eer_cos_table(trial_path, table_path, device='cuda'):
+    """eer_cos_* on the packed table: parse trials, reorder the table to the trial list's utterance order,
+    score on the GPU, EER on the CPU."""
+    trials = TrialList.from_file(trial_path)
+    _, emb = load_embedding_table(table_path, trials.utts)
+    return eer_cos(trials, emb, device)
+
+
 def _eer_cos_dir(exp_dir, sub, trial_path, root='exp', device='cuda'):
     trials = TrialList.from_file(trial_path)
     emb = load_embeddings(os.path.join(root, str(exp_dir), sub), trials.utts)

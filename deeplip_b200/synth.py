@@ -153,6 +153,41 @@ def make_audio_state_dict(opts, seed=SEED, randomize=True):
     return sd
 
 
+AUDIO_RESNET_OPTS = {'arch': 'resnet',
+                     'resnet': dict(input_dim=1, hidden_dim=[64, 128, 256], residual_block_layers=[3, 3, 3],
+                                    fc_layers=1, embedding_dim=256, pooling='average')}   # conf/audio_config.yaml:93-102
+
+
+def make_audio_resnet_state_dict(opts=None, seed=SEED, randomize=True):
+    """Weights for the build-defined audio ResNet (deeplip_b200/audio_models/resnet.py)."""
+    o = (opts or AUDIO_RESNET_OPTS)['resnet']
+    rng = np.random.default_rng(seed + 4000)
+    sd = {}
+    hidden, blocks = o['hidden_dim'], o['residual_block_layers']
+    sd['conv1.weight'] = _t(rng.normal(0, math.sqrt(2.0 / 9), (hidden[0], 1, 3, 3)))
+    _bn(sd, 'bn0', hidden[0], rng, randomize)
+    inpl = hidden[0]
+    for i, (planes, nb) in enumerate(zip(hidden, blocks)):
+        for b in range(nb):
+            p = 'layer%d.%d.' % (i + 1, b)
+            stride = 2 if (i > 0 and b == 0) else 1
+            sd[p + 'conv1.weight'] = _t(rng.normal(0, math.sqrt(2.0 / (9 * planes)), (planes, inpl, 3, 3)))
+            _bn(sd, p + 'bn1', planes, rng, randomize)
+            sd[p + 'conv2.weight'] = _t(rng.normal(0, math.sqrt(2.0 / (9 * planes)), (planes, planes, 3, 3)))
+            _bn(sd, p + 'bn2', planes, rng, randomize)
+            if stride != 1 or inpl != planes:
+                sd[p + 'downsample.0.weight'] = _t(rng.normal(0, math.sqrt(2.0 / planes), (planes, inpl, 1, 1)))
+                _bn(sd, p + 'downsample.1', planes, rng, randomize)
+            inpl = planes
+    pooled = inpl * (2 if o.get('pooling', 'average') == 'statistic' else 1)
+    e = o['embedding_dim']
+    b1 = 1.0 / math.sqrt(pooled)
+    sd['fc1.weight'] = _t(rng.uniform(-b1, b1, (e, pooled)))
+    sd['fc1.bias'] = _t(rng.uniform(-b1, b1, e))
+    _bn(sd, 'bn1', e, rng, randomize)
+    return sd
+
+
 def make_fusion_state_dict(input_size=1024, hidden=512, seed=SEED, randomize=True):
     rng = np.random.default_rng(seed + 2000)
     sd = {}

@@ -95,6 +95,30 @@ def speaker_forward(sd, x, opts):
     return _bn(F.leaky_relu(xv, 0.2), sd, 'bn2')
 
 
+def audio_resnet_extract_embedding(sd, x, opts):
+    """fp32 restatement of deeplip_b200.audio_models.resnet.SpeakerEmbNet -- a BUILD-DEFINED model: the
+    reference's `models/resnet.py` does not exist, only conf/audio_config.yaml:93-102 and the
+    call sites train_audio.py:64-66, 183-184, 250-252.  PARITY UNPINNED with respect to the reference.
+    x: (B,1,F,T) -> (xv, x_a)."""
+    sd = _strip(sd)
+    o = opts[opts['arch']] if 'arch' in opts else opts
+    h = F.relu(_bn(F.conv2d(x, sd['conv1.weight'], None, padding=1), sd, 'bn0'))
+    for i, nb in enumerate(o['residual_block_layers']):
+        for b in range(nb):
+            p = 'layer%d.%d.' % (i + 1, b)
+            stride = 2 if (i > 0 and b == 0) else 1
+            out = F.relu(_bn(F.conv2d(h, sd[p + 'conv1.weight'], None, stride=stride, padding=1), sd, p + 'bn1'))
+            out = _bn(F.conv2d(out, sd[p + 'conv2.weight'], None, padding=1), sd, p + 'bn2')
+            res = h
+            if p + 'downsample.0.weight' in sd:
+                res = _bn(F.conv2d(h, sd[p + 'downsample.0.weight'], None, stride=stride), sd, p + 'downsample.1')
+            h = F.relu(out + res)
+    flat = h.flatten(2)
+    pooled = flat.mean(dim=2) if o.get('pooling', 'average') == 'average' else torch.cat([flat.mean(2), flat.std(2)], 1)
+    xa = F.linear(pooled, sd['fc1.weight'], sd['fc1.bias'])
+    return xa, xa
+
+
 # ----------------------------------------------------------------------------- video
 def video_preprocess(frames_u8, crop=88, mean=0.421, std=0.165):
     """models/video_models/dataloaders.py:19-24 + preprocess.py:60-68, 80-92.

@@ -518,3 +518,24 @@ def video_tcn_case(B=2, T=12, seed=1):
            'argmax_equal': bool((got.argmax(1).cpu() == ref.argmax(1)).all())}
     assert out['cos_vs_oracle'] > 0.999 and out['cos_vs_reference_golden'] > 0.999 and out['argmax_equal'], out
     return out
+
+
+def audio_resnet_case(B=3, Fd=24, T=120, pooling='average', seed=1):
+    """Build-defined audio ResNet (absent upstream) vs the fp32 restatement of the same definition."""
+    import copy
+    from deeplip_b200.audio_models.resnet import SpeakerEmbNet
+    opts = copy.deepcopy(synth.AUDIO_RESNET_OPTS)
+    opts['resnet']['pooling'] = pooling
+    sd = synth.make_audio_resnet_state_dict(opts, seed=seed)
+    net = SpeakerEmbNet(opts)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    wav = synth.speech_like_audio(list(range(B)), nsamp=400 + 160 * (T - 1), seed=seed)
+    feats = torch.from_numpy(np.stack([frontend_np.extract_feature(w.astype(np.float64)).T for w in wav]))[:, None]
+    with torch.no_grad():
+        ref, _ = models_ref.audio_resnet_extract_embedding(sd, feats, opts)
+        got, _ = net.extract_embedding(feats.to(DEV))
+    torch.cuda.synchronize()
+    out = {'cos_min': float(cosine_rows(got, ref).min()), 'rel': rel_err(got, ref)}
+    assert out['cos_min'] > 0.999, out
+    return out

@@ -31,6 +31,11 @@ def test_audio_model_vs_oracle(arch, pooling):
     G.audio_model_case(arch=arch, pooling=pooling)
 
 
+@pytest.mark.parametrize('pooling', ['average', 'statistic'])
+def test_audio_resnet_build_defined(pooling):
+    G.audio_resnet_case(pooling=pooling)
+
+
 def test_audio_model_vs_reference_golden():
     G.audio_golden_case()
 

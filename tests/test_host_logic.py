@@ -82,6 +82,19 @@ def test_trial_list_parsing_matches_oracle(tmp_path):
         assert sh[0] == slice(0, 2500) and sh[7] == slice(17500, 20000)
 
 
+def test_packed_embedding_table_roundtrip(tmp_path):
+    from deeplip_b200.fusion_models import utils as U
+    utts = ['s1/a.wav', 's2/b.wav', 's3/c.wav']
+    emb = np.arange(12, dtype=np.float32).reshape(3, 4)
+    U.save_embedding_table(str(tmp_path / 'tab'), utts, torch.from_numpy(emb))
+    have, e = U.load_embedding_table(str(tmp_path / 'tab'))
+    assert have == utts and np.array_equal(e, emb)
+    _, e2 = U.load_embedding_table(str(tmp_path / 'tab'), ['s3/c.wav', 's1/a.wav'])
+    assert np.array_equal(e2, emb[[2, 0]])
+    with pytest.raises(KeyError):
+        U.load_embedding_table(str(tmp_path / 'tab'), ['nope.wav'])
+
+
 def test_packing_layouts():
     from deeplip_b200 import packing
     w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)

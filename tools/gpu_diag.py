@@ -48,6 +48,8 @@ run('video_tcn', G.video_tcn_case)
 run('audio_model_etdnn', G.audio_model_case)
 run('audio_model_tdnn_attn', G.audio_model_case, arch='tdnn', pooling='attentive_statistic')
 run('audio_golden', G.audio_golden_case)
+run('audio_resnet_avg', G.audio_resnet_case)
+run('audio_resnet_stat', G.audio_resnet_case, pooling='statistic')
 run('fusion_golden', G.fusion_golden_case)
 import tempfile
 run('scoring_full_grid', G.scoring_full_case, tmpdir=tempfile.mkdtemp(), kind='grid')
