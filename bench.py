@@ -312,12 +312,10 @@ def run_ours(args, rank, world, local):
     audio_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
 
     # ---- trial scoring on a trial_grid_v1-shaped list, sharded over ranks
-    sys.path.insert(0, os.path.join(ROOT, 'tests'))
     scoring = None
     try:
-        import gpu_checks
         tmp = tempfile.mkdtemp()
-        tl = TrialList.from_file(gpu_checks.make_trial_file(os.path.join(tmp, 'trial_grid_shape.txt'), 'grid'))
+        tl = TrialList.from_file(synth.make_trial_file(os.path.join(tmp, 'trial_grid_shape.txt'), 'grid'))
         emb = torch.from_numpy(synth.structured_embeddings([synth.speaker_of_utt(u) for u in tl.utts],
                                                            dim=1024, seed=3, within=6.0)).to(dev)
         sl = tl.shard(rank, world)

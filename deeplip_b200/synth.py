@@ -267,3 +267,25 @@ def structured_embeddings(speakers, dim=1024, seed=SEED, within=0.6):
             cents[s] = np.random.default_rng(seed * 31337 + s).standard_normal(dim)
         out[i] = cents[s] + within * rng.standard_normal(dim)
     return out
+
+
+def make_trial_file(path, kind='grid', seed=1, n_target=4000, n_non=16000):
+    """Synthetic trial list with the shape of database/trial_{grid,lomgrid}_v1.txt:
+    targets first, then non-targets; '<label> <utt1> <utt2>' + trailing TAB (grid) / space (lomgrid)."""
+    rng = np.random.default_rng(seed)
+    spk = [s for s in range(1, 35) if s != 21] if kind == 'grid' else list(range(2, 56, 1))[:36]
+    per = 900 if kind == 'grid' else 100
+    def utt(s, i):
+        return 's%d/u%05d.wav' % (s, i) if kind == 'grid' else 's%d_l_u%05d.wav' % (s, i)
+    tail = '\t' if kind == 'grid' else ' '
+    lines = []
+    for _ in range(n_target):
+        s = spk[rng.integers(len(spk))]
+        a, b = rng.choice(per, 2, replace=False)
+        lines.append('1 %s %s%s' % (utt(s, a), utt(s, b), tail))
+    for _ in range(n_non):
+        s1, s2 = rng.choice(len(spk), 2, replace=False)
+        lines.append('0 %s %s%s' % (utt(spk[s1], rng.integers(per)), utt(spk[s2], rng.integers(per)), tail))
+    with open(path, 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    return path
