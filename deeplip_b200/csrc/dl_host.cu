@@ -138,13 +138,14 @@ int make_tiled_4d_bf16_noswizzle(CUtensorMap* map, const void* base, uint64_t co
 }
 
 int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int img_rows,
-                          int R, int S,
+                          int img_cols, int R, int S,
                           int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                           uint32_t channels, uint32_t pixels) {
   int st = load_driver();
   if (st != DL_OK) return st;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)img_rows * W * ldx * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)img_cols * ldx * 2,
+                           (cuuint64_t)img_rows * img_cols * ldx * 2};
   // Bounding box of the filter's top-left anchor: starts at -pad and stops so that the last tap
   // (offset (S-1)*dil) still lies within the padded image.
   int lower[2] = {-pad_w, -pad_h};
@@ -159,7 +160,7 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
   // Drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (a flag in the
   // second descriptor word that must be clear); same remedy as NVIDIA's own conv templates apply.
   if (g_driver_version <= 13010) {
-    uint64_t bytes = (uint64_t)N * img_rows * W * ldx * 2;
+    uint64_t bytes = (uint64_t)N * img_rows * img_cols * ldx * 2;
     if (bytes < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
   }
   return DL_OK;
@@ -168,15 +169,17 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 }  // namespace dl
 
 namespace dl {
-static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1};
+static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1}, g_opt_dbg{0};
 int opt_pair() { return g_opt_pair.load(std::memory_order_relaxed); }
 int opt_pair_resident() { return g_opt_pair_resident.load(std::memory_order_relaxed); }
+int opt_dbg() { return g_opt_dbg.load(std::memory_order_relaxed); }
 }  // namespace dl
 
 extern "C" {
 int dl_set_option(const char* name, int value) {
   if (!name) return DL_ERR_INVALID;
   if (!strcmp(name, "pair")) { dl::g_opt_pair.store(value); return DL_OK; }
+  if (!strcmp(name, "dbg")) { dl::g_opt_dbg.store(value); return DL_OK; }
   if (!strcmp(name, "pair_resident")) { dl::g_opt_pair_resident.store(value); return DL_OK; }
   return dl::fail(DL_ERR_INVALID, "unknown option '%s'", name);
 }

@@ -14,6 +14,7 @@ int check_launch(const char* what);          // cudaGetLastError -> DL_OK / DL_E
 int device_sm_count();
 int require_sm100();
 int opt_pair();            // tuning switches (dl_set_option): CTA-pair kernels on / off
+int opt_dbg();
 int opt_pair_resident();   // resident weight-half variant of the pair kernel on / off                          // DL_OK or DL_ERR_UNSUPPORTED
 
 // 2-D tiled map over a row-major (rows, cols) 16-bit matrix with row pitch `ld` elements;
@@ -32,7 +33,7 @@ int make_tiled_4d_bf16_noswizzle(CUtensorMap* map, const void* base, uint64_t co
 // im2col map over an NHWC 16-bit activation tensor (pitch ldx elements per pixel): loads
 // `pixels` output positions x `channels` channels per request, 128-byte swizzle, zero OOB fill.
 int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ldx, int img_rows,
-                          int R, int S,
+                          int img_cols, int R, int S,
                           int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                           uint32_t channels, uint32_t pixels);
 

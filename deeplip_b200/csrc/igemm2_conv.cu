@@ -129,8 +129,11 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               const uint32_t lbar = mapa_shared(smem_u32(&full[stage]), 0);       // the leader's barrier
               if (rank == 0) mbar_expect_tx_cluster(lbar, 2u * Cfg::STAGE_BYTES);
               else mbar_arrive_cluster(lbar);
-              tma2_load_im2col_4d(sa, &mapA, lbar, cc * 64, w0, h0, img, (uint16_t)(s * p.dil_w),
-                                  (uint16_t)(r * p.dil_h));
+              if (p.lin)                   // guarded-linear A: the tile's rows shifted by the tap, plain 2D box
+                tma2_load_2d(sa, &mapA, lbar, cc * 64, m0 + (r * p.dil_h - p.pad_h) * p.lin_w + s * p.dil_w - p.pad_w);
+              else
+                tma2_load_im2col_4d(sa, &mapA, lbar, cc * 64, w0, h0, img, (uint16_t)(s * p.dil_w),
+                                    (uint16_t)(r * p.dil_h));
               if (!kResB)
                 tma2_load_2d(sa + Cfg::A_BYTES, &mapB, lbar, kb * 64, n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -158,7 +161,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const uint64_t adesc = umma_desc_sw128_kmajor(sa);
           const uint64_t bdesc = umma_desc_sw128_kmajor(kResB ? smem_u32(bres) + kb * Cfg::B_BYTES : sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < ((p.dbg & 8) ? 1 : 4); ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma2_commit_both(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -170,20 +173,21 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   } else {
     const int quarter = warp & 3;
     const int chunk0 = (warp - 2) >> 2;
-    const bool has_res = p.residual != nullptr;
+    const bool has_res = p.residual != nullptr && !(p.dbg & 1);
     const bool fast = p.y != nullptr && p.yf == nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < total; t += num_pairs) {
       const int mp = t / p.num_n_blocks;
       const int n_blk = t - mp * p.num_n_blocks;
-      const long long row = (long long)(2 * mp + (int)rank) * 128 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      long long row = (long long)(2 * mp + (int)rank) * 128 + quarter * 32 + lane;
+      const bool row_ok = igemm_map_row(p, row) && !(p.dbg & 2);
       const int cbase = n_blk * BLOCK_N;
       uint4 res[4];
       igemm_prefetch_residual(p, row, row_ok, cbase, chunk0, has_res, res);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (!(p.dbg & 4))
       igemm_epilogue_tile<BLOCK_N>(p, prm, Cfg::PSTRIDE, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
                                    res);
       tc_fence_before();

@@ -16,6 +16,9 @@ struct IgemmParams {
   int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   int num_m_blocks, num_n_blocks;
   int ldy, ldf;
+  int lin, lin_w, lin_h, valid_w, valid_h;   // guarded-linear operand A (tiled TMA): geometry and stored extents
+  int dbg;
+  int out_hp, out_wp;                        // im2col mode writing into a guarded tensor (0 = dense)
   float f32_slope;
   const float* scale;
   const float* shift;
@@ -26,6 +29,24 @@ struct IgemmParams {
   uint16_t* y;
   float* yf;
 };
+
+// GEMM row -> row of y / residual, and whether it is stored at all.
+__device__ __forceinline__ bool igemm_map_row(const IgemmParams& p, long long& row) {
+  if (row >= p.M) return false;
+  if (p.lin) {                                   // same geometry in and out; guard positions are never written
+    const int r = (int)row;
+    const int line = r / p.lin_w;
+    return r - line * p.lin_w < p.valid_w && line % p.lin_h < p.valid_h;
+  }
+  if (p.out_wp > 0) {
+    const int r = (int)row;
+    const int img = r / p.PQ;
+    const int rem = r - img * p.PQ;
+    const int pp = rem / p.Q;
+    row = ((long long)img * p.out_hp + pp) * p.out_wp + (rem - pp * p.Q);
+  }
+  return true;
+}
 
 // Residual rows of this warp's first 32-channel chunk, requested BEFORE the wait on the accumulator so that the
 // L2 round trip overlaps the tile's MMAs.

@@ -122,8 +122,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               mbar_wait(&empty[stage], phase ^ 1);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
               mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-              tma_load_im2col_4d(sa, &mapA, &full[stage], cc * 64, w0, h0, img, (uint16_t)(s * p.dil_w),
-                                 (uint16_t)(r * p.dil_h));
+              if (p.lin)                   // guarded-linear A: the tile's rows shifted by the tap, plain 2D box
+                tma_load_2d(sa, &mapA, &full[stage], cc * 64, m0 + (r * p.dil_h - p.pad_h) * p.lin_w + s * p.dil_w - p.pad_w);
+              else
+                tma_load_im2col_4d(sa, &mapA, &full[stage], cc * 64, w0, h0, img, (uint16_t)(s * p.dil_w),
+                                   (uint16_t)(r * p.dil_h));
               if (!kResB) tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full[stage], kb * 64, n_blk * BLOCK_N);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -173,8 +176,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_blocks;
       const int n_blk = tile - m_blk * p.num_n_blocks;
-      const long long row = (long long)m_blk * Cfg::BLOCK_M + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      long long row = (long long)m_blk * Cfg::BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = igemm_map_row(p, row);
       const int cbase = n_blk * BLOCK_N;
       // residual of this warp's first chunk: requested BEFORE waiting for the accumulator so the L2 round trip
       // overlaps the tile's MMAs
@@ -244,9 +247,23 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
                "conv_igemm: bad filter geometry");
   DL_CHECK_ARG((d->S - 1) * d->dil_w <= 255 && (d->R - 1) * d->dil_h <= 255 && d->pad_w <= 127 && d->pad_h <= 127,
                "conv_igemm: filter extent exceeds the TMA im2col offset range");
-  const int P = (d->H + 2 * d->pad_h - d->dil_h * (d->R - 1) - 1) / d->stride_h + 1;
-  const int Q = (d->W + 2 * d->pad_w - d->dil_w * (d->S - 1) - 1) / d->stride_w + 1;
-  DL_CHECK_ARG(P > 0 && Q > 0, "conv_igemm: input smaller than the filter");
+  const bool lin = d->lin != 0;
+  int P, Q;
+  if (lin) {
+    DL_CHECK_ARG(d->stride_h == 1 && d->stride_w == 1, "conv_igemm: lin mode needs stride 1");
+    DL_CHECK_ARG(d->valid_h >= 1 && d->valid_h <= d->H && d->valid_w >= 1 && d->valid_w <= d->W,
+                 "conv_igemm: lin mode needs 1 <= valid_h <= H and 1 <= valid_w <= W");
+    DL_CHECK_ARG(d->img_rows == 0 && d->img_cols == 0 && d->out_img_rows == 0 && d->out_img_cols == 0,
+                 "conv_igemm: lin mode takes its pitches from H and W");
+    P = d->H; Q = d->W;
+  } else {
+    P = (d->H + 2 * d->pad_h - d->dil_h * (d->R - 1) - 1) / d->stride_h + 1;
+    Q = (d->W + 2 * d->pad_w - d->dil_w * (d->S - 1) - 1) / d->stride_w + 1;
+    DL_CHECK_ARG(P > 0 && Q > 0, "conv_igemm: input smaller than the filter");
+    DL_CHECK_ARG((d->out_img_rows == 0) == (d->out_img_cols == 0), "conv_igemm: out_img_rows/cols must come together");
+    DL_CHECK_ARG(d->out_img_rows == 0 || (d->out_img_rows >= P && d->out_img_cols >= Q),
+                 "conv_igemm: output pitches smaller than the output");
+  }
   int st = require_sm100();
   if (st != DL_OK) return st;
 
@@ -261,6 +278,9 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   p.pad_h = d->pad_h; p.pad_w = d->pad_w;
   p.dil_h = d->dil_h; p.dil_w = d->dil_w;
   p.ldy = d->ldy; p.ldf = d->ldf;
+  p.lin = lin ? 1 : 0; p.lin_w = d->W; p.lin_h = d->H; p.valid_w = d->valid_w; p.valid_h = d->valid_h;
+  p.dbg = opt_dbg();
+  p.out_hp = lin ? 0 : d->out_img_rows; p.out_wp = lin ? 0 : d->out_img_cols;
   p.f32_slope = d->f32_slope;
   p.scale = scale; p.shift = shift; p.slope = slope; p.scale2 = scale2; p.shift2 = shift2;
   p.residual = static_cast<const uint16_t*>(residual);
@@ -273,10 +293,15 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   const long long Ktot = (long long)d->R * d->S * p.cchunks * 64;
 
   CUtensorMap mapA, mapB;
-  const int img_rows = d->img_rows > 0 ? d->img_rows : d->H;
-  DL_CHECK_ARG(img_rows >= d->H, "conv_igemm: img_rows < H");
-  st = make_im2col_nhwc_bf16(&mapA, x, d->N, d->H, d->W, d->C, d->ldx, img_rows, d->R, d->S, d->stride_h, d->stride_w, d->pad_h,
-                             d->pad_w, d->dil_h, d->dil_w, 64, 128);
+  if (lin) {
+    st = make_tiled_2d_bf16(&mapA, x, (uint64_t)M, (uint64_t)d->C, (uint64_t)d->ldx, 128, 64);
+  } else {
+    const int img_rows = d->img_rows > 0 ? d->img_rows : d->H;
+    const int img_cols = d->img_cols > 0 ? d->img_cols : d->W;
+    DL_CHECK_ARG(img_rows >= d->H && img_cols >= d->W, "conv_igemm: img_rows < H or img_cols < W");
+    st = make_im2col_nhwc_bf16(&mapA, x, d->N, d->H, d->W, d->C, d->ldx, img_rows, img_cols, d->R, d->S, d->stride_h,
+                               d->stride_w, d->pad_h, d->pad_w, d->dil_h, d->dil_w, 64, 128);
+  }
   if (st != DL_OK) return st;
   const long long num_kb = (long long)d->R * d->S * p.cchunks;
   const bool resident = p.num_n_blocks == 1 && num_kb * block_n * 128 <= kResidentBBytes;

@@ -7,7 +7,7 @@
 // (7 rows x 8 columns of the 7x7 window, zero-weight padding) -> one 64-wide K block per temporal tap.
 // With a single input channel TMA im2col cannot form operand A (16-byte minimum inner extent), so 8 producer
 // warps build the 128B-swizzled K-major A tile in shared memory from a small staged input strip; a single
-// thread issues tcgen05.mma into a double-buffered TMEM accumulator; 4 epilogue warps apply BN+PReLU, park the
+// thread issues tcgen05.mma into a double-buffered TMEM accumulator; 8 epilogue warps apply BN+PReLU, park the
 // bf16 conv rows in a shared-memory ring and max-pool completed rows straight to global memory.
 //
 // Roofline: tensor pipe; algorithmic work 2*Ho*Wo*64*245 flop per frame (DESIGN.md "Kernels").
@@ -16,17 +16,19 @@
 
 namespace dl {
 
-constexpr int kStemAStages = 4;
+constexpr int kStemAStages = 6;                     // even: builder group g owns stages g, g+2, ...
 constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 64 K (bf16)
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
-constexpr int kStemThreads = 14 * 32;               // 4 epilogue + 1 MMA + 1 TMA + 8 builder warps
-constexpr int kStripSlots = 6;                      // strip ring: slot s % 6 -> consumer group s % 2
+constexpr int kStemThreads = 18 * 32;               // 8 epilogue + 1 MMA + 1 TMA + 8 builder warps
+constexpr int kStemEpiThreads = 256;
+constexpr int kStripSlotsMax = 16;                  // strip ring (even count, p.strip_slots): slot s % slots -> consumer group s % 2
+constexpr int kStemBars = 2 * kStemAStages + 5 + 2 * kStripSlotsMax;
 constexpr int kStripRowsMax = 24;                   // strip rows per stage (TMA box height)
 
 struct StemParams {
   int B, T, H, W;
   int Ho, Wo, Hp, Wp, Mf, tiles_per_frame;
-  int ring_rows;        // power of two
+  int ring_rows;        // conv rows parked for pooling (any count >= span + 6)
   int strip_rows, strip_pitch;                      // pitch = roundup8(W + 8) elements (cols c = ix + 3)
   const float* scale;
   const float* shift;
@@ -34,6 +36,8 @@ struct StemParams {
   uint16_t* y;
   int frames;
   int out_img_rows;     // row pitch of one output frame (>= Hp)
+  int strip_slots;
+  int dbg;
 };
 
 // (frame, tile, temporal tap) of a pipeline stage; every role walks the same sequence.
@@ -65,17 +69,17 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // kStripSlots x strip_rows x strip_pitch bf16
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const int strip_buf = (strip_elems + 63) & ~63;
-  float* chan = reinterpret_cast<float*>(strip + kStripSlots * strip_buf);   // scale, shift, slope
+  float* chan = reinterpret_cast<float*>(strip + p.strip_slots * strip_buf);   // scale, shift, slope
   uint64_t* bars = reinterpret_cast<uint64_t*>(chan + 192);
   uint64_t* full = bars;                         // [kStemAStages]
   uint64_t* empty = bars + kStemAStages;         // [kStemAStages]
   uint64_t* tfull = bars + 2 * kStemAStages;     // [2]
   uint64_t* tempty = tfull + 2;                  // [2]
   uint64_t* wbar = tempty + 2;                   // [1]
-  uint64_t* sfull = wbar + 1;                    // [kStripSlots] strip slot filled (its loader warp)
-  uint64_t* sempty = sfull + kStripSlots;        // [kStripSlots] strip slot consumed (4 builder warps of one group)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + kStripSlots);
-  int* tile_iy0 = reinterpret_cast<int*>(sempty + kStripSlots + 1);   // [tiles_per_frame <= 64] first input row of a tile's strip
+  uint64_t* sfull = wbar + 1;                    // [kStripSlotsMax] strip slot filled (its loader warp)
+  uint64_t* sempty = sfull + kStripSlotsMax;     // [kStripSlotsMax] strip slot consumed (4 builder warps of one group)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + kStripSlotsMax);
+  int* tile_iy0 = reinterpret_cast<int*>(sempty + kStripSlotsMax + 1);   // [tiles_per_frame <= 64] first input row of a tile's strip
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,20 +89,20 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
     chan[i] = i < 64 ? p.scale[c] : (i < 128 ? p.shift[c] : p.slope[c]);
   }
   for (int i = threadIdx.x; i < p.tiles_per_frame; i += kStemThreads) tile_iy0[i] = 2 * ((i * 128) / p.Wo) - 3;
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       for (int s = 0; s < kStemAStages; ++s) {
         mbar_init(&full[s], 4);      // one elected arrive per builder warp of the owning group
         mbar_init(&empty[s], 1);
       }
-      for (int s = 0; s < kStripSlots; ++s) {
+      for (int s = 0; s < p.strip_slots; ++s) {
         mbar_init(&sfull[s], 1);      // the producer's expect_tx arrive
         mbar_init(&sempty[s], 4);
       }
       mbar_init(&tfull[0], 1);
       mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], 128);
-      mbar_init(&tempty[1], 128);
+      mbar_init(&tempty[0], kStemEpiThreads);
+      mbar_init(&tempty[1], kStemEpiThreads);
       mbar_init(wbar, 1);
       fence_mbar_init();
       tma_prefetch_desc(&mapW);
@@ -112,12 +116,12 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 6) {
+  if (warp >= 10) {
     // =============================================================== builders: operand A from the staged strip
     // Two groups of 4 warps alternate pipeline stages (group g owns stages s = g, g+2, ...), so two A tiles are
     // in flight; thread <-> A-tile row (conv pixel), 8 chunks of 16 B: chunk kh = 8 consecutive input pixels of
     // window row kh (chunk 7 = zero padding of K).
-    const int bt = threadIdx.x - 6 * 32;          // 0..255
+    const int bt = threadIdx.x - 10 * 32;         // 0..255
     const int group = bt >> 7;
     const int arow = bt & 127;
     const int SP = p.strip_pitch;
@@ -127,9 +131,9 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
     uint32_t arel = 0;
     bool avalid = false;
     uint32_t sslot = group, sph = 0;              // strip ring position of stage s: s % kStripSlots, (s / kStripSlots) & 1
-    for (uint32_t s = group; cur.frame < p.frames; s += 2) {
-      const int slot = s & 3;
-      const uint32_t ph = (s >> 2) & 1;
+    int slot = group;                             // A stage of pipeline step s: s % kStemAStages, phase (s / kStemAStages) & 1
+    uint32_t ph = 0;
+    for (; cur.frame < p.frames;) {
       if (cur.tile != cached_tile || cur.frame != cached_frame) {
         cached_tile = cur.tile; cached_frame = cur.frame;
         const int m = cur.tile * 128 + arow;
@@ -143,7 +147,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
 #pragma unroll
       for (int kh = 0; kh < 7; ++kh) {
         v[kh] = make_uint4(0u, 0u, 0u, 0u);
-        if (avalid) {
+        if (avalid && !(p.dbg & 16)) {
           const uint32_t* sp = srow + kh * (SP >> 1);
           v[kh].x = sp[0]; v[kh].y = sp[1]; v[kh].z = sp[2]; v[kh].w = sp[3];
         }
@@ -152,7 +156,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
       mbar_wait(&empty[slot], ph ^ 1);
       uint8_t* dst_row = smA + slot * kStemABytes + arow * 128;
 #pragma unroll
-      for (int kh = 0; kh < 8; ++kh) *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v[kh];
+      for (int kh = 0; kh < 8; ++kh) if (!(p.dbg & 16)) *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v[kh];
       // one proxy fence covers both hand-offs: the A tile written above becomes visible to the tensor core (async
       // proxy), and the strip reads are performed before TMA may refill the slot (an arrive issued right after the
       // loads can overtake them)
@@ -163,11 +167,13 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
         mbar_arrive(&full[slot]);
       }
       sslot += 2;
-      if (sslot >= kStripSlots) { sslot -= kStripSlots; sph ^= 1; }
+      if (sslot >= (uint32_t)p.strip_slots) { sslot -= p.strip_slots; sph ^= 1; }
+      slot += 2;
+      if (slot >= kStemAStages) { slot -= kStemAStages; ph ^= 1; }
       cur.advance();
       cur.advance();
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =============================================================== strip producer: one thread, TMA only
     // The input was normalised / zero-bordered once by stem_prepass_kernel into (B, T, H+8, pitch) bf16, so the
     // strip of a stage is a plain 2-D box of that tensor: rows iy0 .. iy0+strip_rows-1 of frame t+kt-2 (a frame
@@ -183,10 +189,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
         mbar_wait(&sempty[slot], ph ^ 1);
         mbar_expect_tx(&sfull[slot], strip_bytes);
         tma_load_4d(strip + slot * strip_buf, &mapX, &sfull[slot], 0, tile_iy0[cur.tile] + 3, ft + cur.kt - 2, fb);
-        if (++slot == kStripSlots) { slot = 0; ph ^= 1; }
+        if (++slot == (uint32_t)p.strip_slots) { slot = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // =============================================================== MMA issuer
     if (lane == 0) {
       mbar_expect_tx(wbar, kStemBBytes);
@@ -208,7 +214,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
             const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smA + stage * kStemABytes));
             const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smB + kt * 8192));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kt | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < ((p.dbg & 8) ? 1 : 4); ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kt | k) != 0 ? 1u : 0u);
             umma_commit(&empty[stage]);
             if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
           }
@@ -220,61 +226,61 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
     }
   } else {
     // =============================================================== epilogue: BN + PReLU -> ring -> max-pool
-    const int et = threadIdx.x;                 // 0..127 ; warp == TMEM lane quarter
+    // 8 warps: warp & 3 = TMEM lane quarter (tile rows 32*(warp&3) ..), warp >> 2 = channel half (32 channels)
+    const int et = threadIdx.x;                 // 0..255
+    const int erow = et & 127;
+    const int half = et >> 7;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int ring_mask = p.ring_rows - 1;
     const int row_bytes = p.Wo * 128;
     for (int frame = blockIdx.x; frame < p.frames; frame += gridDim.x) {
       int py_done = 0;
       uint16_t* yframe = p.y + (size_t)frame * p.out_img_rows * p.Wp * 64;
       for (int tile = 0; tile < p.tiles_per_frame; ++tile) {
-        const int m = tile * 128 + et;
+        const int m = tile * 128 + erow;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 64;
-        tmem_ld_32x32(taddr, r0);
-        tmem_ld_32x32(taddr + 32, r1);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * 64 + half * 32, r);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        if (m < p.Mf) {
+        if (m < p.Mf && !(p.dbg & 32)) {
           const int yy = m / p.Wo, xx = m - yy * p.Wo;
-          uint8_t* dst = ring + (yy & ring_mask) * row_bytes + xx * 128;
-          const float4* c4 = reinterpret_cast<const float4*>(chan);
+          uint8_t* dst = ring + (yy % p.ring_rows) * row_bytes + xx * 128;
+          const float4* c4 = reinterpret_cast<const float4*>(chan) + half * 8;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
+          for (int ch = 0; ch < 4; ++ch) {
             float v[8];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float4 sc = c4[2 * ch + h], sh = c4[16 + 2 * ch + h], sl = c4[32 + 2 * ch + h];
               const int c = ch * 8 + 4 * h;
               float z;
-              z = fmaf(__uint_as_float(c < 32 ? r0[c] : r1[c - 32]), sc.x, sh.x);         v[4 * h + 0] = z > 0.f ? z : z * sl.x;
-              z = fmaf(__uint_as_float(c < 32 ? r0[c + 1] : r1[c - 31]), sc.y, sh.y);     v[4 * h + 1] = z > 0.f ? z : z * sl.y;
-              z = fmaf(__uint_as_float(c < 32 ? r0[c + 2] : r1[c - 30]), sc.z, sh.z);     v[4 * h + 2] = z > 0.f ? z : z * sl.z;
-              z = fmaf(__uint_as_float(c < 32 ? r0[c + 3] : r1[c - 29]), sc.w, sh.w);     v[4 * h + 3] = z > 0.f ? z : z * sl.w;
+              z = fmaf(__uint_as_float(r[c]), sc.x, sh.x);         v[4 * h + 0] = z > 0.f ? z : z * sl.x;
+              z = fmaf(__uint_as_float(r[c + 1]), sc.y, sh.y);     v[4 * h + 1] = z > 0.f ? z : z * sl.y;
+              z = fmaf(__uint_as_float(r[c + 2]), sc.z, sh.z);     v[4 * h + 2] = z > 0.f ? z : z * sl.z;
+              z = fmaf(__uint_as_float(r[c + 3]), sc.w, sh.w);     v[4 * h + 3] = z > 0.f ? z : z * sl.w;
             }
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(dst + ((ch ^ (xx & 7)) << 4)) = o;
+            *reinterpret_cast<uint4*>(dst + (((half * 4 + ch) ^ (xx & 7)) << 4)) = o;
           }
         }
-        named_bar_sync(2, 128);
+        named_bar_sync(2, kStemEpiThreads);
         // pooled rows whose three conv rows are now complete
         const int m_end = min((tile + 1) * 128, p.Mf);
         const int rows_complete = m_end / p.Wo;               // conv rows 0 .. rows_complete-1 are final
         const int py_ready = rows_complete / 2;               // needs conv row 2*py+1 <= rows_complete-1
-        for (int py = py_done; py < py_ready; ++py) {
+        for (int py = py_done; py < py_ready && !(p.dbg & 32); ++py) {
           const int cy0 = max(2 * py - 1, 0);                  // clamped rows/cols repeat an element: max unchanged
-          const uint8_t* r0p = ring + (cy0 & ring_mask) * row_bytes;
-          const uint8_t* r1p = ring + ((2 * py) & ring_mask) * row_bytes;
-          const uint8_t* r2p = ring + ((2 * py + 1) & ring_mask) * row_bytes;
-          for (int it = et; it < p.Wp * 8; it += 128) {
+          const uint8_t* r0p = ring + (cy0 % p.ring_rows) * row_bytes;
+          const uint8_t* r1p = ring + ((2 * py) % p.ring_rows) * row_bytes;
+          const uint8_t* r2p = ring + ((2 * py + 1) % p.ring_rows) * row_bytes;
+          for (int it = et; it < p.Wp * 8; it += kStemEpiThreads) {
             const int ch = it & 7, px = it >> 3;
             const int cx1 = 2 * px, cx2 = cx1 + 1, cx0 = max(cx1 - 1, 0);
             const int o0 = cx0 * 128 + ((ch ^ (cx0 & 7)) << 4);
@@ -305,14 +311,14 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
           }
         }
         py_done = py_ready;
-        named_bar_sync(2, 128);
+        named_bar_sync(2, kStemEpiThreads);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc<128>(tmem_base);
   }
@@ -381,9 +387,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   p.Mf = p.Ho * p.Wo;
   p.tiles_per_frame = (p.Mf + 127) / 128;
   const int span = (127 + p.Wo - 1) / p.Wo;           // extra conv rows a tile can reach past its first row
-  int rr = 1;
-  while (rr < span + 6) rr <<= 1;
-  p.ring_rows = rr;
+  p.ring_rows = span + 6;
   p.strip_rows = 2 * span + 7;
   p.strip_pitch = (W + 8 + 7) / 8 * 8;
   DL_CHECK_ARG(p.strip_rows <= kStripRowsMax, "stem: frame too narrow (strip of %d rows)", p.strip_rows);
@@ -391,6 +395,8 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   p.y = static_cast<uint16_t*>(y);
   p.frames = B * T;
   p.out_img_rows = out_img_rows > 0 ? out_img_rows : p.Hp;
+  p.dbg = opt_dbg();
+  p.strip_slots = (p.dbg >> 8) ? (p.dbg >> 8) : 6;
   DL_CHECK_ARG(p.out_img_rows >= p.Hp, "stem: out_img_rows < H/4");
   DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
 
@@ -410,7 +416,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
-                      kStripSlots * (size_t)((strip_elems + 63) & ~63) * 2 + 192 * 4 + 32 * 8 + 16 + 64 * 4;
+                      p.strip_slots * (size_t)((strip_elems + 63) & ~63) * 2 + 192 * 4 + (kStemBars + 1) * 8 + 16 + 64 * 4;
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
   CUtensorMap mapW, mapX;
   st = make_tiled_2d_bf16(&mapW, w_packed, 64, 320, 320, 64, 64);

@@ -107,34 +107,64 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
 # ------------------------------------------------------------------ K3 / K5 / K7
 def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=(1, 1), scale=None, shift=None,
                slope=None, residual=None, want_bf16=True, want_f32=False, scale2=None, shift2=None,
-               f32_slope=1.0, H=None, out=None, out_channel_offset=0):
-    """x: (N,H,W,ldx) bf16 channels-last -- or (N,img_rows,W,ldx) stacked rows with the true height passed as H.
-    Returns (y_bf16 (N,P,Q,Cout) | None, y_f32 (N*P*Q,Cout) | None)."""
+               f32_slope=1.0, H=None, W=None, out=None, out_channel_offset=0):
+    """x: (N,H,W,ldx) bf16 channels-last -- or (N,img_rows,img_cols,ldx) stacked / guarded with the true extents
+    passed as H, W.  `out` may be a wider (channel slice) and / or guarded (N, >=P, >=Q, ld) caller-owned buffer.
+    Returns (y_bf16 (N,P,Q,Cout) | out | None, y_f32 (N*P*Q,Cout) | None)."""
     _need_cuda(x, w_packed, scale, shift, slope, residual, scale2, shift2)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
-    N, img_rows, W, ldx = x.shape
+    N, img_rows, img_cols, ldx = x.shape
     H = H or img_rows
+    W = W or img_cols
     P = (H + 2 * pad[0] - dil[0] * (R - 1) - 1) // stride[0] + 1
     Q = (W + 2 * pad[1] - dil[1] * (S - 1) - 1) // stride[1] + 1
     ldy = Cout
     y_ptr = None
+    out_rows = out_cols = 0
     if out is not None:          # write Cout channels into a slice of a wider channels-last buffer (concat for free)
-        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape[:3] == (N, P, Q)
-        assert out_channel_offset % 8 == 0 and out_channel_offset + Cout <= out.shape[3] and residual is None
+        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.dim() == 4 and out.shape[0] == N
+        assert out.shape[1] >= P and out.shape[2] >= Q
+        assert out_channel_offset % 8 == 0 and out_channel_offset + Cout <= out.shape[3]
+        if tuple(out.shape[1:3]) != (P, Q):
+            out_rows, out_cols = out.shape[1], out.shape[2]
+            assert not want_f32
         y, ldy = out, out.shape[3]
         y_ptr = C.c_void_p(out.data_ptr() + 2 * out_channel_offset)
+        assert residual is None or (out_channel_offset == 0 and residual.shape == out.shape)
     else:
         y = torch.empty((N, P, Q, Cout), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     yf = torch.empty((N * P * Q, Cout), device=x.device, dtype=torch.float32) if want_f32 else None
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.numel() == y.numel()
     d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ldy, Cout,
-                 float(f32_slope), img_rows)
+                 float(f32_slope), img_rows, img_cols, 0, 0, 0, out_rows, out_cols)
     st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
                                        _ptr(residual), y_ptr if y_ptr is not None else _ptr(y), _ptr(yf),
                                        _ptr(scale2), _ptr(shift2), C.byref(d), _stream())
     _lib.check(st, 'dl_conv_igemm_bf16')
     return y, yf
+
+
+def conv_igemm_lin(x, w_packed, Cin, Cout, valid, R=1, S=1, pad=(0, 0), dil=(1, 1), scale=None, shift=None,
+                   slope=None, residual=None, out=None):
+    """Stride-1 convolution on a guarded tensor (include/deeplip_b200.h, "Guarded layouts"): x, out and residual
+    are (N, Hg, Wg, ld) bf16 whose guard rows / columns (>= pad below / right of every image) are zero; outputs
+    are stored for h < valid[0], w < valid[1] only.  `out` None allocates a zeroed tensor."""
+    _need_cuda(x, w_packed, scale, shift, slope, residual, out)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    N, Hg, Wg, ldx = x.shape
+    if out is None:
+        out = torch.zeros((N, Hg, Wg, Cout), device=x.device, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and tuple(out.shape[:3]) == (N, Hg, Wg)
+    assert out.shape[3] >= Cout
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == out.shape
+    d = ConvDesc(N, Hg, Wg, Cin, ldx, Cout, R, S, 1, 1, pad[0], pad[1], dil[0], dil[1], out.shape[3], Cout,
+                 1.0, 0, 0, 1, valid[0], valid[1], 0, 0)
+    st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
+                                       _ptr(residual), _ptr(out), None, None, None, C.byref(d), _stream())
+    _lib.check(st, 'dl_conv_igemm_bf16')
+    return out
 
 
 def conv3x3_halo(x, w_packed, scale, shift, slope, H, out, residual=None):

@@ -89,6 +89,20 @@ int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, 
  *     y_f32    : (N*P*Q, ldf) f32 or NULL = lrelu(acc * scale2[c] + shift2[c], f32_slope)  (side output,
  *                e.g. x_a of extract_embedding, tdnn.py:93; scale2/shift2 NULL = raw accumulator)
  *     Cout % 8 == 0.
+ *
+ *     Guarded layouts.  TMA im2col delivers ~5 cycles per pixel row on B200, which bounds every stride-1
+ *     layer below the tensor pipe; plain tiled TMA boxes are several times faster.  A stride-1 convolution
+ *     can use them when the zero padding is materialised in the tensor itself:
+ *       lin = 1 : x, y and residual all are (N, H, W, ld) where H and W INCLUDE the guard rows / columns
+ *                 (>= pad_h rows below and >= pad_w columns right of every image, kept zero by the caller).
+ *                 Output pixel (n, h, w) sits at the same (n, h, w) as the input pixel under the filter
+ *                 anchor + pad; it is stored only for h < valid_h and w < valid_w, so the guards stay zero.
+ *                 Tap (r, s) of a 128-pixel tile is the tile's row range shifted by
+ *                 (r*dil_h - pad_h) * W + (s*dil_w - pad_w) rows.  stride must be 1.  Conv1d over
+ *                 (B, T, C) needs no guards at all: H = 1, W = T, valid_w = T - (S-1)*dil (tdnn.py:35-43).
+ *       out_img_rows / out_img_cols : (lin = 0) the im2col kernel writes y / reads residual at
+ *                 ((n * out_img_rows + p) * out_img_cols + q) instead of the dense (n*P + p)*Q + q, i.e.
+ *                 straight into a guarded tensor;  img_rows / img_cols: it reads x from one.
  */
 typedef struct dl_conv_desc {
   int N, H, W, C, ldx;
@@ -96,7 +110,11 @@ typedef struct dl_conv_desc {
   int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   int ldy, ldf;
   float f32_slope;   /* leaky slope applied to the f32 side output (1.0f = none) */
-  int img_rows;      /* row pitch of one input image (>= H; 0 = H): input may be in the stacked-rows layout */
+  int img_rows;      /* row pitch of one input image (>= H; 0 = H): input may be in a stacked / guarded layout */
+  int img_cols;      /* column pitch of one input row (>= W; 0 = W) */
+  int lin;           /* 1 = guarded-linear operand A (tiled TMA), see above */
+  int valid_h, valid_w;            /* lin = 1: extents of the stored outputs */
+  int out_img_rows, out_img_cols;  /* lin = 0: pitches of y / residual (0 = dense P, Q) */
 } dl_conv_desc;
 
 int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,

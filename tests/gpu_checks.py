@@ -64,6 +64,68 @@ def conv_case(N, H, W, C, Cout, R, S, stride=1, pad=0, dil=(1, 1), residual=Fals
     return out
 
 
+def conv_lin_case(N, H, W, C, Cout, R, S, pad=(0, 0), dil=(1, 1), guard=(0, 0), residual=False, seed=0, tol=1.5e-2):
+    """Guarded-linear operand A (tiled TMA) vs F.conv2d: stride 1, guards of `guard` rows / columns."""
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(N, H, W, C, generator=g))
+    w = bf16r(torch.randn(Cout, C, R, S, generator=g) / (C * R * S) ** 0.5)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.2
+    slope = torch.rand(Cout, generator=g) * 0.5
+    acc = F.conv2d(x.permute(0, 3, 1, 2), w, None, stride=1, padding=pad, dilation=dil)   # (N,Cout,P,Q)
+    P, Q = acc.shape[2], acc.shape[3]
+    ref = acc * scale[None, :, None, None] + shift[None, :, None, None]
+    Hg, Wg = H + guard[0], W + guard[1]
+    res_g = None
+    if residual:
+        res = bf16r(torch.randn(ref.shape, generator=g))
+        ref = ref + res
+        res_g = torch.zeros(N, Hg, Wg, Cout)
+        res_g[:, :P, :Q] = res.permute(0, 2, 3, 1)
+        res_g = res_g.to(DEV).to(torch.bfloat16)
+    ref = torch.where(ref > 0, ref, ref * slope[None, :, None, None])
+    ld = packing.ceil_to(C, 8)
+    xg = torch.zeros(N, Hg, Wg, ld)
+    xg[:, :H, :W, :C] = x
+    y = ops.conv_igemm_lin(xg.to(DEV).to(torch.bfloat16), packing.pack_conv_weight(w.to(DEV), Cout), C, Cout, (P, Q),
+                           R, S, pad, dil, scale.to(DEV), shift.to(DEV), slope.to(DEV), residual=res_g)
+    torch.cuda.synchronize()
+    yc = y.float().cpu()
+    out = {'bf16_rel': rel_err(yc[:, :P, :Q].permute(0, 3, 1, 2), ref)}
+    mask = torch.ones(Hg, Wg, dtype=torch.bool)
+    mask[:P, :Q] = False
+    out['guard_abs'] = float(yc[:, mask].abs().max()) if mask.any() else 0.0
+    assert out['bf16_rel'] < tol, out
+    assert out['guard_abs'] == 0.0, out
+    return out
+
+
+def conv_guarded_io_case(N=3, H=22, W=22, C=64, Cout=128, R=3, S=3, stride=2, pad=1, seed=0, tol=1.5e-2):
+    """im2col kernel reading a guarded input (img_rows / img_cols) and writing a guarded output."""
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(N, H, W, C, generator=g))
+    w = bf16r(torch.randn(Cout, C, R, S, generator=g) / (C * R * S) ** 0.5)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.2
+    slope = torch.rand(Cout, generator=g) * 0.5
+    acc = F.conv2d(x.permute(0, 3, 1, 2), w, None, stride=stride, padding=pad)
+    P, Q = acc.shape[2], acc.shape[3]
+    ref = acc * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = torch.where(ref > 0, ref, ref * slope[None, :, None, None])
+    xg = torch.zeros(N, H + 1, W + 2, C)
+    xg[:, :H, :W] = x
+    out_buf = torch.zeros(N, P + 1, Q + 1, Cout, device=DEV, dtype=torch.bfloat16)
+    y, _ = ops.conv_igemm(xg.to(DEV).to(torch.bfloat16), packing.pack_conv_weight(w.to(DEV), Cout), C, Cout, R, S,
+                          (stride, stride), (pad, pad), (1, 1), scale.to(DEV), shift.to(DEV), slope.to(DEV),
+                          H=H, W=W, out=out_buf)
+    torch.cuda.synchronize()
+    yc = y.float().cpu()
+    out = {'bf16_rel': rel_err(yc[:, :P, :Q].permute(0, 3, 1, 2), ref),
+           'guard_abs': float(max(yc[:, P:].abs().max(), yc[:, :, Q:].abs().max()))}
+    assert out['bf16_rel'] < tol and out['guard_abs'] == 0.0, out
+    return out
+
+
 def halo_case(N=5, H=22, W=22, residual=True, seed=0):
     """dl_conv3x3_c64_halo_bf16 on the stacked-rows layout vs F.conv2d."""
     g = torch.Generator().manual_seed(seed)

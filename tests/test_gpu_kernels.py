@@ -22,6 +22,24 @@ def test_conv3x3_halo(kw):
     G.halo_case(**kw)
 
 
+@pytest.mark.parametrize('kw', [
+    dict(N=3, H=11, W=11, C=128, Cout=128, R=3, S=3, pad=(1, 1), guard=(1, 1), residual=True),      # 1-CTA kernel
+    dict(N=150, H=11, W=11, C=128, Cout=128, R=3, S=3, pad=(1, 1), guard=(1, 1), residual=True),    # CTA pairs
+    dict(N=600, H=6, W=6, C=256, Cout=256, R=3, S=3, pad=(1, 1), guard=(1, 1)),
+    dict(N=2, H=5, W=9, C=64, Cout=64, R=3, S=3, pad=(2, 2), dil=(2, 2), guard=(2, 3), residual=True),
+    dict(N=2, H=1, W=140, C=512, Cout=512, R=1, S=3, dil=(1, 3)),                                   # TDNN, no guards
+    dict(N=80, H=1, W=300, C=512, Cout=512, R=1, S=5, dil=(1, 1)),
+    dict(N=64, H=1, W=296, C=512, Cout=1504, R=1, S=1),
+])
+def test_conv_igemm_guarded_linear(kw):
+    G.conv_lin_case(**kw)
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(N=2, H=11, W=11, C=128, Cout=256, R=1, S=1, pad=0)])
+def test_conv_igemm_guarded_io(kw):
+    G.conv_guarded_io_case(**kw)
+
+
 def test_conv_igemm_rejects_bad_shapes():
     from deeplip_b200 import ops
     x = torch.zeros(1, 4, 4, 12, device='cuda', dtype=torch.bfloat16)          # ldx not a multiple of 8

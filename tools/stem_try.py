@@ -1,0 +1,18 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from deeplip_b200 import ops, packing, _lib, synth
+from deeplip_b200.pipeline import build_models
+from lin_bench import timeit
+_, video = build_models()
+pk = video._packed()
+B, T = 64, 75
+x = torch.from_numpy(synth.lip_crops_u8([1] * B, T=T, H=96, W=96, seed=3)).cuda()
+cases = []
+for slots in (6,):
+    cases += [(slots << 8, '%d slots full' % slots), ((slots << 8) | 48, '%d slots, MMA only' % slots), ((slots << 8) | 32, '%d slots, epilogue idle' % slots), ((slots << 8) | 16, '%d slots, builders idle' % slots)]
+for dbg, what in cases:
+    _lib.set_option('dbg', dbg)
+    t = timeit(lambda: ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a']), n=10)
+    print('stem %-24s %7.1f us (incl. prepass)' % (what, t), flush=True)
+_lib.set_option('dbg', 0)
