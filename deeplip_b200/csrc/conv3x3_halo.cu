@@ -21,11 +21,10 @@ namespace dl {
 
 constexpr int kHaloPatchRows = 18, kHaloPatchCols = 16;
 constexpr int kHaloPatchBytes = kHaloPatchRows * kHaloPatchCols * 128;   // 36 864
-constexpr int kHaloStages = 3;
+constexpr int kHaloStages = 4;
 constexpr int kHaloWBytes = 9 * 64 * 64 * 2;                             // 73 728 resident weights
-constexpr int kHaloResBytes = 128 * 128;                                 // residual tile: 128 pixels x 64 ch bf16
 constexpr int kHaloThreads = 320;
-constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 2 * kHaloResBytes + 3 * 64 * 4 + 16 * 8 + 16 + 1024;
+constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 3 * 64 * 4 + 16 * 8 + 16 + 1024;
 
 struct HaloParams {
   int rows_total, img_rows, H, W;
@@ -39,22 +38,19 @@ struct HaloParams {
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
-                    const __grid_constant__ CUtensorMap mapR, const HaloParams p) {
+                    const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* patches = smem;
   uint8_t* wres = smem + kHaloStages * kHaloPatchBytes;
-  uint8_t* rbuf = wres + kHaloWBytes;                       // 2 x residual tile (TMA, 128B swizzle)
-  float* prm = reinterpret_cast<float*>(rbuf + 2 * kHaloResBytes);
+  float* prm = reinterpret_cast<float*>(wres + kHaloWBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 192);
   uint64_t* full = bars;
   uint64_t* empty = bars + kHaloStages;
   uint64_t* tfull = bars + 2 * kHaloStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
-  uint64_t* rfull = wfull + 1;                              // [2] residual tile landed
-  uint64_t* rempty = rfull + 2;                             // [2] residual tile consumed (8 epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -62,7 +58,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapW);
-    tma_prefetch_desc(&mapR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -75,10 +70,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       mbar_init(&tempty[0], 256);
       mbar_init(&tempty[1], 256);
       mbar_init(wfull, 1);
-      mbar_init(&rfull[0], 1);
-      mbar_init(&rfull[1], 1);
-      mbar_init(&rempty[0], 8);
-      mbar_init(&rempty[1], 8);
       fence_mbar_init();
     }
     __syncwarp();
@@ -100,8 +91,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &mapW, wfull, tap * 64, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int rs = 0;
-      uint32_t rph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int rt = tile / p.num_groups;
         const int g = tile - rt * p.num_groups;
@@ -110,13 +99,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         mbar_expect_tx(&full[stage], kHaloPatchBytes);
         tma_load_3d(patches + stage * kHaloPatchBytes, &mapX, &full[stage], 0, x0 - 1, rt * 16 - 1);
         if (++stage == kHaloStages) { stage = 0; phase ^= 1; }
-        if (p.residual != nullptr) {                        // residual tile of the same 16 x 8 output pixels
-          mbar_wait(&rempty[rs], rph ^ 1);
-          mbar_expect_tx(&rfull[rs], kHaloResBytes);
-          tma_load_3d(rbuf + rs * kHaloResBytes, &mapR, &rfull[rs], 0, x0, rt * 16);
-          rs ^= 1;
-          if (rs == 0) rph ^= 1;
-        }
       }
     }
   } else if (warp == 1) {
@@ -164,31 +146,29 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     const int rr = m >> 3, xx = m & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int rs = 0;
-    uint32_t rph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    // (stored?, element offset) of this thread's pixel in a tile; same offset in y and residual
+    auto locate = [&](int tile, size_t& off) -> bool {
       const int rt = tile / p.num_groups;
       const int g = tile - rt * p.num_groups;
       const int x0 = min(8 * g, p.W - 8);
       const int R = rt * 16 + rr;
       const int x = x0 + xx;
-      const bool ok = R < p.rows_total && (R % p.img_rows) < p.H && x >= 8 * g;
-      const size_t off = ((size_t)R * p.W + x) * 64 + chunk * 32;
+      off = ((size_t)R * p.W + x) * 64 + chunk * 32;
+      return R < p.rows_total && (R % p.img_rows) < p.H && x >= 8 * g;
+    };
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      size_t off;
+      const bool ok = locate(tile, off);
+      // residual straight from global memory into registers, requested before the wait on the accumulator (staging
+      // it in shared memory through TMA competes with the tensor pipe's operand fetch and was no faster)
       uint4 res[4];
-      if (has_res) {                                        // residual tile staged by TMA: row m, 16-B chunk c at
-        mbar_wait(&rfull[rs], rph);                         // m*128 + ((c ^ (m & 7)) << 4)
-        const uint8_t* rrow = rbuf + rs * kHaloResBytes + m * 128;
+      if (has_res && ok) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          res[q] = *reinterpret_cast<const uint4*>(rrow + (((chunk * 4 + q) ^ (m & 7)) << 4));
-        // The slot is refilled by TMA (async proxy) as soon as all warps have arrived: the generic-proxy reads above
-        // must be PERFORMED first.  Without this fence the arrive overtakes the loads (seen on B200 as ~5 % of
-        // launches with corrupted tiles).
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rempty[rs]);
-        rs ^= 1;
-        if (rs == 0) rph ^= 1;
+        for (int q = 0; q < 4; ++q) res[q] = __ldg(rp + q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) res[q] = make_uint4(0u, 0u, 0u, 0u);
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -270,16 +250,14 @@ extern "C" int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, con
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.residual = static_cast<const uint16_t*>(residual);
   p.y = static_cast<uint16_t*>(y);
-  CUtensorMap mapX, mapW, mapR;
+  CUtensorMap mapX, mapW;
   st = make_tiled_3d_bf16(&mapX, x, (uint64_t)p.rows_total, (uint64_t)W, 64, kHaloPatchRows, kHaloPatchCols, 64);
-  if (st != DL_OK) return st;
-  st = make_tiled_3d_bf16(&mapR, residual ? residual : x, (uint64_t)p.rows_total, (uint64_t)W, 64, 16, 8, 64);
   if (st != DL_OK) return st;
   st = make_tiled_2d_bf16(&mapW, w_packed, 64, 576, 576, 64, 64);
   if (st != DL_OK) return st;
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.total_tiles < grid) grid = p.total_tiles;
-  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(mapX, mapW, mapR, p);
+  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(mapX, mapW, p);
   return check_launch("conv3x3_halo_kernel");
 }

@@ -169,9 +169,10 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 }  // namespace dl
 
 namespace dl {
-static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1}, g_opt_dbg{0};
+static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1}, g_opt_dbg{0}, g_opt_tap_share{1};
 int opt_pair() { return g_opt_pair.load(std::memory_order_relaxed); }
 int opt_pair_resident() { return g_opt_pair_resident.load(std::memory_order_relaxed); }
+int opt_tap_share() { return g_opt_tap_share.load(std::memory_order_relaxed); }
 int opt_dbg() { return g_opt_dbg.load(std::memory_order_relaxed); }
 }  // namespace dl
 
@@ -179,6 +180,7 @@ extern "C" {
 int dl_set_option(const char* name, int value) {
   if (!name) return DL_ERR_INVALID;
   if (!strcmp(name, "pair")) { dl::g_opt_pair.store(value); return DL_OK; }
+  if (!strcmp(name, "tap_share")) { dl::g_opt_tap_share.store(value); return DL_OK; }
   if (!strcmp(name, "dbg")) { dl::g_opt_dbg.store(value); return DL_OK; }
   if (!strcmp(name, "pair_resident")) { dl::g_opt_pair_resident.store(value); return DL_OK; }
   return dl::fail(DL_ERR_INVALID, "unknown option '%s'", name);

@@ -15,6 +15,7 @@ int device_sm_count();
 int require_sm100();
 int opt_pair();            // tuning switches (dl_set_option): CTA-pair kernels on / off
 int opt_dbg();
+int opt_tap_share();     // pair kernel shares one operand-A box across horizontal taps (guarded-linear mode)
 int opt_pair_resident();   // resident weight-half variant of the pair kernel on / off                          // DL_OK or DL_ERR_UNSUPPORTED
 
 // 2-D tiled map over a row-major (rows, cols) 16-bit matrix with row pitch `ld` elements;

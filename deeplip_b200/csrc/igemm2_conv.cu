@@ -21,13 +21,20 @@ constexpr int kPairResidentBBytes = 144 * 1024;   // this CTA's half of the whol
 constexpr int kPairResidentMaxCout = 512;
 
 // kResB: single N block and the CTA's weight half (all K blocks) fits in shared memory -> loaded once per CTA,
-// the stages carry operand A only.  Removes the weight re-reads that keep layer2 (11x11 maps) L2-bound.
-template <int BLOCK_N, bool kResB>
+// the stages carry operand A only.
+// TAPS > 1 (guarded-linear operand A only): one pipeline stage holds ONE A box of 128 + (TAPS-1)*dil_w rows and the
+// weight blocks of all TAPS horizontal taps; tap s multiplies the view of the box that starts s*dil_w rows in
+// (the 128B swizzle is a function of the absolute shared-memory address, so a view shifted by whole 128-byte rows
+// is a valid operand).  A's share of the per-SM ingest (measured ceiling ~50 B/cycle) drops TAPS-fold.
+constexpr int kTapBoxRows = 144;                  // A box capacity: 128 + (TAPS-1)*dil_w <= 144
+
+template <int BLOCK_N, bool kResB, int TAPS>
 struct Igemm2Cfg {
-  static constexpr int A_BYTES = 128 * 64 * 2;
+  static_assert(TAPS == 1 || !kResB, "tap sharing streams its weights");
+  static constexpr int A_BYTES = (TAPS > 1 ? kTapBoxRows : 128) * 64 * 2;
   static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of one weight K block
-  static constexpr int STAGE_BYTES = kResB ? A_BYTES : A_BYTES + B_BYTES;
-  static constexpr int STAGES = kResB ? 4 : (BLOCK_N == 256 ? 6 : 8);
+  static constexpr int STAGE_BYTES = kResB ? A_BYTES : A_BYTES + TAPS * B_BYTES;
+  static constexpr int STAGES = kResB ? 4 : (TAPS == 1 ? (BLOCK_N == 256 ? 6 : 8) : (201 * 1024) / STAGE_BYTES);
   static constexpr int BRES_BYTES = kResB ? kPairResidentBBytes : 0;
   static constexpr int PSTRIDE = kResB ? kPairResidentMaxCout : kMaxCout;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -35,13 +42,14 @@ struct Igemm2Cfg {
   static constexpr int PARAM_BYTES = 3 * PSTRIDE * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
   static constexpr int THREADS = 320;
+  static_assert(STAGES >= 2, "pipeline depth");
 };
 
-template <int BLOCK_N, bool kResB>
+template <int BLOCK_N, bool kResB, int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const IgemmParams p) {
-  using Cfg = Igemm2Cfg<BLOCK_N, kResB>;
+  using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -120,6 +128,25 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const int qq = rem - pp * p.Q;
         const int w0 = qq * p.stride_w - p.pad_w;
         const int h0 = pp * p.stride_h - p.pad_h;
+        if (TAPS > 1) {                  // one A box + the weight blocks of all TAPS horizontal taps per stage
+          const uint32_t tx = (uint32_t)p.a_rows * 128u + TAPS * Cfg::B_BYTES;
+          for (int r = 0; r < p.R; ++r) {
+            for (int cc = 0; cc < p.cchunks; ++cc) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              const uint32_t lbar = mapa_shared(smem_u32(&full[stage]), 0);
+              if (rank == 0) mbar_expect_tx_cluster(lbar, 2u * tx);
+              else mbar_arrive_cluster(lbar);
+              tma2_load_2d(sa, &mapA, lbar, cc * 64, m0 + (r * p.dil_h - p.pad_h) * p.lin_w - p.pad_w);
+#pragma unroll
+              for (int s = 0; s < TAPS; ++s)
+                tma2_load_2d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES, &mapB, lbar, ((r * TAPS + s) * p.cchunks + cc) * 64,
+                             n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         int kb = 0;
         for (int r = 0; r < p.R; ++r) {
           for (int s = 0; s < p.S; ++s) {
@@ -154,6 +181,23 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * BLOCK_N;
+        if (TAPS > 1) {
+          const int iters = p.R * p.cchunks;
+          for (int it = 0; it < iters; ++it) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int s = 0; s < TAPS; ++s) {
+              const uint64_t adesc = umma_desc_sw128_kmajor(sa + (uint32_t)(s * p.dil_w) * 128u);
+              const uint64_t bdesc = umma_desc_sw128_kmajor(sa + Cfg::A_BYTES + s * Cfg::B_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | s | k) != 0 ? 1u : 0u);
+            }
+            umma2_commit_both(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -207,14 +251,14 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
 }
 
-template <int BLOCK_N, bool kResB>
+template <int BLOCK_N, bool kResB, int TAPS>
 static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, cudaStream_t stream) {
-  using Cfg = Igemm2Cfg<BLOCK_N, kResB>;
+  using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N, kResB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N, kResB, TAPS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "igemm2 smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -222,18 +266,30 @@ static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const
   int pairs = device_sm_count() / 2;
   if (pairs <= 0) pairs = 74;
   if (super_tiles < pairs) pairs = super_tiles;
-  igemm2_conv_kernel<BLOCK_N, kResB><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+  igemm2_conv_kernel<BLOCK_N, kResB, TAPS><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
   return check_launch("igemm2_conv_kernel");
+}
+
+// Horizontal taps one pipeline stage of the pair kernel shares an A box across (1 = none); the caller sizes
+// operand A's TMA box to 128 + (taps - 1) * dil_w rows.
+int igemm_pair_taps(const IgemmParams& p, int block_n) {
+  if (!p.lin || !opt_tap_share() || (p.S - 1) * p.dil_w > kTapBoxRows - 128) return 1;
+  if (p.S == 3) return 3;
+  if (p.S == 5 && block_n == 256) return 5;
+  return 1;
 }
 
 // Called by dl_conv_igemm_bf16 (igemm_conv.cu) for wide, large-M problems.
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
                       cudaStream_t stream) {
+  if (p.taps == 3)
+    return block_n == 128 ? launch_igemm2<128, false, 3>(mapA, mapB, p, stream) : launch_igemm2<256, false, 3>(mapA, mapB, p, stream);
+  if (p.taps == 5) return launch_igemm2<256, false, 5>(mapA, mapB, p, stream);
   const long long num_kb = (long long)p.R * p.S * p.cchunks;
   const bool res = opt_pair_resident() && p.num_n_blocks == 1 && num_kb * (block_n / 2) * 128 <= kPairResidentBBytes &&
                    p.Cout <= kPairResidentMaxCout;
-  if (block_n == 128) return res ? launch_igemm2<128, true>(mapA, mapB, p, stream) : launch_igemm2<128, false>(mapA, mapB, p, stream);
-  return res ? launch_igemm2<256, true>(mapA, mapB, p, stream) : launch_igemm2<256, false>(mapA, mapB, p, stream);
+  if (block_n == 128) return res ? launch_igemm2<128, true, 1>(mapA, mapB, p, stream) : launch_igemm2<128, false, 1>(mapA, mapB, p, stream);
+  return res ? launch_igemm2<256, true, 1>(mapA, mapB, p, stream) : launch_igemm2<256, false, 1>(mapA, mapB, p, stream);
 }
 
 }  // namespace dl

@@ -18,6 +18,7 @@ struct IgemmParams {
   int ldy, ldf;
   int lin, lin_w, lin_h, valid_w, valid_h;   // guarded-linear operand A (tiled TMA): geometry and stored extents
   int dbg;
+  int taps, a_rows;                          // pair kernel: horizontal taps sharing one A box of a_rows rows
   int out_hp, out_wp;                        // im2col mode writing into a guarded tensor (0 = dense)
   float f32_slope;
   const float* scale;

@@ -224,6 +224,7 @@ static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
 
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
                       cudaStream_t stream);   // igemm2_conv.cu
+int igemm_pair_taps(const IgemmParams& p, int block_n);
 
 }  // namespace dl
 
@@ -292,9 +293,16 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   p.num_n_blocks = (d->Cout + block_n - 1) / block_n;
   const long long Ktot = (long long)d->R * d->S * p.cchunks * 64;
 
+  const long long num_kb = (long long)d->R * d->S * p.cchunks;
+  const bool resident = p.num_n_blocks == 1 && num_kb * block_n * 128 <= kResidentBBytes;
+  // CTA pairs (cta_group::2) for wide tiles on problems large enough to fill the chip twice over
+  const bool pair = opt_pair() && block_n >= 128 && !resident && p.num_m_blocks >= 128;
+  p.taps = pair ? igemm_pair_taps(p, block_n) : 1;
+  p.a_rows = 128 + (p.taps - 1) * d->dil_w;
+
   CUtensorMap mapA, mapB;
   if (lin) {
-    st = make_tiled_2d_bf16(&mapA, x, (uint64_t)M, (uint64_t)d->C, (uint64_t)d->ldx, 128, 64);
+    st = make_tiled_2d_bf16(&mapA, x, (uint64_t)M, (uint64_t)d->C, (uint64_t)d->ldx, (uint32_t)p.a_rows, 64);
   } else {
     const int img_rows = d->img_rows > 0 ? d->img_rows : d->H;
     const int img_cols = d->img_cols > 0 ? d->img_cols : d->W;
@@ -303,10 +311,6 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
                                d->stride_w, d->pad_h, d->pad_w, d->dil_h, d->dil_w, 64, 128);
   }
   if (st != DL_OK) return st;
-  const long long num_kb = (long long)d->R * d->S * p.cchunks;
-  const bool resident = p.num_n_blocks == 1 && num_kb * block_n * 128 <= kResidentBBytes;
-  // CTA pairs (cta_group::2) for wide tiles on problems large enough to fill the chip twice over
-  const bool pair = opt_pair() && block_n >= 128 && !resident && p.num_m_blocks >= 128;
   st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot,
                           (uint32_t)(pair ? block_n / 2 : block_n), 64);
   if (st != DL_OK) return st;

@@ -14,6 +14,9 @@ from .. import ops, packing
 
 # layer1 (64 -> 64, 3x3, stride 1) runs on the halo-reuse kernel (dl_conv3x3_c64_halo_bf16) unless disabled
 USE_HALO = os.environ.get('DL_USE_HALO', '1') != '0'
+# layer2 (128 -> 128, 3x3, stride 1) keeps its activations in the guarded layout (one zero row / column after every
+# image) so that the CTA-pair kernel can share one tiled-TMA box of operand A across the three horizontal taps
+USE_GUARDED = os.environ.get('DL_USE_GUARDED', '1') != '0'
 
 
 def conv3x3(in_planes, out_planes, stride=1):
@@ -86,18 +89,41 @@ class BasicBlock(nn.Module):
         ops.conv3x3_halo(mid, pk['w2'], pk['s2'], pk['h2'], pk['a2'], H, out=out, residual=x)
         return out
 
-    def forward_nhwc(self, x, H=None):
-        """x: (N,H,W,inplanes) bf16 -> (N,P,Q,planes) bf16  (reference forward :56-69).  With H given, x is in
-        the stacked-rows layout (N, img_rows > H, W, C); only blocks with a downsample branch accept that."""
+    def forward_guarded(self, x, H, W, bufs, x_guarded):
+        """Output (and, when x_guarded, input) in the guarded layout (N, P+1, Q+1, planes) -- one zero row / column
+        after every image, see include/deeplip_b200.h.  bufs: three caller-owned zeroed guarded buffers, none of
+        them x; returns the one holding the block output.  x not guarded: (N, img_rows >= H, W, C)."""
+        pk = self._packed()
+        st = (self.stride, self.stride)
+        mid, res, out = bufs
+        P, Q = mid.shape[1] - 1, mid.shape[2] - 1
+        if self.downsample is not None:      # stride-2 entry block: im2col kernel writing the guarded layout
+            ops.conv_igemm(x, pk['w1'], self.inplanes, self.planes, 3, 3, st, (1, 1), (1, 1),
+                           pk['s1'], pk['h1'], pk['a1'], H=H, W=W, out=mid)
+            ops.conv_igemm(x, pk['wd'], self.inplanes, self.planes, 1, 1, st, (0, 0), (1, 1),
+                           pk['sd'], pk['hd'], pk['ad'], H=H, W=W, out=res)
+        else:
+            assert x_guarded and self.stride == 1
+            ops.conv_igemm_lin(x, pk['w1'], self.inplanes, self.planes, (P, Q), 3, 3, (1, 1), (1, 1),
+                               pk['s1'], pk['h1'], pk['a1'], out=mid)
+            res = x
+        ops.conv_igemm_lin(mid, pk['w2'], self.planes, self.planes, (P, Q), 3, 3, (1, 1), (1, 1),
+                           pk['s2'], pk['h2'], pk['a2'], residual=res, out=out)
+        return out
+
+    def forward_nhwc(self, x, H=None, W=None):
+        """x: (N,H,W,inplanes) bf16 -> (N,P,Q,planes) bf16  (reference forward :56-69).  With H (W) given, x is in
+        a stacked / guarded layout (N, img_rows >= H, img_cols >= W, C); only blocks with a downsample branch
+        accept that."""
         pk = self._packed()
         st = (self.stride, self.stride)
         out, _ = ops.conv_igemm(x, pk['w1'], self.inplanes, self.planes, 3, 3, st, (1, 1), (1, 1),
-                                pk['s1'], pk['h1'], pk['a1'], H=H)
+                                pk['s1'], pk['h1'], pk['a1'], H=H, W=W)
         if self.downsample is not None:
             res, _ = ops.conv_igemm(x, pk['wd'], self.inplanes, self.planes, 1, 1, st, (0, 0), (1, 1),
-                                    pk['sd'], pk['hd'], pk['ad'], H=H)
+                                    pk['sd'], pk['hd'], pk['ad'], H=H, W=W)
         else:
-            assert H is None, 'identity residual needs the dense layout'
+            assert H is None and W is None, 'identity residual needs the dense layout'
             res = x
         out, _ = ops.conv_igemm(out, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1),
                                 pk['s2'], pk['h2'], pk['a2'], residual=res)
@@ -164,6 +190,21 @@ class ResNet(nn.Module):
     def halo_enabled(self, W):
         return USE_HALO and W >= 8 and all(b.halo_ok for b in self.layer1) and self.layer2[0].downsample is not None
 
+    def guarded_enabled(self, N, P, Q):
+        """Worth it only where the CTA-pair kernel runs (>= 128 row blocks): the guards add (P+1)(Q+1)/(PQ) work."""
+        l2, l3 = self.layer2, self.layer3
+        return (USE_GUARDED and N * (P + 1) * (Q + 1) >= 128 * 128 and l2[0].planes == 128 and
+                l2[0].downsample is not None and all(b.downsample is None and b.stride == 1 for b in list(l2)[1:]) and
+                l3[0].downsample is not None)
+
+    def guarded_buffers(self, N, P, Q, device):
+        """Persistent zeroed (N, P+1, Q+1, 128) buffers; the kernels never write the guard row / column."""
+        key = (N, P, Q, str(device))
+        if getattr(self, '_grd_key', None) != key:
+            self._grd = [torch.zeros((N, P + 1, Q + 1, 128), device=device, dtype=torch.bfloat16) for _ in range(3)]
+            self._grd_key = key
+        return self._grd
+
     def stacked_buffers(self, N, H, W, device, count):
         """Persistent zero-initialised (N, H+1, W, 64) activation buffers (padding rows are never written)."""
         key = (N, H, W, str(device), count)
@@ -185,14 +226,25 @@ class ResNet(nn.Module):
                 x = bufs[-1]
             for i, blk in enumerate(self.layer1):
                 x = blk.forward_stacked(x, H, bufs[2 * i], bufs[2 * i + 1])
-            x = self.layer2[0].forward_nhwc(x, H=H)
-            rest = list(self.layer2)[1:]
+            P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            if self.guarded_enabled(N, P, Q):
+                # layer2 in the guarded layout; layer3's stride-2 entry block reads it through im2col pitches
+                g = self.guarded_buffers(N, P, Q, x.device)
+                x = self.layer2[0].forward_guarded(x, H, W, (g[0], g[1], g[2]), x_guarded=False)
+                for blk in list(self.layer2)[1:]:
+                    free = [b for b in g if b is not x]
+                    x = blk.forward_guarded(x, P, Q, (free[0], None, free[1]), x_guarded=True)
+                x = self.layer3[0].forward_nhwc(x, H=P, W=Q)
+                rest = list(self.layer3)[1:]
+            else:
+                x = self.layer2[0].forward_nhwc(x, H=H)
+                rest = list(self.layer2)[1:] + list(self.layer3)
         else:
             assert stacked_H is None
             for blk in self.layer1:
                 x = blk.forward_nhwc(x)
-            rest = list(self.layer2)
-        for blk in rest + list(self.layer3) + list(self.layer4):
+            rest = list(self.layer2) + list(self.layer3)
+        for blk in rest + list(self.layer4):
             x = blk.forward_nhwc(x)
         return x
 

@@ -352,6 +352,35 @@ def video_model_case(B=2, T=6, seed=1, u8=True, speakers=None):
     return out
 
 
+def video_guarded_case(B=4, T=30, seed=2, reps=8):
+    """layer2 on the guarded layout (tap-sharing CTA-pair kernel) vs the dense im2col path and the fp32 oracle;
+    needs >= 114 frames for the guarded path to be taken."""
+    from deeplip_b200.video_models import resnet as R
+    from deeplip_b200.video_models.model import Lipreading
+    sd = synth.make_video_state_dict(seed=seed, randomize=True)
+    m = Lipreading(relu_type='prelu', backbone_type='resnet', extract_feats=True, tcn_options=synth.TCN_OPTIONS)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    raw = torch.from_numpy(synth.lip_crops_u8(list(range(B)), T=T, seed=seed))
+    x = torch.stack([models_ref.video_preprocess(r) for r in raw])
+    assert R.USE_GUARDED and m.trunk.guarded_enabled(B * T, 11, 11)
+    with torch.no_grad():
+        got = [m.trunk_maps(raw.to(DEV)).clone() for _ in range(reps)]
+        R.USE_GUARDED = False
+        try:
+            dense = m.trunk_maps(raw.to(DEV)).clone()
+        finally:
+            R.USE_GUARDED = True
+        ref = models_ref.lipreading_features(sd, x[:, None])                     # (B,T,512)
+        feats = m(x[:, None].to(DEV), lengths=[T] * B)
+    torch.cuda.synchronize()
+    out = {'mismatch_runs': sum(int(not torch.equal(got[0], g)) for g in got[1:]),
+           'rel_vs_dense': rel_err(got[0].float().cpu(), dense.float().cpu()),
+           'frame_cos_min': float(cosine_rows(feats.reshape(B * T, -1), ref.reshape(B * T, -1)).min())}
+    assert out['mismatch_runs'] == 0 and out['rel_vs_dense'] < 1e-2 and out['frame_cos_min'] > 0.999, out
+    return out
+
+
 def video_golden_case():
     import os
     from deeplip_b200.video_models.model import Lipreading

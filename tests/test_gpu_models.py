@@ -17,6 +17,10 @@ def test_video_model_vs_oracle():
     G.video_model_case()
 
 
+def test_video_guarded_layer2_path():
+    G.video_guarded_case()
+
+
 def test_video_tcn_head_vs_oracle_and_reference_golden():
     G.video_tcn_case()
 

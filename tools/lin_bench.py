@@ -38,7 +38,7 @@ def run(name, N, H, W, C, Cout, R, S, pad, dil=(1, 1), guard=(1, 1)):
 
 
 if __name__ == '__main__':
-    B = 64 * 29
+    B = 64 * 75
     run('layer2 3x3 128', B, 11, 11, 128, 128, 3, 3, (1, 1))
     run('layer3 3x3 256', B, 6, 6, 256, 256, 3, 3, (1, 1))
     run('layer1 3x3 64', B, 22, 22, 64, 64, 3, 3, (1, 1))
