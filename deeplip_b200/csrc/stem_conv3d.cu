@@ -396,7 +396,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   p.frames = B * T;
   p.out_img_rows = out_img_rows > 0 ? out_img_rows : p.Hp;
   p.dbg = opt_dbg();
-  p.strip_slots = (p.dbg >> 8) ? (p.dbg >> 8) : 6;
+  p.strip_slots = 6;
   DL_CHECK_ARG(p.out_img_rows >= p.Hp, "stem: out_img_rows < H/4");
   DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
 

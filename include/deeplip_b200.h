@@ -32,7 +32,11 @@ extern "C" {
 int dl_version(void);
 const char* dl_last_error(void);
 /* Tuning switches for A/B measurements: "pair" (CTA-pair igemm kernels, default 1), "pair_resident"
- * (smem-resident weight half in the pair kernel, default 1).  Results are identical either way. */
+ * (smem-resident weight half in the pair kernel, default 1), "tap_share" (one operand-A box per filter row in
+ * the guarded-linear pair kernel, default 1).  Results agree to fp32 summation order either way.
+ * "dbg" (default 0) is a measurement aid only: bits 1/2/4 drop the residual / stores / whole epilogue of the
+ * pair kernel, 8 issues one MMA in four, 16/32 idle the stem's builders / epilogue (tools/epi_try.py,
+ * tools/stem_try.py) -- any non-zero value produces WRONG results by design. */
 int dl_set_option(const char* name, int value);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long dl_launch_count(void);
