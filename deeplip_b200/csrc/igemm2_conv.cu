@@ -266,6 +266,7 @@ static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const
   int pairs = device_sm_count() / 2;
   if (pairs <= 0) pairs = 74;
   if (super_tiles < pairs) pairs = super_tiles;
+  if ((p.dbg & 64) && pairs > 1) pairs /= 2;          // measurement aid: half the SMs (per-SM vs chip-wide ingest)
   igemm2_conv_kernel<BLOCK_N, kResB, TAPS><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
   return check_launch("igemm2_conv_kernel");
 }

@@ -5,10 +5,14 @@
 //
 // GEMM view per frame: M = Ho*Wo conv pixels (row-major, 128 per tile), N = 64, K = 5 temporal taps x 64
 // (7 rows x 8 columns of the 7x7 window, zero-weight padding) -> one 64-wide K block per temporal tap.
-// With a single input channel TMA im2col cannot form operand A (16-byte minimum inner extent), so 8 producer
-// warps build the 128B-swizzled K-major A tile in shared memory from a small staged input strip; a single
-// thread issues tcgen05.mma into a double-buffered TMEM accumulator; 8 epilogue warps apply BN+PReLU, park the
-// bf16 conv rows in a shared-memory ring and max-pool completed rows straight to global memory.
+// With a single input channel TMA im2col cannot form operand A (16-byte minimum inner extent), so 8 builder
+// warps assemble the A rows in registers from a TMA-staged input strip and write them with tcgen05.st into TENSOR
+// MEMORY: the MMAs read A from TMEM (tcgen05.mma [d], [a], b-desc) and only the 2 KB weight slice per MMA from
+// shared memory.  With N = 64 an SS MMA is bound by its shared-memory operand fetch (4 KB of A per 32 cycles of
+// math, measured ~120 cycles); moving A off the shared-memory port also frees it for the builders' strip reads
+// and the pooling epilogue.  A single thread issues the MMAs into a double-buffered TMEM accumulator; 8 epilogue
+// warps apply BN+PReLU, park the bf16 conv rows in a shared-memory ring and max-pool completed rows straight to
+// global memory.
 //
 // Roofline: tensor pipe; algorithmic work 2*Ho*Wo*64*245 flop per frame (DESIGN.md "Kernels").
 #include "dl_host.cuh"
@@ -16,8 +20,9 @@
 
 namespace dl {
 
-constexpr int kStemAStages = 6;                     // even: builder group g owns stages g, g+2, ...
-constexpr int kStemABytes = 128 * 64 * 2;           // one A tile: 128 pixels x 64 K (bf16)
+constexpr int kStemAStages = 8;                     // even: builder group g owns stages g, g+2, ...; 32 TMEM columns each
+constexpr int kStemTmemCols = 512;                  // 2 x 64 accumulator columns + kStemAStages x 32 operand-A columns
+constexpr int kStemTmemA = 128;                     // first operand-A column
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
 constexpr int kStemThreads = 18 * 32;               // 8 epilogue + 1 MMA + 1 TMA + 8 builder warps
 constexpr int kStemEpiThreads = 256;
@@ -62,8 +67,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // round up inside the shared window (pointer arithmetic on the __shared__ symbol keeps LDS/STS addressing)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smA = smem;                                           // kStemAStages x 16 KB
-  uint8_t* smB = smA + kStemAStages * kStemABytes;               // 40 KB
+  uint8_t* smB = smem;                                           // 40 KB
   uint8_t* ring = smB + kStemBBytes;                             // ring_rows x Wo x 128 B
   const int ring_bytes = p.ring_rows * p.Wo * 128;
   uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // kStripSlots x strip_rows x strip_pitch bf16
@@ -109,7 +113,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
       tma_prefetch_desc(&mapX);
     }
     __syncwarp();
-    tmem_alloc<128>(tmem_slot);
+    tmem_alloc<kStemTmemCols>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -119,11 +123,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   if (warp >= 10) {
     // =============================================================== builders: operand A from the staged strip
     // Two groups of 4 warps alternate pipeline stages (group g owns stages s = g, g+2, ...), so two A tiles are
-    // in flight; thread <-> A-tile row (conv pixel), 8 chunks of 16 B: chunk kh = 8 consecutive input pixels of
-    // window row kh (chunk 7 = zero padding of K).
-    const int bt = threadIdx.x - 10 * 32;         // 0..255
-    const int group = bt >> 7;
-    const int arow = bt & 127;
+    // in flight; thread <-> A row (conv pixel) = TMEM lane (a warp may only touch lane quarter warp & 3); the row is
+    // 8 chunks of 16 B: chunk kh = 8 consecutive input pixels of window row kh (chunk 7 = zero padding of K).
+    const int group = (warp - 10) >> 2;
+    const int arow = (warp & 3) * 32 + lane;
     const int SP = p.strip_pitch;
     StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
     if (group == 1) cur.advance();
@@ -153,14 +156,19 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
         }
       }
       v[7] = make_uint4(0u, 0u, 0u, 0u);
-      mbar_wait(&empty[slot], ph ^ 1);
-      uint8_t* dst_row = smA + slot * kStemABytes + arow * 128;
+      mbar_wait(&empty[slot], ph ^ 1);              // the MMAs that read this A stage have completed
+      tc_fence_after();
+      if (!(p.dbg & 16)) {
+        uint32_t a[32];                             // K order kh*8 + kw = the order of the packed weights
 #pragma unroll
-      for (int kh = 0; kh < 8; ++kh) if (!(p.dbg & 16)) *reinterpret_cast<uint4*>(dst_row + ((kh ^ (arow & 7)) << 4)) = v[kh];
-      // one proxy fence covers both hand-offs: the A tile written above becomes visible to the tensor core (async
-      // proxy), and the strip reads are performed before TMA may refill the slot (an arrive issued right after the
-      // loads can overtake them)
-      fence_proxy_async_smem();
+        for (int kh = 0; kh < 8; ++kh) { a[4 * kh] = v[kh].x; a[4 * kh + 1] = v[kh].y; a[4 * kh + 2] = v[kh].z; a[4 * kh + 3] = v[kh].w; }
+        tmem_st_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kStemTmemA + slot * 32, a);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      // The strip slot is released to TMA below.  Its reads have been PERFORMED by now -- tcgen05.st consumed the
+      // loaded registers -- so no generic->async proxy fence is needed (an arrive issued right after bare loads
+      // could overtake them).
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&sempty[sslot]);
@@ -211,10 +219,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
           for (int kt = 0; kt < 5; ++kt) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smA + stage * kStemABytes));
+            const uint32_t a = tmem_base + kStemTmemA + stage * 32;       // 8 columns per K = 16 step
             const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smB + kt * 8192));
 #pragma unroll
-            for (int k = 0; k < ((p.dbg & 8) ? 1 : 4); ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kt | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < ((p.dbg & 8) ? 1 : 4); ++k) umma_bf16_ts(d, a + 8 * k, bdesc + 2 * k, idesc, (kt | k) != 0 ? 1u : 0u);
             umma_commit(&empty[stage]);
             if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
           }
@@ -320,7 +328,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<kStemTmemCols>(tmem_base);
   }
 }
 
@@ -415,7 +423,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   }
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
-  const size_t smem = 1024 + (size_t)kStemAStages * kStemABytes + kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
+  const size_t smem = 1024 + (size_t)kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
                       p.strip_slots * (size_t)((strip_elems + 63) & ~63) * 2 + 192 * 4 + (kStemBars + 1) * 8 + 16 + 64 * 4;
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
   CUtensorMap mapW, mapX;
