@@ -56,6 +56,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp.  Unlike `lane == 0`, ptxas knows exactly one thread runs the guarded region,
+// so uniform-datapath instructions in it (UTCHMMA, UTCBAR, UBLKCP) are issued directly instead of from a
+// per-active-lane loop (R2UR + vote + branch around every tcgen05.mma).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

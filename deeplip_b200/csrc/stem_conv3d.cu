@@ -20,9 +20,10 @@
 
 namespace dl {
 
-constexpr int kStemAStages = 8;                     // even: builder group g owns stages g, g+2, ...; 32 TMEM columns each
-constexpr int kStemTmemCols = 512;                  // 2 x 64 accumulator columns + kStemAStages x 32 operand-A columns
-constexpr int kStemTmemA = 128;                     // first operand-A column
+constexpr int kStemAStages = 6;                     // = stages per (frame pair, tile): stage index == step index, so the MMA thread's
+                                                    // descriptors are loop constants; builder group g owns stages g, g+2, g+4; 32 TMEM columns each
+constexpr int kStemTmemCols = 512;                  // 2 x 128 accumulator columns (frame pair) + kStemAStages x 32 operand-A columns
+constexpr int kStemTmemA = 256;                     // first operand-A column
 constexpr int kStemBBytes = 5 * 64 * 64 * 2;        // weights: 5 K blocks of [64 cout x 64 K]
 constexpr int kStemThreads = 18 * 32;               // 8 epilogue + 1 MMA + 1 TMA + 8 builder warps
 constexpr int kStemEpiThreads = 256;
@@ -39,20 +40,29 @@ struct StemParams {
   const float* shift;
   const float* slope;
   uint16_t* y;
-  int frames;
+  int pairs_per_clip, units;                        // work unit = two consecutive output frames of one clip
   int out_img_rows;     // row pitch of one output frame (>= Hp)
   int strip_slots;
   int dbg;
 };
 
-// (frame, tile, temporal tap) of a pipeline stage; every role walks the same sequence.
+// Two consecutive output frames (t0, t0+1) of one clip are computed together: their 3-D windows share 4 of the 6
+// input frames t0-2 .. t0+3, so an A tile (input frame f, spatial tile) is built ONCE and multiplied by the weight
+// slices of both frames in one N=128 MMA (D columns [frame t0 | frame t0+1], B rows [W[kt] ; W[kt-1]]).  That halves
+// the MMA count and cuts the builders' work to 6/10, and lifts the N=64 MMAs off their operand-A delivery bound
+// (~90 cycles for 32 cycles of math).  Stage order: the two stages that touch ONE accumulator come first and
+// overwrite it (k = 0), the four shared ones accumulate.
+constexpr int kStemSt = 6;                          // input frames (pipeline stages) per (frame pair, tile)
+__device__ __forceinline__ int stem_stage_dt(int st) { return st == 0 ? -2 : (st == 1 ? 3 : st - 3); }
+
+// (frame pair, tile, stage) of a pipeline step; every role walks the same sequence.
 struct StemCursor {
-  int frame, tile, kt, ft, stride, tiles;
-  __device__ StemCursor(int first, int stride_, int tiles_) : frame(first), tile(0), kt(0), ft(0), stride(stride_), tiles(tiles_) {}
+  int unit, tile, st, stride, tiles;
+  __device__ StemCursor(int first, int stride_, int tiles_) : unit(first), tile(0), st(0), stride(stride_), tiles(tiles_) {}
   __device__ __forceinline__ void advance() {
-    if (++kt == 5) {
-      kt = 0;
-      if (++tile == tiles) { tile = 0; frame += stride; }
+    if (++st == kStemSt) {
+      st = 0;
+      if (++tile == tiles) { tile = 0; unit += stride; }
     }
   }
 };
@@ -67,10 +77,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // round up inside the shared window (pointer arithmetic on the __shared__ symbol keeps LDS/STS addressing)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smB = smem;                                           // 40 KB
-  uint8_t* ring = smB + kStemBBytes;                             // ring_rows x Wo x 128 B
+  uint8_t* smB = smem;                                           // 40 KB: block i = W[kt = 4 - i]
+  uint8_t* ring = smB + kStemBBytes;                             // 2 frames x ring_rows x Wo x 128 B
   const int ring_bytes = p.ring_rows * p.Wo * 128;
-  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + ring_bytes);   // kStripSlots x strip_rows x strip_pitch bf16
+  uint16_t* strip = reinterpret_cast<uint16_t*>(ring + 2 * ring_bytes);   // strip_slots x strip_rows x strip_pitch bf16
   const int strip_elems = p.strip_rows * p.strip_pitch;
   const int strip_buf = (strip_elems + 63) & ~63;
   float* chan = reinterpret_cast<float*>(strip + p.strip_slots * strip_buf);   // scale, shift, slope
@@ -80,7 +90,7 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   uint64_t* tfull = bars + 2 * kStemAStages;     // [2]
   uint64_t* tempty = tfull + 2;                  // [2]
   uint64_t* wbar = tempty + 2;                   // [1]
-  uint64_t* sfull = wbar + 1;                    // [kStripSlotsMax] strip slot filled (its loader warp)
+  uint64_t* sfull = wbar + 1;                    // [kStripSlotsMax] strip slot filled (TMA)
   uint64_t* sempty = sfull + kStripSlotsMax;     // [kStripSlotsMax] strip slot consumed (4 builder warps of one group)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + kStripSlotsMax);
   int* tile_iy0 = reinterpret_cast<int*>(sempty + kStripSlotsMax + 1);   // [tiles_per_frame <= 64] first input row of a tile's strip
@@ -130,15 +140,15 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
     const int SP = p.strip_pitch;
     StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
     if (group == 1) cur.advance();
-    int cached_tile = -1, cached_frame = -1;
+    int cached_tile = -1;
     uint32_t arel = 0;
     bool avalid = false;
-    uint32_t sslot = group, sph = 0;              // strip ring position of stage s: s % kStripSlots, (s / kStripSlots) & 1
-    int slot = group;                             // A stage of pipeline step s: s % kStemAStages, phase (s / kStemAStages) & 1
+    uint32_t sslot = group, sph = 0;              // strip ring position of step s: s % strip_slots, (s / strip_slots) & 1
+    int slot = group;                             // A stage of step s: s % kStemAStages, phase (s / kStemAStages) & 1
     uint32_t ph = 0;
-    for (; cur.frame < p.frames;) {
-      if (cur.tile != cached_tile || cur.frame != cached_frame) {
-        cached_tile = cur.tile; cached_frame = cur.frame;
+    for (; cur.unit < p.units;) {
+      if (cur.tile != cached_tile) {
+        cached_tile = cur.tile;
         const int m = cur.tile * 128 + arow;
         avalid = m < p.Mf;
         const int yy = m / p.Wo, xx = m - yy * p.Wo;
@@ -184,48 +194,60 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   } else if (warp == 9) {
     // =============================================================== strip producer: one thread, TMA only
     // The input was normalised / zero-bordered once by stem_prepass_kernel into (B, T, H+8, pitch) bf16, so the
-    // strip of a stage is a plain 2-D box of that tensor: rows iy0 .. iy0+strip_rows-1 of frame t+kt-2 (a frame
+    // strip of a stage is a plain 2-D box of that tensor: rows iy0 .. iy0+strip_rows-1 of input frame t0+dt (a frame
     // index outside [0,T) is out of bounds in the T dimension -> the TMA unit zero-fills it: Conv3d's temporal pad).
-    if (lane == 0) {
+    if (elect_one_sync()) {
       StemCursor cur(blockIdx.x, gridDim.x, p.tiles_per_frame);
-      int fb = cur.frame / p.T, ft = cur.frame - fb * p.T;
-      int last_frame = cur.frame;
+      int last_unit = -1, fb = 0, t0 = 0;
       const uint32_t strip_bytes = (uint32_t)strip_elems * 2u;
       uint32_t slot = 0, ph = 0;
-      for (; cur.frame < p.frames; cur.advance()) {
-        if (cur.frame != last_frame) { last_frame = cur.frame; fb = cur.frame / p.T; ft = cur.frame - fb * p.T; }
+      for (; cur.unit < p.units; cur.advance()) {
+        if (cur.unit != last_unit) { last_unit = cur.unit; fb = cur.unit / p.pairs_per_clip; t0 = 2 * (cur.unit - fb * p.pairs_per_clip); }
         mbar_wait(&sempty[slot], ph ^ 1);
         mbar_expect_tx(&sfull[slot], strip_bytes);
-        tma_load_4d(strip + slot * strip_buf, &mapX, &sfull[slot], 0, tile_iy0[cur.tile] + 3, ft + cur.kt - 2, fb);
+        tma_load_4d(strip + slot * strip_buf, &mapX, &sfull[slot], 0, tile_iy0[cur.tile] + 3, t0 + stem_stage_dt(cur.st), fb);
         if (++slot == (uint32_t)p.strip_slots) { slot = 0; ph ^= 1; }
       }
     }
   } else if (warp == 8) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(wbar, kStemBBytes);
-      for (int kt = 0; kt < 5; ++kt) tma_load_2d(smB + kt * 8192, &mapW, wbar, kt * 64, 0);
+      for (int i = 0; i < 5; ++i) tma_load_2d(smB + i * 8192, &mapW, wbar, (4 - i) * 64, 0);   // block i = W[kt = 4-i]
       mbar_wait(wbar, 0);
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      int stage = 0;
+      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
+      static_assert(kStemAStages == kStemSt, "stage index == step index");
+      // A single thread issues everything, so every instruction between two MMAs is pipe idle time: all operand
+      // addresses below are loop invariants (the compiler keeps them in uniform registers).
+      const uint64_t bd0 = umma_desc_sw128_kmajor(smem_u32(smB));
+      const uint32_t a0 = tmem_base + kStemTmemA;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int frame = blockIdx.x; frame < p.frames; frame += gridDim.x) {
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
         for (int tile = 0; tile < p.tiles_per_frame; ++tile) {
           mbar_wait(&tempty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d = tmem_base + acc * 64;
-          for (int kt = 0; kt < 5; ++kt) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t a = tmem_base + kStemTmemA + stage * 32;       // 8 columns per K = 16 step
-            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smB + kt * 8192));
+          const uint32_t d = tmem_base + acc * 128;           // columns [frame t0 | frame t0+1]
 #pragma unroll
-            for (int k = 0; k < ((p.dbg & 8) ? 1 : 4); ++k) umma_bf16_ts(d, a + 8 * k, bdesc + 2 * k, idesc, (kt | k) != 0 ? 1u : 0u);
-            umma_commit(&empty[stage]);
-            if (++stage == kStemAStages) { stage = 0; phase ^= 1; }
+          for (int st = 0; st < kStemSt; ++st) {
+            mbar_wait(&full[st], phase);
+            tc_fence_after();
+            // st 0: input t0-2 -> frame t0 only (kt 0);  st 1: input t0+3 -> frame t0+1 only (kt 4);
+            // st 2..5: input t0+dt, kt = dt+2 for frame t0 and kt-1 for frame t0+1 = adjacent weight blocks
+            const uint32_t dd = st == 1 ? d + 64 : d;
+            const uint32_t wblk = st == 0 ? 4u : (st == 1 ? 0u : (uint32_t)(5 - st));
+            const uint64_t bdesc = bd0 + (uint64_t)(wblk * 8192u >> 4);
+            const uint32_t idesc = st < 2 ? idesc64 : idesc128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if ((p.dbg & 8) && k) break;
+              umma_bf16_ts(dd, a0 + st * 32 + 8 * k, bdesc + 2 * k, idesc, (st >= 2 || k != 0) ? 1u : 0u);   // 8 columns per K = 16
+            }
+            umma_commit(&empty[st]);
           }
+          phase ^= 1;
           umma_commit(&tfull[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -234,48 +256,57 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
     }
   } else {
     // =============================================================== epilogue: BN + PReLU -> ring -> max-pool
-    // 8 warps: warp & 3 = TMEM lane quarter (tile rows 32*(warp&3) ..), warp >> 2 = channel half (32 channels)
+    // 8 warps: warp & 3 = TMEM lane quarter (tile rows 32*(warp&3) ..), warp >> 2 = channel half (32 channels);
+    // both frames of the pair per tile, each with its own ring of conv rows.
     const int et = threadIdx.x;                 // 0..255
     const int erow = et & 127;
     const int half = et >> 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int row_bytes = p.Wo * 128;
-    for (int frame = blockIdx.x; frame < p.frames; frame += gridDim.x) {
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int fb = unit / p.pairs_per_clip;
+      const int t0 = 2 * (unit - fb * p.pairs_per_clip);
+      const int nfr = min(2, p.T - t0);                     // a clip with an odd frame count ends on a half pair
       int py_done = 0;
-      uint16_t* yframe = p.y + (size_t)frame * p.out_img_rows * p.Wp * 64;
+      uint16_t* yframe0 = p.y + ((size_t)fb * p.T + t0) * p.out_img_rows * p.Wp * 64;
       for (int tile = 0; tile < p.tiles_per_frame; ++tile) {
         const int m = tile * 128 + erow;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * 64 + half * 32, r);
+        uint32_t r[2][32];
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * 128 + half * 32;
+        tmem_ld_32x32(taddr, r[0]);
+        tmem_ld_32x32(taddr + 64, r[1]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        if (m < p.Mf && !(p.dbg & 32)) {
+        if (m < p.Mf && !(p.dbg & (32 | 2048))) {
           const int yy = m / p.Wo, xx = m - yy * p.Wo;
-          uint8_t* dst = ring + (yy % p.ring_rows) * row_bytes + xx * 128;
           const float4* c4 = reinterpret_cast<const float4*>(chan) + half * 8;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            float v[8];
+          for (int g = 0; g < 2; ++g) {
+            uint8_t* dst = ring + g * ring_bytes + (yy % p.ring_rows) * row_bytes + xx * 128;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 sc = c4[2 * ch + h], sh = c4[16 + 2 * ch + h], sl = c4[32 + 2 * ch + h];
-              const int c = ch * 8 + 4 * h;
-              float z;
-              z = fmaf(__uint_as_float(r[c]), sc.x, sh.x);         v[4 * h + 0] = z > 0.f ? z : z * sl.x;
-              z = fmaf(__uint_as_float(r[c + 1]), sc.y, sh.y);     v[4 * h + 1] = z > 0.f ? z : z * sl.y;
-              z = fmaf(__uint_as_float(r[c + 2]), sc.z, sh.z);     v[4 * h + 2] = z > 0.f ? z : z * sl.z;
-              z = fmaf(__uint_as_float(r[c + 3]), sc.w, sh.w);     v[4 * h + 3] = z > 0.f ? z : z * sl.w;
+            for (int ch = 0; ch < 4; ++ch) {
+              float v[8];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 sc = c4[2 * ch + h], sh = c4[16 + 2 * ch + h], sl = c4[32 + 2 * ch + h];
+                const int c = ch * 8 + 4 * h;
+                float z;
+                z = fmaf(__uint_as_float(r[g][c]), sc.x, sh.x);         v[4 * h + 0] = z > 0.f ? z : z * sl.x;
+                z = fmaf(__uint_as_float(r[g][c + 1]), sc.y, sh.y);     v[4 * h + 1] = z > 0.f ? z : z * sl.y;
+                z = fmaf(__uint_as_float(r[g][c + 2]), sc.z, sh.z);     v[4 * h + 2] = z > 0.f ? z : z * sl.z;
+                z = fmaf(__uint_as_float(r[g][c + 3]), sc.w, sh.w);     v[4 * h + 3] = z > 0.f ? z : z * sl.w;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(dst + (((half * 4 + ch) ^ (xx & 7)) << 4)) = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(dst + (((half * 4 + ch) ^ (xx & 7)) << 4)) = o;
           }
         }
         named_bar_sync(2, kStemEpiThreads);
@@ -283,40 +314,45 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
         const int m_end = min((tile + 1) * 128, p.Mf);
         const int rows_complete = m_end / p.Wo;               // conv rows 0 .. rows_complete-1 are final
         const int py_ready = rows_complete / 2;               // needs conv row 2*py+1 <= rows_complete-1
-        for (int py = py_done; py < py_ready && !(p.dbg & 32); ++py) {
+        const int per_row = p.Wp * 8;
+        const int items = (py_ready - py_done) * per_row * nfr;
+        for (int it = et; it < items && !(p.dbg & (32 | 1024)); it += kStemEpiThreads) {
+          const int g = it / ((py_ready - py_done) * per_row);
+          const int rem = it - g * (py_ready - py_done) * per_row;
+          const int py = py_done + rem / per_row;
+          const int q = rem - (py - py_done) * per_row;
+          const int ch = q & 7, px = q >> 3;
+          const uint8_t* rg = ring + g * ring_bytes;
           const int cy0 = max(2 * py - 1, 0);                  // clamped rows/cols repeat an element: max unchanged
-          const uint8_t* r0p = ring + (cy0 % p.ring_rows) * row_bytes;
-          const uint8_t* r1p = ring + ((2 * py) % p.ring_rows) * row_bytes;
-          const uint8_t* r2p = ring + ((2 * py + 1) % p.ring_rows) * row_bytes;
-          for (int it = et; it < p.Wp * 8; it += kStemEpiThreads) {
-            const int ch = it & 7, px = it >> 3;
-            const int cx1 = 2 * px, cx2 = cx1 + 1, cx0 = max(cx1 - 1, 0);
-            const int o0 = cx0 * 128 + ((ch ^ (cx0 & 7)) << 4);
-            const int o1 = cx1 * 128 + ((ch ^ (cx1 & 7)) << 4);
-            const int o2 = cx2 * 128 + ((ch ^ (cx2 & 7)) << 4);
-            uint4 v[9];
-            v[0] = *reinterpret_cast<const uint4*>(r0p + o0); v[1] = *reinterpret_cast<const uint4*>(r0p + o1);
-            v[2] = *reinterpret_cast<const uint4*>(r0p + o2); v[3] = *reinterpret_cast<const uint4*>(r1p + o0);
-            v[4] = *reinterpret_cast<const uint4*>(r1p + o1); v[5] = *reinterpret_cast<const uint4*>(r1p + o2);
-            v[6] = *reinterpret_cast<const uint4*>(r2p + o0); v[7] = *reinterpret_cast<const uint4*>(r2p + o1);
-            v[8] = *reinterpret_cast<const uint4*>(r2p + o2);
-            __nv_bfloat162 best[4];
+          const uint8_t* r0p = rg + (cy0 % p.ring_rows) * row_bytes;
+          const uint8_t* r1p = rg + ((2 * py) % p.ring_rows) * row_bytes;
+          const uint8_t* r2p = rg + ((2 * py + 1) % p.ring_rows) * row_bytes;
+          const int cx1 = 2 * px, cx2 = cx1 + 1, cx0 = max(cx1 - 1, 0);
+          const int o0 = cx0 * 128 + ((ch ^ (cx0 & 7)) << 4);
+          const int o1 = cx1 * 128 + ((ch ^ (cx1 & 7)) << 4);
+          const int o2 = cx2 * 128 + ((ch ^ (cx2 & 7)) << 4);
+          uint4 v[9];
+          v[0] = *reinterpret_cast<const uint4*>(r0p + o0); v[1] = *reinterpret_cast<const uint4*>(r0p + o1);
+          v[2] = *reinterpret_cast<const uint4*>(r0p + o2); v[3] = *reinterpret_cast<const uint4*>(r1p + o0);
+          v[4] = *reinterpret_cast<const uint4*>(r1p + o1); v[5] = *reinterpret_cast<const uint4*>(r1p + o2);
+          v[6] = *reinterpret_cast<const uint4*>(r2p + o0); v[7] = *reinterpret_cast<const uint4*>(r2p + o1);
+          v[8] = *reinterpret_cast<const uint4*>(r2p + o2);
+          __nv_bfloat162 best[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 m01 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[0])[q],
-                                           reinterpret_cast<const __nv_bfloat162*>(&v[1])[q]);
-              __nv_bfloat162 m23 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[2])[q],
-                                           reinterpret_cast<const __nv_bfloat162*>(&v[3])[q]);
-              __nv_bfloat162 m45 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[4])[q],
-                                           reinterpret_cast<const __nv_bfloat162*>(&v[5])[q]);
-              __nv_bfloat162 m67 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[6])[q],
-                                           reinterpret_cast<const __nv_bfloat162*>(&v[7])[q]);
-              best[q] = __hmax2(__hmax2(__hmax2(m01, m23), __hmax2(m45, m67)),
-                                reinterpret_cast<const __nv_bfloat162*>(&v[8])[q]);
-            }
-            *reinterpret_cast<uint4*>(yframe + ((size_t)py * p.Wp + px) * 64 + ch * 8) =
-                *reinterpret_cast<const uint4*>(best);
+          for (int qq = 0; qq < 4; ++qq) {
+            __nv_bfloat162 m01 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[0])[qq],
+                                         reinterpret_cast<const __nv_bfloat162*>(&v[1])[qq]);
+            __nv_bfloat162 m23 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[2])[qq],
+                                         reinterpret_cast<const __nv_bfloat162*>(&v[3])[qq]);
+            __nv_bfloat162 m45 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[4])[qq],
+                                         reinterpret_cast<const __nv_bfloat162*>(&v[5])[qq]);
+            __nv_bfloat162 m67 = __hmax2(reinterpret_cast<const __nv_bfloat162*>(&v[6])[qq],
+                                         reinterpret_cast<const __nv_bfloat162*>(&v[7])[qq]);
+            best[qq] = __hmax2(__hmax2(__hmax2(m01, m23), __hmax2(m45, m67)),
+                               reinterpret_cast<const __nv_bfloat162*>(&v[8])[qq]);
           }
+          uint16_t* yf = yframe0 + (size_t)g * p.out_img_rows * p.Wp * 64;
+          *reinterpret_cast<uint4*>(yf + ((size_t)py * p.Wp + px) * 64 + ch * 8) = *reinterpret_cast<const uint4*>(best);
         }
         py_done = py_ready;
         named_bar_sync(2, kStemEpiThreads);
@@ -401,7 +437,8 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   DL_CHECK_ARG(p.strip_rows <= kStripRowsMax, "stem: frame too narrow (strip of %d rows)", p.strip_rows);
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.y = static_cast<uint16_t*>(y);
-  p.frames = B * T;
+  p.pairs_per_clip = (T + 1) / 2;
+  p.units = B * p.pairs_per_clip;
   p.out_img_rows = out_img_rows > 0 ? out_img_rows : p.Hp;
   p.dbg = opt_dbg();
   p.strip_slots = 6;
@@ -414,16 +451,16 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
   const int dh = is_u8 ? (Hraw - H) / 2 : 0, dw = is_u8 ? (Wraw - W) / 2 : 0;
   {
-    const long long n = (long long)p.frames * rows * (pitch / 8);
+    const long long n = (long long)B * T * rows * (pitch / 8);
     stem_prepass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
-        x, is_u8, p.frames, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f,
+        x, is_u8, B * T, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f,
         rows, pitch, static_cast<uint16_t*>(workspace));
     st = check_launch("stem_prepass_kernel");
     if (st != DL_OK) return st;
   }
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
-  const size_t smem = 1024 + (size_t)kStemBBytes + (size_t)p.ring_rows * p.Wo * 128 +
+  const size_t smem = 1024 + (size_t)kStemBBytes + 2 * (size_t)p.ring_rows * p.Wo * 128 +
                       p.strip_slots * (size_t)((strip_elems + 63) & ~63) * 2 + 192 * 4 + (kStemBars + 1) * 8 + 16 + 64 * 4;
   DL_CHECK_ARG(smem <= 227 * 1024, "stem: shared-memory budget exceeded (%zu B)", smem);
   CUtensorMap mapW, mapX;
@@ -434,7 +471,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   if (st != DL_OK) return st;
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
-  if (p.frames < grid) grid = p.frames;
+  if (p.units < grid) grid = p.units;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(stem_conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
