@@ -86,7 +86,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(wfull, kHaloWBytes);
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(wres + tap * 8192, &mapW, wfull, tap * 64, 0);
       int stage = 0;
@@ -102,7 +102,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {           // one thread, known to ptxas as such: no per-lane loops around UTCHMMA
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       mbar_wait(wfull, 0);
       const uint32_t wbase = smem_u32(wres);

@@ -108,7 +108,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int num_kb = p.R * p.S * p.cchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       if (kResB) {                       // whole weight half of this CTA, credited to the leader's barrier
         const uint32_t bb = mapa_shared(smem_u32(bfull), 0);
         if (rank == 0) mbar_expect_tx_cluster(bb, 2u * (uint32_t)num_kb * Cfg::B_BYTES);
@@ -170,7 +170,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && elect_one_sync()) {   // one thread, known to ptxas as such: no per-lane loops around UTCHMMA
       constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
       if (kResB) mbar_wait(bfull, 0);
       int stage = 0;

@@ -98,7 +98,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int num_kb = p.R * p.S * p.cchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       if (kResB) {
         mbar_expect_tx(bfull, (uint32_t)num_kb * Cfg::B_BYTES);
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(bres + kb * Cfg::B_BYTES, &mapB, bfull, kb * 64, 0);
@@ -135,7 +135,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {           // one thread, known to ptxas as such: UTCHMMA / UTCBAR issue without per-lane loops
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
       if (kResB) mbar_wait(bfull, 0);
       int stage = 0;

@@ -10,7 +10,7 @@ def run(name, N, H, W, C, Cout):
     sc = torch.ones(Cout, device=DEV); sh = torch.zeros(Cout, device=DEV); sl = torch.full((Cout,), 0.2, device=DEV)
     x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16)
     res = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
-    for dbg, what in ((0, 'full'), (1, 'no residual'), (2, 'no stores'), (3, 'no res, no stores'), (4, 'no epilogue'), (8, '1 of 4 MMAs'), (12, 'no epi + 1/4 MMAs'), (76, 'no epi + 1/4 MMAs, half the SMs'), (64, 'full, half the SMs')):
+    for dbg, what in ((0, 'full'), (4, 'no epilogue'), (12, 'no epi + 1/4 MMAs')):
         _lib.set_option('dbg', dbg)
         t = timeit(lambda: ops.conv_igemm(x, w, C, Cout, 3, 3, (1, 1), (1, 1), (1, 1), sc, sh, sl, residual=res))
         print('%-16s %-20s %7.1f us' % (name, what, t), flush=True)
