@@ -23,8 +23,9 @@ constexpr int kHaloPatchRows = 18, kHaloPatchCols = 16;
 constexpr int kHaloPatchBytes = kHaloPatchRows * kHaloPatchCols * 128;   // 36 864
 constexpr int kHaloStages = 4;
 constexpr int kHaloWBytes = 9 * 64 * 64 * 2;                             // 73 728 resident weights
-constexpr int kHaloThreads = 320;
-constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 3 * 64 * 4 + 16 * 8 + 16 + 1024;
+constexpr int kHaloThreads = 576;                                        // TMA + MMA warps, 2 epilogue groups x 8 warps
+constexpr int kHaloAccs = 4;                                             // TMEM accumulators (64 columns each)
+constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 3 * 64 * 4 + 24 * 8 + 16 + 1024;
 
 struct HaloParams {
   int rows_total, img_rows, H, W;
@@ -48,8 +49,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   uint64_t* full = bars;
   uint64_t* empty = bars + kHaloStages;
   uint64_t* tfull = bars + 2 * kHaloStages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* wfull = tempty + 2;
+  uint64_t* tempty = tfull + kHaloAccs;
+  uint64_t* wfull = tempty + kHaloAccs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -65,15 +66,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
       }
-      mbar_init(&tfull[0], 1);
-      mbar_init(&tfull[1], 1);
-      mbar_init(&tempty[0], 256);
-      mbar_init(&tempty[1], 256);
+      for (int a = 0; a < kHaloAccs; ++a) {
+        mbar_init(&tfull[a], 1);
+        mbar_init(&tempty[a], 256);          // the 8 warps of the epilogue group that owns the accumulator
+      }
       mbar_init(wfull, 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<128>(tmem_slot);
+    tmem_alloc<64 * kHaloAccs>(tmem_slot);
   }
   for (int c = threadIdx.x; c < 64; c += kHaloThreads) {
     prm[c] = p.scale[c];
@@ -134,17 +135,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         umma_commit(&empty[stage]);
         umma_commit(&tfull[acc]);
         if (++stage == kHaloStages) { stage = 0; phase ^= 1; }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == kHaloAccs) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
+    // Two epilogue groups of 8 warps take alternate tiles (group g: tiles g, g+2, ... of this CTA; accumulator
+    // i & 3), so one group's global-memory round trips (residual loads, stores) overlap the other's and the MMA
+    // thread can run two tiles ahead.
     const int quarter = warp & 3;
-    const int chunk = (warp - 2) >> 2;          // 32-channel half handled by this warp
+    const int chunk = ((warp - 2) >> 2) & 1;    // 32-channel half handled by this warp
+    const int egroup = (warp - 2) >> 3;
     const bool has_res = p.residual != nullptr;
     const int m = quarter * 32 + lane;          // accumulator row == TMEM lane
     const int rr = m >> 3, xx = m & 7;
-    int acc = 0;
+    int acc = egroup;
     uint32_t acc_phase = 0;
     // (stored?, element offset) of this thread's pixel in a tile; same offset in y and residual
     auto locate = [&](int tile, size_t& off) -> bool {
@@ -156,7 +160,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       off = ((size_t)R * p.W + x) * 64 + chunk * 32;
       return R < p.rows_total && (R % p.img_rows) < p.H && x >= 8 * g;
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + egroup * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       size_t off;
       const bool ok = locate(tile, off);
       // residual straight from global memory into registers, requested before the wait on the accumulator (staging
@@ -177,8 +181,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      acc += 2;
+      if (acc >= kHaloAccs) { acc -= kHaloAccs; acc_phase ^= 1; }
       const float4* sc = reinterpret_cast<const float4*>(prm + chunk * 32);
       const float4* sh = reinterpret_cast<const float4*>(prm + 64 + chunk * 32);
       const float4* sl = reinterpret_cast<const float4*>(prm + 128 + chunk * 32);
@@ -222,7 +226,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<64 * kHaloAccs>(tmem_base);
   }
 }
 
