@@ -355,7 +355,8 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
           *reinterpret_cast<uint4*>(yf + ((size_t)py * p.Wp + px) * 64 + ch * 8) = *reinterpret_cast<const uint4*>(best);
         }
         py_done = py_ready;
-        named_bar_sync(2, kStemEpiThreads);
+        // No second barrier: a warp that runs ahead writes the NEXT tile's conv rows [rc, rc+span] while the others
+        // still pool rows [rc-5, rc-1] -- disjoint in a ring of span + 6 rows -- and then stops at that tile's barrier.
       }
     }
   }
