@@ -34,9 +34,10 @@ struct Igemm2Cfg {
   static constexpr int A_BYTES = (TAPS > 1 ? kTapBoxRows : 128) * 64 * 2;
   static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of one weight K block
   static constexpr int STAGE_BYTES = kResB ? A_BYTES : A_BYTES + TAPS * B_BYTES;
-  static constexpr int STAGES = kResB ? 4 : (TAPS == 1 ? (BLOCK_N == 256 ? 6 : 8) : (201 * 1024) / STAGE_BYTES);
   static constexpr int BRES_BYTES = kResB ? kPairResidentBBytes : 0;
-  static constexpr int PSTRIDE = kResB ? kPairResidentMaxCout : kMaxCout;
+  static constexpr int PSTRIDE = (kResB || TAPS > 1) ? kPairResidentMaxCout : kMaxCout;   // staged epilogue parameters
+  static constexpr int STAGES =
+      kResB ? 4 : (TAPS == 1 ? (BLOCK_N == 256 ? 6 : 8) : (225 * 1024 - 3 * PSTRIDE * 4) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
   static constexpr int PARAM_BYTES = 3 * PSTRIDE * 4;
@@ -274,7 +275,7 @@ static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const
 // Horizontal taps one pipeline stage of the pair kernel shares an A box across (1 = none); the caller sizes
 // operand A's TMA box to 128 + (taps - 1) * dil_w rows.
 int igemm_pair_taps(const IgemmParams& p, int block_n) {
-  if (!p.lin || !opt_tap_share() || (p.S - 1) * p.dil_w > kTapBoxRows - 128) return 1;
+  if (!p.lin || !opt_tap_share() || (p.S - 1) * p.dil_w > kTapBoxRows - 128 || p.Cout > kPairResidentMaxCout) return 1;
   if (p.S == 3) return 3;
   if (p.S == 5 && block_n == 256) return 5;
   return 1;
