@@ -363,16 +363,18 @@ def video_guarded_case(B=4, T=30, seed=2, reps=8):
     m = m.to(DEV).eval()
     raw = torch.from_numpy(synth.lip_crops_u8(list(range(B)), T=T, seed=seed))
     x = torch.stack([models_ref.video_preprocess(r) for r in raw])
-    assert R.USE_GUARDED and m.trunk.guarded_enabled(B * T, 11, 11)
+    saved = R.USE_GUARDED
     with torch.no_grad():
-        got = [m.trunk_maps(raw.to(DEV)).clone() for _ in range(reps)]
-        R.USE_GUARDED = False
         try:
+            R.USE_GUARDED = True
+            assert m.trunk.guarded_enabled(B * T, 11, 11)
+            got = [m.trunk_maps(raw.to(DEV)).clone() for _ in range(reps)]
+            feats = m(x[:, None].to(DEV), lengths=[T] * B)
+            R.USE_GUARDED = False
             dense = m.trunk_maps(raw.to(DEV)).clone()
         finally:
-            R.USE_GUARDED = True
+            R.USE_GUARDED = saved
         ref = models_ref.lipreading_features(sd, x[:, None])                     # (B,T,512)
-        feats = m(x[:, None].to(DEV), lengths=[T] * B)
     torch.cuda.synchronize()
     out = {'mismatch_runs': sum(int(not torch.equal(got[0], g)) for g in got[1:]),
            'rel_vs_dense': rel_err(got[0].float().cpu(), dense.float().cpu()),
