@@ -264,11 +264,16 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const int row_bytes = p.Wo * 128;
+    // this thread's conv pixel (yy, xx) and ring row advance by 128 pixels per tile: no divisions in the loop
+    const int yy0 = erow / p.Wo, xx0 = erow - yy0 * p.Wo, ry0 = yy0 % p.ring_rows;
+    const int sy = 128 / p.Wo, sx = 128 - sy * p.Wo;
+    const int per_row = p.Wp * 8;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int fb = unit / p.pairs_per_clip;
       const int t0 = 2 * (unit - fb * p.pairs_per_clip);
       const int nfr = min(2, p.T - t0);                     // a clip with an odd frame count ends on a half pair
-      int py_done = 0;
+      int py_done = 0, pr1 = 0;                             // pr1 = (2 * py_done) % ring_rows
+      int yy = yy0, xx = xx0, ry = ry0;
       uint16_t* yframe0 = p.y + ((size_t)fb * p.T + t0) * p.out_img_rows * p.Wp * 64;
       for (int tile = 0; tile < p.tiles_per_frame; ++tile) {
         const int m = tile * 128 + erow;
@@ -284,11 +289,10 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         if (m < p.Mf && !(p.dbg & (32 | 2048))) {
-          const int yy = m / p.Wo, xx = m - yy * p.Wo;
           const float4* c4 = reinterpret_cast<const float4*>(chan) + half * 8;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            uint8_t* dst = ring + g * ring_bytes + (yy % p.ring_rows) * row_bytes + xx * 128;
+            uint8_t* dst = ring + g * ring_bytes + ry * row_bytes + xx * 128;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               float v[8];
@@ -314,19 +318,30 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
         const int m_end = min((tile + 1) * 128, p.Mf);
         const int rows_complete = m_end / p.Wo;               // conv rows 0 .. rows_complete-1 are final
         const int py_ready = rows_complete / 2;               // needs conv row 2*py+1 <= rows_complete-1
-        const int per_row = p.Wp * 8;
-        const int items = (py_ready - py_done) * per_row * nfr;
-        for (int it = et; it < items && !(p.dbg & (32 | 1024)); it += kStemEpiThreads) {
-          const int g = it / ((py_ready - py_done) * per_row);
-          const int rem = it - g * (py_ready - py_done) * per_row;
-          const int py = py_done + rem / per_row;
-          const int q = rem - (py - py_done) * per_row;
-          const int ch = q & 7, px = q >> 3;
+        xx += sx; yy += sy; ry += sy;
+        if (xx >= p.Wo) { xx -= p.Wo; ++yy; ++ry; }
+        if (ry >= p.ring_rows) ry -= p.ring_rows;
+        // work items (frame g, pooled row py, pixel px, 16-byte channel chunk ch) of this tile spread evenly over the
+        // 256 threads; decoded by subtraction (a tile completes at most a few pooled rows)
+        const int npy = py_ready - py_done;
+        const int n1 = npy * per_row;
+        for (int it = et; it < n1 * nfr && !(p.dbg & (32 | 1024)); it += kStemEpiThreads) {
+          const int g = it >= n1 ? 1 : 0;
+          int rem = it - g * n1;
+          int py = py_done, q1 = pr1;                          // q1 = (2 * py) % ring_rows
+          while (rem >= per_row) {
+            rem -= per_row; ++py; q1 += 2;
+            if (q1 >= p.ring_rows) q1 -= p.ring_rows;
+          }
+          // ring rows of conv rows 2py-1 (clamped: repeating a row leaves the max unchanged), 2py, 2py+1
+          const int q0 = py > 0 ? (q1 == 0 ? p.ring_rows - 1 : q1 - 1) : 0;
+          const int q2 = q1 + 1 == p.ring_rows ? 0 : q1 + 1;
+          const int ch = rem & 7, px = rem >> 3;
+          {
           const uint8_t* rg = ring + g * ring_bytes;
-          const int cy0 = max(2 * py - 1, 0);                  // clamped rows/cols repeat an element: max unchanged
-          const uint8_t* r0p = rg + (cy0 % p.ring_rows) * row_bytes;
-          const uint8_t* r1p = rg + ((2 * py) % p.ring_rows) * row_bytes;
-          const uint8_t* r2p = rg + ((2 * py + 1) % p.ring_rows) * row_bytes;
+          const uint8_t* r0p = rg + q0 * row_bytes;
+          const uint8_t* r1p = rg + q1 * row_bytes;
+          const uint8_t* r2p = rg + q2 * row_bytes;
           const int cx1 = 2 * px, cx2 = cx1 + 1, cx0 = max(cx1 - 1, 0);
           const int o0 = cx0 * 128 + ((ch ^ (cx0 & 7)) << 4);
           const int o1 = cx1 * 128 + ((ch ^ (cx1 & 7)) << 4);
@@ -353,7 +368,9 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
           }
           uint16_t* yf = yframe0 + (size_t)g * p.out_img_rows * p.Wp * 64;
           *reinterpret_cast<uint4*>(yf + ((size_t)py * p.Wp + px) * 64 + ch * 8) = *reinterpret_cast<const uint4*>(best);
+          }
         }
+        pr1 = (pr1 + 2 * npy) % p.ring_rows;
         py_done = py_ready;
         // No second barrier: a warp that runs ahead writes the NEXT tile's conv rows [rc, rc+span] while the others
         // still pool rows [rc-5, rc-1] -- disjoint in a ring of span + 6 rows -- and then stops at that tile's barrier.
