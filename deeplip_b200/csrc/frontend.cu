@@ -28,7 +28,7 @@ __device__ __forceinline__ int bitrev9(int v) { return __brev((unsigned)v) >> 23
 
 // grid (ceil(T/16), B); block 256 = 8 warps, two frames per warp (two-for-one real FFT).  Writes raw (pre-CMVN) features to
 // feat (B, F, T) f32.
-__global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __restrict__ wav,
+__global__ void __launch_bounds__(256, 5) frontend_frames_kernel(const float* __restrict__ wav,
                                                               const int32_t* __restrict__ lengths, int nsamp, int T,
                                                               FrontendTables tb, float* __restrict__ feat) {
   __shared__ float2 buf[8][kNfft];
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
                                           // constant cache would serialise 32-fold
   __shared__ float logmel[8][kMaxFilt];
   __shared__ float logmel2[8][kMaxFilt];
-  __shared__ float dctm[kMaxFilt * 26];   // DCT rows (ncep x 26 filters), mfcc only
+  __shared__ float dctm[26 * 26];         // DCT rows (ncep <= 26 x 26 filters), mfcc only; 40.6 KB in all -> 5 CTAs / SM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int t0 = (blockIdx.x * 8 + warp) * 2;       // this warp transforms frames t0 and t0+1 with ONE complex FFT
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) frontend_frames_kernel(const float* __res
   }
 }
 
-// grid B; block 256: warp w normalises coefficients w, w+8, ...  (biased std, + 2e-12), writes f32 in place
+// grid (B, ceil(F/8)); block 256: one coefficient row per warp (biased std, + 2e-12), writes f32 in place
 // and the channels-last bf16 copy the TDNN consumes.
 __global__ void __launch_bounds__(256) frontend_cmvn_kernel(float* __restrict__ feat, const int32_t* __restrict__ lengths,
                                                             int nsamp, int T, int F, int cmvn,
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) frontend_cmvn_kernel(float* __restrict__ 
   const int len = lengths ? min(lengths[b], nsamp) : nsamp;
   int nfr = len <= kFrameLen ? 1 : 1 + (len - kFrameLen + kFrameStep - 1) / kFrameStep;
   nfr = min(nfr, T);
-  for (int f = warp; f < F; f += 8) {
+  for (int f = blockIdx.y * 8 + warp; f < F; f += 8 * gridDim.y) {
     float* row = feat + ((size_t)b * F + f) * T;
     float mean = 0.f, inv = 1.f;
     if (cmvn) {
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) frontend_cmvn_kernel(float* __restrict__ 
     }
   }
   if (out_bf16) {   // zero the padded channels
-    for (int i = threadIdx.x; i < T * (ld - F); i += 256) {
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < T * (ld - F); i += 256 * gridDim.y) {
       const int t = i / (ld - F), c = F + i % (ld - F);
       reinterpret_cast<__nv_bfloat16*>(out_bf16)[((size_t)b * T + t) * ld + c] = __float2bfloat16_rn(0.f);
     }
@@ -254,6 +254,6 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
   frontend_frames_kernel<<<grid, 256, 0, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
   st = check_launch("frontend_frames_kernel");
   if (st != DL_OK) return st;
-  frontend_cmvn_kernel<<<B, 256, 0, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, (uint16_t*)feat_bf16, ld_bf16);
+  frontend_cmvn_kernel<<<dim3(B, (F + 7) / 8), 256, 0, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, (uint16_t*)feat_bf16, ld_bf16);
   return check_launch("frontend_cmvn_kernel");
 }
