@@ -111,6 +111,7 @@ class HostPipeline:
         self.slots = slots
         self._stage = [None] * slots
         self._ready = [torch.cuda.Event() for _ in range(slots)]
+        self._ready_wav = [torch.cuda.Event() for _ in range(slots)]
         self._free = [torch.cuda.Event() for _ in range(slots)]
 
     def _upload(self, k, wav_h, vid_h):
@@ -123,9 +124,11 @@ class HostPipeline:
                       torch.empty(vid_h.shape, dtype=vid_h.dtype, device=self.device))
                 self._stage[slot] = st
             st[0].copy_(wav_h, non_blocking=True)
+            self._ready_wav[slot].record(self.copy_stream)         # the audio branch starts while the crops still upload
             st[1].copy_(vid_h, non_blocking=True)
             self._ready[slot].record(self.copy_stream)
 
+    @torch.no_grad()
     def run(self, batches, post=None):
         """batches: sequence of (wav_host (B,nsamp) f32 pinned, video_host (B,T,H,W) u8/f32 pinned).
         Returns the list of fused embeddings as pinned host tensors (valid after the final synchronize,
@@ -135,19 +138,28 @@ class HostPipeline:
         for ev in self._free:
             ev.record(main)
         outs = []
+        pool = None
         if batches:
             self._upload(0, *batches[0])
         for k in range(len(batches)):
             slot = k % self.slots
             if k + 1 < len(batches):
                 self._upload(k + 1, *batches[k + 1])
-            main.wait_event(self._ready[slot])
             wav_d, vid_d = self._stage[slot]
-            emb = self.ex.extract(wav_d, vid_d)
+            if self.ex.fusion in ('audio', 'video'):
+                main.wait_event(self._ready[slot])
+                emb = self.ex.extract(wav_d, vid_d)
+            else:                  # same arithmetic as AVExtractor.extract, split at the two upload events
+                main.wait_event(self._ready_wav[slot])
+                xv = self.ex.audio_embedding(wav_d)
+                main.wait_event(self._ready[slot])
+                emb = self.ex.fuse(xv, self.ex.video_embedding(vid_d))
             self._free[slot].record(main)
             if post is not None:
                 emb = post(emb)
-            h = torch.empty(emb.shape, dtype=emb.dtype, pin_memory=True)
+            if pool is None:       # one pinned allocation per run (cudaHostAlloc per step would serialise the pipeline)
+                pool = torch.empty((len(batches),) + tuple(emb.shape), dtype=emb.dtype, pin_memory=True)
+            h = pool[k]
             h.copy_(emb, non_blocking=True)
             outs.append(h)
         torch.cuda.synchronize(self.device)
