@@ -21,11 +21,12 @@ namespace dl {
 
 constexpr int kHaloPatchRows = 18, kHaloPatchCols = 16;
 constexpr int kHaloPatchBytes = kHaloPatchRows * kHaloPatchCols * 128;   // 36 864
-constexpr int kHaloStages = 4;
+constexpr int kHaloStages = 3;
 constexpr int kHaloWBytes = 9 * 64 * 64 * 2;                             // 73 728 resident weights
 constexpr int kHaloThreads = 576;                                        // TMA + MMA warps, 2 epilogue groups x 8 warps
 constexpr int kHaloAccs = 4;                                             // TMEM accumulators (64 columns each)
-constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 3 * 64 * 4 + 24 * 8 + 16 + 1024;
+constexpr int kHaloOutBytes = 128 * 128;                                 // one output tile (128 px x 64 ch bf16) staged for the TMA store
+constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 2 * kHaloOutBytes + 3 * 64 * 4 + 24 * 8 + 16 + 1024;
 
 struct HaloParams {
   int rows_total, img_rows, H, W;
@@ -39,12 +40,13 @@ struct HaloParams {
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
-                    const HaloParams p) {
+                    const __grid_constant__ CUtensorMap mapY, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* patches = smem;
   uint8_t* wres = smem + kHaloStages * kHaloPatchBytes;
-  float* prm = reinterpret_cast<float*>(wres + kHaloWBytes);
+  uint8_t* outst = wres + kHaloWBytes;                      // 2 x output tile, one per epilogue group (1024-aligned)
+  float* prm = reinterpret_cast<float*>(outst + 2 * kHaloOutBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 192);
   uint64_t* full = bars;
   uint64_t* empty = bars + kHaloStages;
@@ -59,6 +61,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapY);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -150,24 +153,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     const int rr = m >> 3, xx = m & 7;
     int acc = egroup;
     uint32_t acc_phase = 0;
-    // (stored?, element offset) of this thread's pixel in a tile; same offset in y and residual
-    auto locate = [&](int tile, size_t& off) -> bool {
+    // Output tiles leave through shared memory and ONE TMA store per tile (full 128-byte lines, asynchronous) instead
+    // of 16-byte stores at a 128-byte stride.  The box covers all 16 x 8 pixels: pixels of the zero rows between
+    // images are staged as zeros (so they stay zero), rows past the tensor end are clipped by the TMA unit, and the
+    // columns the last column group shares with its neighbour are written twice with identical values.
+    uint8_t* stg = outst + egroup * kHaloOutBytes;
+    const bool issuer = (warp & 7) == 2 && lane == 0;       // first warp of each group (warps 2 and 10)
+    for (int tile = blockIdx.x + egroup * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const int rt = tile / p.num_groups;
       const int g = tile - rt * p.num_groups;
       const int x0 = min(8 * g, p.W - 8);
       const int R = rt * 16 + rr;
-      const int x = x0 + xx;
-      off = ((size_t)R * p.W + x) * 64 + chunk * 32;
-      return R < p.rows_total && (R % p.img_rows) < p.H && x >= 8 * g;
-    };
-    for (int tile = blockIdx.x + egroup * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
-      size_t off;
-      const bool ok = locate(tile, off);
-      // residual straight from global memory into registers, requested before the wait on the accumulator (staging
-      // it in shared memory through TMA competes with the tensor pipe's operand fetch and was no faster)
+      const bool inimg = R < p.rows_total && (R % p.img_rows) < p.H;
+      // residual straight from global memory into registers, requested before the wait on the accumulator
       uint4 res[4];
-      if (has_res && ok) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+      if (has_res && inimg) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + ((size_t)R * p.W + x0 + xx) * 64 + chunk * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) res[q] = __ldg(rp + q);
       } else {
@@ -214,14 +215,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         o[q].x = pack_bf16x2(v[0], v[1]); o[q].y = pack_bf16x2(v[2], v[3]);
         o[q].z = pack_bf16x2(v[4], v[5]); o[q].w = pack_bf16x2(v[6], v[7]);
       }
-      if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.y + off);
+      // the group's previous TMA store must have finished reading the staging tile
+      if (issuer) bulk_wait_group_read0();
+      named_bar_sync(3 + egroup, 256);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = o[q];
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(stg + m * 128 + (((chunk * 4 + q) ^ (m & 7)) << 4)) = inimg ? o[q] : make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();                   // generic-proxy writes -> visible to the TMA unit
+      named_bar_sync(3 + egroup, 256);
+      if (issuer) {
+        tma_store_3d(&mapY, stg, 0, x0, rt * 16);
+        bulk_commit_group();
       }
     }
   }
 
+  if (warp >= 2 && (warp & 7) == 2 && lane == 0) bulk_wait_group0();     // outstanding output stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -254,14 +263,16 @@ extern "C" int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, con
   p.scale = scale; p.shift = shift; p.slope = slope;
   p.residual = static_cast<const uint16_t*>(residual);
   p.y = static_cast<uint16_t*>(y);
-  CUtensorMap mapX, mapW;
+  CUtensorMap mapX, mapW, mapY;
   st = make_tiled_3d_bf16(&mapX, x, (uint64_t)p.rows_total, (uint64_t)W, 64, kHaloPatchRows, kHaloPatchCols, 64);
   if (st != DL_OK) return st;
   st = make_tiled_2d_bf16(&mapW, w_packed, 64, 576, 576, 64, 64);
   if (st != DL_OK) return st;
+  st = make_tiled_3d_bf16(&mapY, y, (uint64_t)p.rows_total, (uint64_t)W, 64, 16, 8, 64);
+  if (st != DL_OK) return st;
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.total_tiles < grid) grid = p.total_tiles;
-  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(mapX, mapW, p);
+  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(mapX, mapW, mapY, p);
   return check_launch("conv3x3_halo_kernel");
 }

@@ -69,6 +69,11 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Named barrier among `threads` threads of the CTA (ids 1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -234,6 +239,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* map, uint64_t
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA store of a 3-D box from shared memory (bulk async-group completion).
+__device__ __forceinline__ void tma_store_3d(const void* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // General K-major 128B-swizzle descriptor: explicit stride between 8-row groups and swizzle-phase base offset
 // (for operand views whose start is not 1024-byte aligned).
 __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor_ex(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {

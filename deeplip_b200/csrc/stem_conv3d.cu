@@ -67,9 +67,6 @@ struct StemCursor {
   }
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
