@@ -3,9 +3,9 @@
 //
 // The generic implicit-GEMM kernel (igemm_conv.cu) fetches one [128 px x 64 ch] im2col box per filter tap, i.e.
 // every activation crosses L2 -> SM nine times; with only 64 output channels per tile that makes layer1
-// L2-bandwidth bound (measured ~10 TB/s, 445 TFLOP/s).  Here ONE TMA box -- an 18-row x 16-pixel halo patch --
+// L2-bandwidth bound (measured ~10 TB/s, 445 TFLOP/s).  Here ONE TMA box -- an 18-row x 10-pixel halo patch --
 // feeds all nine taps: the A operand of tap (r, s) is simply a shifted view of the patch, expressed through the
-// UMMA shared-memory descriptor (start + (16 r + s) * 128 B, 2048 B between 8-pixel row groups), and the whole
+// UMMA shared-memory descriptor (start + (10 r + s) * 128 B, 1280 B between 8-pixel row groups), and the whole
 // 64 x 576 weight matrix stays resident in shared memory.  L2 traffic per output tile drops from 216 KB to 36 KB.
 //
 // Layout contract ("stacked rows"): activations are (N, img_rows, W, 64) bf16 with img_rows >= H + 1 and rows
@@ -19,14 +19,15 @@
 
 namespace dl {
 
-constexpr int kHaloPatchRows = 18, kHaloPatchCols = 16;
-constexpr int kHaloPatchBytes = kHaloPatchRows * kHaloPatchCols * 128;   // 36 864
-constexpr int kHaloStages = 3;
+constexpr int kHaloPatchRows = 18, kHaloPatchCols = 10;                  // 16 x 8 output pixels + a one-pixel halo
+constexpr int kHaloPatchBytes = kHaloPatchRows * kHaloPatchCols * 128;   // 23 040 bytes landed by TMA
+constexpr int kHaloPatchStride = (kHaloPatchBytes + 1023) / 1024 * 1024; // stage stride: patch bases stay 1024-byte aligned
+constexpr int kHaloStages = 5;
 constexpr int kHaloWBytes = 9 * 64 * 64 * 2;                             // 73 728 resident weights
 constexpr int kHaloThreads = 576;                                        // TMA + MMA warps, 2 epilogue groups x 8 warps
 constexpr int kHaloAccs = 4;                                             // TMEM accumulators (64 columns each)
 constexpr int kHaloOutBytes = 128 * 128;                                 // one output tile (128 px x 64 ch bf16) staged for the TMA store
-constexpr int kHaloSmem = kHaloStages * kHaloPatchBytes + kHaloWBytes + 2 * kHaloOutBytes + 3 * 64 * 4 + 24 * 8 + 16 + 1024;
+constexpr int kHaloSmem = kHaloStages * kHaloPatchStride + kHaloWBytes + 2 * kHaloOutBytes + 3 * 64 * 4 + 24 * 8 + 16 + 1024;
 
 struct HaloParams {
   int rows_total, img_rows, H, W;
@@ -44,7 +45,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* patches = smem;
-  uint8_t* wres = smem + kHaloStages * kHaloPatchBytes;
+  uint8_t* wres = smem + kHaloStages * kHaloPatchStride;
   uint8_t* outst = wres + kHaloWBytes;                      // 2 x output tile, one per epilogue group (1024-aligned)
   float* prm = reinterpret_cast<float*>(outst + 2 * kHaloOutBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(prm + 192);
@@ -101,7 +102,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         const int x0 = min(8 * g, p.W - 8);
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], kHaloPatchBytes);
-        tma_load_3d(patches + stage * kHaloPatchBytes, &mapX, &full[stage], 0, x0 - 1, rt * 16 - 1);
+        tma_load_3d(patches + stage * kHaloPatchStride, &mapX, &full[stage], 0, x0 - 1, rt * 16 - 1);
         if (++stage == kHaloStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -119,18 +120,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * 64;
-        const uint32_t pbase = smem_u32(patches + stage * kHaloPatchBytes);
+        const uint32_t pbase = smem_u32(patches + stage * kHaloPatchStride);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int r = tap / 3, s = tap - 3 * r;
-          // rows of the A view: output pixel (rr, xx) reads patch pixel (rr + r, xx + s); pitch 16 px = 2048 B
+          // rows of the A view: output pixel (rr, xx) reads patch pixel (rr + r, xx + s); pitch 10 px = 1280 B
           const uint32_t a0 = pbase + (uint32_t)(r * kHaloPatchCols + s) * 128u;
           // The 128B swizzle is a function of the absolute shared-memory address bits (verified on B200: a view that
           // starts s pixels into the row needs NO descriptor base offset; setting one scrambles the operand).
           const uint32_t bo = 0u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = umma_desc_sw128_kmajor_ex(a0 + 32u * k, 2048u, bo);
+            const uint64_t adesc = umma_desc_sw128_kmajor_ex(a0 + 32u * k, kHaloPatchCols * 128u, bo);
             const uint64_t bdesc = umma_desc_sw128_kmajor(wbase + tap * 8192u + 32u * k);
             umma_bf16(d, adesc, bdesc, idesc, (tap | k) != 0 ? 1u : 0u);
           }
