@@ -6,14 +6,14 @@
 // L2-bandwidth bound (measured ~10 TB/s, 445 TFLOP/s).  Here ONE TMA box -- an 18-row x 10-pixel halo patch --
 // feeds all nine taps: the A operand of tap (r, s) is simply a shifted view of the patch, expressed through the
 // UMMA shared-memory descriptor (start + (10 r + s) * 128 B, 1280 B between 8-pixel row groups), and the whole
-// 64 x 576 weight matrix stays resident in shared memory.  L2 traffic per output tile drops from 216 KB to 36 KB.
+// 64 x 576 weight matrix stays resident in shared memory.  L2 traffic per output tile drops from 216 KB to 23 KB.
 //
 // Layout contract ("stacked rows"): activations are (N, img_rows, W, 64) bf16 with img_rows >= H + 1 and rows
 // H .. img_rows-1 of every image all zero.  Stacked row R = n * img_rows + y; the zero row is at once the bottom
 // padding of image n and the top padding of image n + 1, so a tile may span images.  Left / right padding comes
 // from TMA out-of-bounds zero fill.  An output tile is 16 stacked rows x 8 columns (M = 128); column groups of a
-// row start at 0, 8, ..., W - 8 (the last one may overlap its neighbour; duplicates are not written).  The kernel
-// never writes the padding rows of y: they must be zero when y is used as an input again.
+// row start at 0, 8, ..., W - 8 (the last one may overlap its neighbour: those pixels are written twice with identical
+// values).  The padding rows of y are written as zeros, so y can be used as an input again.
 #include "dl_host.cuh"
 #include "dl_ptx.cuh"
 

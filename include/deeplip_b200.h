@@ -129,7 +129,7 @@ int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, 
  * feeds all nine taps, weights resident): the ResNet layer1 BasicBlock convs (resnet.py:56-69) at a ninth
  * of the L2 traffic of the generic kernel.  Same fused epilogue (scale, shift, residual, slope).
  * x, y, residual: (N, img_rows, W, 64) bf16 "stacked rows": img_rows >= H + 1 and rows H .. img_rows-1 of
- * every image are zero in x (they act as vertical padding); the kernel never writes those rows of y.
+ * every image are zero in x (they act as vertical padding); the kernel writes zeros to those rows of y.
  * w_packed: (64, 576) bf16 as for dl_conv_igemm_bf16.  W >= 8.
  */
 int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
