@@ -1,26 +1,17 @@
 // K1: fused audio front end -- pre-emphasis + 400/160 framing + 512-point FFT power spectrum + triangular
-// mel filterbank + log (+ DCT-II, lifter, log-energy for MFCC), then per-utterance CMVN.
-// Restates python_speech_features v0.6 as the reference calls it (models/fusion_models/datasets.py:227-246)
-// and `_normalize` (:214-215).  HBM-bound by construction: 4 B/sample in, F*T*(4+2) B out; one warp per frame.
+// mel filterbank + log (+ DCT-II, lifter, log-energy for MFCC), or the `stft` feature (centre-padded Hann frames,
+// log1p |S|), then per-utterance CMVN.
+// Restates python_speech_features v0.6 / librosa.stft as the reference calls them
+// (models/fusion_models/datasets.py:227-246) and `_normalize` (:214-215).  4 B/sample in, F*T*(4+2) B out.
+// Two generations live here: frontend_frames2/cmvn2 (default: register-resident radix-8 FFT, fft512.cuh) and the
+// first radix-2 shared-memory kernels (dl_set_option("frontend", 1)) kept for A/B measurements.
 #include <math.h>
+#include <string.h>
 #include "dl_host.cuh"
 #include "dl_ptx.cuh"
+#include "frontend_gen2.cuh"
 
 namespace dl {
-
-constexpr int kNfft = 512;
-constexpr int kFrameLen = 400;
-constexpr int kFrameStep = 160;
-constexpr int kMaxFilt = 64;
-constexpr float kPreemph = 0.97f;
-
-struct FrontendTables {
-  int nfilt;
-  int ncep;                  // number of coefficients written (F)
-  int kind;                  // 0 mfcc, 1 fbank, 2 logfbank
-  int bins[kMaxFilt + 2];    // FFT-bin edges of the triangular filters
-  float inv_width[kMaxFilt + 1];   // 1 / (bins[j+1] - bins[j])
-};
 
 __constant__ float2 c_twiddle[kNfft / 2];   // exp(-2 pi i k / 512)
 
@@ -205,8 +196,6 @@ __global__ void __launch_bounds__(256) frontend_cmvn_kernel(float* __restrict__ 
   }
 }
 
-static double hz2mel(double hz) { return 2595.0 * log10(1.0 + hz / 700.0); }
-static double mel2hz(double mel) { return 700.0 * (pow(10.0, mel / 2595.0) - 1.0); }
 
 static int upload_twiddles() {
   static bool done = false;
@@ -222,6 +211,28 @@ static int upload_twiddles() {
   return DL_OK;
 }
 
+// FFT twiddles, DCT matrix and Hann window of generation 2, once per device.
+static int upload_tables() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(DL_ERR_CUDA, "frontend: cudaGetDevice failed");
+  if (done[dev]) return DL_OK;
+  static FrontendConst h;
+  fill_frontend_const(&h);
+  cudaError_t e = cudaMemcpyToSymbol(g_fc, &h, sizeof(h));
+  if (e != cudaSuccess) return fail(DL_ERR_CUDA, "frontend tables: %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(frontend_frames2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           frames2_smem_floats(kMaxFilt) * 4);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(frontend_frames2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             frames2_smem_floats(kNfft / 2 + 1) * 4);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(frontend_cmvn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmvn2MaxSmem);
+  if (e != cudaSuccess) return fail(DL_ERR_CUDA, "frontend smem attribute: %s", cudaGetErrorString(e));
+  done[dev] = true;
+  return DL_OK;
+}
+
 }  // namespace dl
 
 extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
@@ -229,31 +240,49 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
   using namespace dl;
   DL_CHECK_ARG(wav && feat_f32, "frontend: wav and feat_f32 are required");
   DL_CHECK_ARG(B > 0 && nsamp > 0, "frontend: empty batch");
-  DL_CHECK_ARG(kind >= 0 && kind <= 2, "frontend: kind must be 0 (mfcc), 1 (fbank) or 2 (logfbank)");
+  DL_CHECK_ARG(kind >= 0 && kind <= 3, "frontend: kind must be 0 (mfcc), 1 (fbank), 2 (logfbank) or 3 (stft)");
+  const bool stft = kind == 3;
   const int nfilt = kind == 0 ? 26 : F;
-  DL_CHECK_ARG(F >= 1 && F <= kMaxFilt && nfilt <= kMaxFilt && F <= nfilt, "frontend: F=%d out of range", F);
-  const int Texp = nsamp <= kFrameLen ? 1 : 1 + (nsamp - kFrameLen + kFrameStep - 1) / kFrameStep;
+  if (stft) {
+    DL_CHECK_ARG(F == kNfft / 2 + 1, "frontend: stft has F = 257 bins (n_fft = 512), got %d", F);
+  } else {
+    DL_CHECK_ARG(F >= 1 && F <= kMaxFilt && nfilt <= kMaxFilt && F <= nfilt, "frontend: F=%d out of range", F);
+  }
+  const int Texp = stft ? 1 + nsamp / kFrameStep
+                        : (nsamp <= kFrameLen ? 1 : 1 + (nsamp - kFrameLen + kFrameStep - 1) / kFrameStep);
   DL_CHECK_ARG(T == Texp, "frontend: T=%d but %d samples give %d frames", T, nsamp, Texp);
   DL_CHECK_ARG(!feat_bf16 || ld_bf16 >= F, "frontend: ld_bf16 < F");
-  int st = upload_twiddles();
-  if (st != DL_OK) return st;
+  const int gen = opt_frontend();
+  DL_CHECK_ARG(!stft || gen >= 2, "frontend: stft needs the generation-2 kernels (dl_set_option(\"frontend\", 2))");
 
   FrontendTables tb;
-  tb.nfilt = nfilt; tb.ncep = F; tb.kind = kind;
-  const double lo = hz2mel(0.0), hi = hz2mel(8000.0);
-  for (int i = 0; i < nfilt + 2; ++i) {
-    const double mel = lo + (hi - lo) * (double)i / (double)(nfilt + 1);
-    tb.bins[i] = (int)floor((kNfft + 1) * mel2hz(mel) / 16000.0);
-  }
-  for (int i = 0; i < nfilt + 1; ++i) {
-    const int w = tb.bins[i + 1] - tb.bins[i];
-    tb.inv_width[i] = w > 0 ? 1.0f / (float)w : 0.0f;
-  }
+  fill_frontend_tables(&tb, kind, F, opt_stft_pad());
   cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid((T + 15) / 16, B);
-  frontend_frames_kernel<<<grid, 256, 0, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
-  st = check_launch("frontend_frames_kernel");
+  int st;
+  if (gen >= 2) {
+    st = upload_tables();
+    if (st != DL_OK) return st;
+    dim3 grid((T + kBlkFrames - 1) / kBlkFrames, B);
+    const size_t smem = (size_t)frames2_smem_floats(F) * 4;
+    if (stft) frontend_frames2_kernel<true><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
+    else frontend_frames2_kernel<false><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
+    st = check_launch("frontend_frames2_kernel");
+  } else {
+    st = upload_twiddles();
+    if (st != DL_OK) return st;
+    dim3 grid((T + 15) / 16, B);
+    frontend_frames_kernel<<<grid, 256, 0, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
+    st = check_launch("frontend_frames_kernel");
+  }
   if (st != DL_OK) return st;
+  const size_t csmem = (size_t)8 * T * 4;
+  const bool bf16_ok = !feat_bf16 || (ld_bf16 % 8 == 0 && ld_bf16 >= (F + 7) / 8 * 8 && ((uintptr_t)feat_bf16 & 15) == 0);
+  if (gen >= 2 && csmem <= (size_t)kCmvn2MaxSmem && bf16_ok) {
+    frontend_cmvn2_kernel<<<dim3(B, (F + 7) / 8), 256, csmem, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, stft ? 1 : 0,
+                                                                  (uint16_t*)feat_bf16, ld_bf16);
+    return check_launch("frontend_cmvn2_kernel");
+  }
+  DL_CHECK_ARG(!stft, "frontend: stft needs ld_bf16 %% 8 == 0, a 16-byte aligned feat_bf16 and T <= %d", kCmvn2MaxSmem / 32);
   frontend_cmvn_kernel<<<dim3(B, (F + 7) / 8), 256, 0, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, (uint16_t*)feat_bf16, ld_bf16);
   return check_launch("frontend_cmvn_kernel");
 }

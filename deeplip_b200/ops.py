@@ -42,20 +42,29 @@ def ceil_to(x, m):
     return (x + m - 1) // m * m
 
 
-def num_frames(nsamp, frame_len=400, step=160):
+def num_frames(nsamp, frame_len=400, step=160, feat_type='mfcc'):
+    """Frames of `nsamp` samples: python_speech_features framing (ceil, tail zero-padded), or for 'stft'
+    librosa's centre-padded framing (1 + nsamp // hop)."""
+    if feat_type == 'stft':
+        return 1 + nsamp // step
     return 1 if nsamp <= frame_len else 1 + -(-(nsamp - frame_len) // step)
 
 
 # ------------------------------------------------------------------ K1
-FEAT_KINDS = {'mfcc': 0, 'fbank': 1, 'logfbank': 2}
+FEAT_KINDS = {'mfcc': 0, 'fbank': 1, 'logfbank': 2, 'stft': 3}
 
 
 def frontend_features(wav, feat_type='mfcc', n_feat=24, cmvn=True, lengths=None, ld=None):
-    """wav (B, nsamp) f32 -> (feat_f32 (B,F,T), feat_bf16 (B,T,ld))."""
+    """wav (B, nsamp) f32 -> (feat_f32 (B,F,T), feat_bf16 (B,T,ld)).  feat_type 'stft' (n_fft 512, hop 160,
+    Hann 400; models/fusion_models/datasets.py:237-241) has n_feat = 257."""
     _need_cuda(wav, lengths)
+    if feat_type not in FEAT_KINDS:
+        raise NotImplementedError('Other features are not implemented!')      # datasets.py:243
     wav = wav.contiguous().float()
     B, nsamp = wav.shape
-    T = num_frames(nsamp)
+    if feat_type == 'stft':
+        n_feat = 257
+    T = num_frames(nsamp, feat_type=feat_type)
     ld = ld or ceil_to(n_feat, 64)
     f32 = torch.empty((B, n_feat, T), device=wav.device, dtype=torch.float32)
     b16 = torch.empty((B, T, ld), device=wav.device, dtype=torch.bfloat16)

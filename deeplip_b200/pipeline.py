@@ -31,8 +31,11 @@ class AVExtractor:
         _, feat = ops.frontend_features(wav, self.feat_type, self.n_feat, self.cmvn, lengths=wav_lengths)
         frames = None
         if wav_lengths is not None:
-            frames = torch.where(wav_lengths <= 400, torch.ones_like(wav_lengths),
-                                 1 + torch.div(wav_lengths - 400 + 159, 160, rounding_mode='floor')).to(torch.int32)
+            if self.feat_type == 'stft':
+                frames = (1 + torch.div(wav_lengths, 160, rounding_mode='floor')).to(torch.int32)
+            else:
+                frames = torch.where(wav_lengths <= 400, torch.ones_like(wav_lengths),
+                                     1 + torch.div(wav_lengths - 400 + 159, 160, rounding_mode='floor')).to(torch.int32)
         xv, _ = self.audio.embed_ntc(feat, frames)
         return xv
 

@@ -42,14 +42,20 @@ int dl_set_option(const char* name, int value);
 long long dl_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
- * K1  audio front end.  Replaces python_speech_features.{mfcc,fbank,logfbank} + `_normalize`
- *     (models/fusion_models/datasets.py:227-246, 214-215).  wav: (B, nsamp) f32 ->
+ * K1  audio front end.  Replaces python_speech_features.{mfcc,fbank,logfbank} / librosa.stft + magphase +
+ *     log1p, and `_normalize` (models/fusion_models/datasets.py:227-246, 214-215).  wav: (B, nsamp) f32 ->
  *     feat_bf16: (B, T, ld_bf16) channels-last bf16 (zero padded to ld_bf16 channels; may be NULL),
  *     feat_f32 : (B, F, T) f32, the layout the reference hands to the model (required: it doubles
  *                as the pre-CMVN scratch, this library never allocates).
- *     kind: 0 = mfcc(numcep=F, nfilt=26), 1 = fbank(nfilt=F), 2 = logfbank(nfilt=F).
+ *     kind: 0 = mfcc(numcep=F, nfilt=26), 1 = fbank(nfilt=F), 2 = logfbank(nfilt=F),
+ *           3 = stft(n_fft=512, hop 160, periodic Hann 400 centred in 512, center=True): F = 257 rows of
+ *               log1p|S|; the centre padding is librosa's pre-0.10 default `reflect` unless
+ *               dl_set_option("stft_pad", 1) selects zeros (librosa >= 0.10).
  *     lengths: per-utterance valid sample counts (device int32, may be NULL = nsamp for all);
- *     T must equal 1 + ceil((nsamp - 400) / 160) for the padded length nsamp (16 kHz, 25/10 ms).
+ *     T must equal 1 + ceil((nsamp - 400) / 160) for the padded length nsamp (16 kHz, 25/10 ms), or
+ *     1 + nsamp / 160 for kind 3.
+ *     dl_set_option("frontend", 1) selects the first-generation kernels (radix-2 FFT in shared memory;
+ *     kinds 0-2 only), kept for A/B measurements; the default (2) holds the FFT in registers.
  */
 int dl_frontend_features(const float* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
                          int cmvn, void* feat_bf16, int ld_bf16, float* feat_f32, int T, void* stream);

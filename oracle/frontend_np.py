@@ -10,7 +10,13 @@ that package's published v0.6 algorithm for the arguments the reference passes:
 ``mfcc(data, rate, winlen, winstep, numcep)``, ``fbank(..., nfilt)``,
 ``logfbank(..., nfilt)``; everything else is the library default
 (nfilt=26, nfft=512 at 16 kHz/25 ms, preemph=0.97, ceplifter=22,
-appendEnergy=True, rectangular window).
+appendEnergy=True, rectangular window).  The ``stft`` feature
+(datasets.py:237-241) goes through ``librosa.stft`` / ``librosa.magphase``
+(unpinned, absent as well): restated from librosa's published algorithm --
+periodic Hann window of ``win_length`` centred in ``n_fft``, ``center=True``
+padding of ``n_fft // 2`` samples (``reflect`` before librosa 0.10, zeros
+since; the reference dates from the ``reflect`` era, which is the default
+here), frames every ``hop_length`` samples, rfft, ``log1p(|S|)``.
 """
 import math
 import numpy as np
@@ -113,6 +119,19 @@ def mfcc(sig, rate=16000, winlen=0.025, winstep=0.01, numcep=13, nfilt=26,
     return feat
 
 
+def stft_logmag(sig, n_fft=512, hop=160, win_length=400, pad_mode='reflect'):
+    """datasets.py:237-241: librosa.stft(data, n_fft, hop_length, win_length) -> magphase -> log1p,
+    transposed to (T, n_fft // 2 + 1)."""
+    sig = np.asarray(sig, dtype=np.float64)
+    win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(win_length) / win_length)   # get_window('hann', fftbins=True)
+    lpad = (n_fft - win_length) // 2
+    win = np.concatenate([np.zeros(lpad), win, np.zeros(n_fft - win_length - lpad)])     # util.pad_center
+    y = np.pad(sig, n_fft // 2, mode=pad_mode)
+    n = 1 + (len(y) - n_fft) // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(n)[:, None]
+    return np.log1p(np.abs(np.fft.rfft(y[idx] * win[None, :], n_fft, axis=1)))
+
+
 def cmvn(feat):
     """models/fusion_models/datasets.py:214-215 (biased std, +2e-12)."""
     return (feat - feat.mean(axis=0)) / (feat.std(axis=0) + 2e-12)
@@ -121,8 +140,8 @@ def cmvn(feat):
 def extract_feature(sig, rate=16000, feat_type='mfcc', opts=None):
     """models/fusion_models/datasets.py:227-246; returns (T, F) float32
     (the datasets then transpose to (F, T), :268, :376)."""
-    o = dict(win_len=0.025, win_shift=0.01, num_cep=24, num_bin=26,
-             normalize=True, delta=False)
+    o = dict(win_len=0.025, win_shift=0.01, num_cep=24, num_bin=26, n_fft=512,
+             normalize=True, delta=False, pad_mode='reflect')
     o.update(opts or {})
     if feat_type == 'mfcc':
         f = mfcc(sig, rate, o['win_len'], o['win_shift'], numcep=o['num_cep'])
@@ -130,6 +149,8 @@ def extract_feature(sig, rate=16000, feat_type='mfcc', opts=None):
         f, _ = fbank(sig, rate, o['win_len'], o['win_shift'], nfilt=o['num_bin'])
     elif feat_type == 'logfbank':
         f = logfbank(sig, rate, o['win_len'], o['win_shift'], nfilt=o['num_bin'])
+    elif feat_type == 'stft':
+        f = stft_logmag(sig, o['n_fft'], int(rate * o['win_shift']), int(rate * o['win_len']), o['pad_mode'])
     else:
         raise NotImplementedError("Other features are not implemented!")
     if o['normalize']:

@@ -1,0 +1,127 @@
+// Runs the SOURCE of the generation-2 front-end kernels (deeplip_b200/csrc/frontend_gen2.cuh) on the CPU: one OS thread
+// per CUDA thread, std::barrier for __syncthreads / __syncwarp, an exchange buffer for the warp shuffles.  Test
+// infrastructure only (tests/test_host_logic.py::test_frontend_kernel_source_on_cpu_threads compares the output with
+// oracle/frontend_np.py); it checks index arithmetic, framing, tables and staging -- not memory-model behaviour.
+//   usage: frontend_cpu_emul kind F nsamp B pad_mode cmvn wav.f32 lengths.i32|- out.bin
+//   out.bin = feat_f32 (B,F,T) float32 followed by feat_bf16 (B,T,ld) uint16, ld = ceil64(F)
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__
+
+struct Idx3 { int x, y, z; };
+thread_local Idx3 threadIdx, blockIdx;
+Idx3 gridDim, blockDim;
+struct uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+using std::max;
+using std::min;
+template <typename T> inline T __ldg(const T* p) { return *p; }
+
+struct BlockCtx {
+  std::barrier<> all{256};
+  std::vector<std::unique_ptr<std::barrier<>>> warp;
+  float xch[8][32];
+  BlockCtx() { for (int i = 0; i < 8; ++i) warp.emplace_back(new std::barrier<>(32)); }
+};
+thread_local BlockCtx* g_ctx;
+inline void __syncthreads() { g_ctx->all.arrive_and_wait(); }
+inline void __syncwarp() { g_ctx->warp[threadIdx.x >> 5]->arrive_and_wait(); }
+
+namespace dl {
+inline float warp_sum(float v) {       // the xor butterfly of dl_ptx.cuh
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int off = 16; off > 0; off >>= 1) {
+    g_ctx->xch[w][lane] = v;
+    __syncwarp();
+    const float o = g_ctx->xch[w][lane ^ off];
+    __syncwarp();
+    v += o;
+  }
+  return v;
+}
+inline uint32_t bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+inline uint32_t pack_bf16x2(float lo, float hi) { return bf16_rn(lo) | (bf16_rn(hi) << 16); }
+alignas(16) float smf[64 * 1024];      // the kernels' dynamic shared memory
+alignas(16) float rows[64 * 1024];
+}  // namespace dl
+
+#include "../deeplip_b200/csrc/frontend_gen2.cuh"
+
+template <typename Fn>
+static void launch(int gx, int gy, Fn fn) {
+  gridDim = Idx3{gx, gy, 1};
+  blockDim = Idx3{256, 1, 1};
+  for (int by = 0; by < gy; ++by)
+    for (int bx = 0; bx < gx; ++bx) {
+      BlockCtx ctx;
+      std::vector<std::thread> th;
+      for (int t = 0; t < 256; ++t)
+        th.emplace_back([&, t] {
+          threadIdx = Idx3{t, 0, 0};
+          blockIdx = Idx3{bx, by, 0};
+          g_ctx = &ctx;
+          fn();
+        });
+      for (auto& x : th) x.join();
+    }
+}
+
+int main(int argc, char** argv) {
+  using namespace dl;
+  if (argc != 10) return 2;
+  const int kind = atoi(argv[1]), F = atoi(argv[2]), nsamp = atoi(argv[3]), B = atoi(argv[4]), pad = atoi(argv[5]),
+            cmvn = atoi(argv[6]);
+  const bool stft = kind == 3;
+  const int T = stft ? 1 + nsamp / kFrameStep
+                     : (nsamp <= kFrameLen ? 1 : 1 + (nsamp - kFrameLen + kFrameStep - 1) / kFrameStep);
+  const int ld = (F + 63) / 64 * 64;
+  std::vector<float> wav((size_t)B * nsamp), feat((size_t)B * F * T, -777.f);
+  std::vector<uint16_t> b16((size_t)B * T * ld, 0x7fc0);
+  std::vector<int32_t> len(B);
+  FILE* f = fopen(argv[7], "rb");
+  if (!f || fread(wav.data(), 4, wav.size(), f) != wav.size()) return 3;
+  fclose(f);
+  const int32_t* lengths = nullptr;
+  if (strcmp(argv[8], "-")) {
+    f = fopen(argv[8], "rb");
+    if (!f || fread(len.data(), 4, B, f) != (size_t)B) return 3;
+    fclose(f);
+    lengths = len.data();
+  }
+  if ((size_t)frames2_smem_floats(F) > sizeof(smf) / 4 || (size_t)8 * T > sizeof(rows) / 4) return 4;
+  fill_frontend_const(&g_fc);
+  FrontendTables tb;
+  fill_frontend_tables(&tb, kind, F, pad);
+  const float* w = wav.data();
+  float* ft = feat.data();
+  uint16_t* ob = b16.data();
+  if (stft) launch((T + kBlkFrames - 1) / kBlkFrames, B, [&] { frontend_frames2_kernel<true>(w, lengths, nsamp, T, tb, ft); });
+  else launch((T + kBlkFrames - 1) / kBlkFrames, B, [&] { frontend_frames2_kernel<false>(w, lengths, nsamp, T, tb, ft); });
+  launch(B, (F + 7) / 8, [&] { frontend_cmvn2_kernel(ft, lengths, nsamp, T, F, cmvn, stft ? 1 : 0, ob, ld); });
+  f = fopen(argv[9], "wb");
+  fwrite(feat.data(), 4, feat.size(), f);
+  fwrite(b16.data(), 2, b16.size(), f);
+  fclose(f);
+  printf("T %d ld %d\n", T, ld);
+  return 0;
+}

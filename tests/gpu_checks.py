@@ -302,12 +302,24 @@ def scoring_case(n_utt=500, D=1024, n_trials=3000, seed=0):
     return out
 
 
-def frontend_case(B=3, nsamp=16000, feat_type='mfcc', n_feat=24, seed=0, lengths=None):
+def frontend_case(B=3, nsamp=16000, feat_type='mfcc', n_feat=24, seed=0, lengths=None, gen=2, stft_pad='reflect'):
+    """K1 against oracle/frontend_np.py; gen selects the kernel generation (dl_set_option("frontend"))."""
+    from deeplip_b200 import _lib
     wav = synth.speech_like_audio(list(range(B)), nsamp=nsamp, seed=seed + 1)
     ln = None if lengths is None else torch.tensor(lengths, dtype=torch.int32, device=DEV)
-    f32, b16 = ops.frontend_features(torch.from_numpy(wav).to(DEV), feat_type, n_feat, lengths=ln)
-    torch.cuda.synchronize()
-    opts = dict(num_cep=n_feat, num_bin=n_feat)
+    _lib.set_option('frontend', gen)
+    _lib.set_option('stft_pad', 0 if stft_pad == 'reflect' else 1)
+    try:
+        f32, b16 = ops.frontend_features(torch.from_numpy(wav).to(DEV), feat_type, n_feat, lengths=ln)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option('frontend', 2)
+        _lib.set_option('stft_pad', 0)
+    if feat_type == 'stft':
+        n_feat = 257
+    assert f32.shape[1] == n_feat and b16.shape[2] % 64 == 0
+    assert float(b16[:, :, n_feat:].float().abs().max()) == 0.0 if b16.shape[2] > n_feat else True
+    opts = dict(num_cep=n_feat, num_bin=n_feat, pad_mode=stft_pad)
     out = {'abs': 0.0}
     for i in range(B):
         n = nsamp if lengths is None else lengths[i]

@@ -87,6 +87,11 @@ def test_scoring_empty_list():
 
 
 @pytest.mark.parametrize('kw', [dict(), dict(feat_type='logfbank', n_feat=60), dict(feat_type='fbank', n_feat=24),
-                                dict(B=3, nsamp=20000, lengths=[20000, 12345, 300]), dict(B=1, nsamp=48000)])
+                                dict(B=3, nsamp=20000, lengths=[20000, 12345, 300]), dict(B=1, nsamp=48000),
+                                dict(gen=1), dict(gen=1, B=3, nsamp=20000, lengths=[20000, 12345, 300]),
+                                dict(feat_type='stft'), dict(feat_type='stft', stft_pad='constant', B=2, nsamp=48000),
+                                dict(feat_type='stft', B=3, nsamp=20000, lengths=[20000, 12345, 700]),
+                                dict(B=2, nsamp=160000, lengths=[160000, 51234]),
+                                dict(feat_type='logfbank', n_feat=60, B=2, nsamp=30000, lengths=[401, 30000])])
 def test_frontend(kw):
     G.frontend_case(**kw)

@@ -39,6 +39,19 @@ def test_argument_validation_without_touching_the_gpu():
     assert b'ldx' in l.dl_last_error()
     assert l.dl_frontend_features(one, None, 1, 48000, 0, 24, 1, None, 64, one, 298, None) == -1
     assert b'299' in l.dl_last_error()
+    assert l.dl_frontend_features(one, None, 1, 48000, 3, 257, 1, None, 320, one, 299, None) == -1      # stft framing
+    assert b'301' in l.dl_last_error()
+    assert l.dl_frontend_features(one, None, 1, 48000, 3, 24, 1, None, 64, one, 301, None) == -1
+    assert b'257' in l.dl_last_error()
+
+
+def test_fft512_phase_functions_on_cpu(tmp_path):
+    """The warp FFT of the front end (deeplip_b200/csrc/fft512.cuh) is written as host+device phase functions:
+    run them on the CPU, lane by lane between the kernel's __syncwarp points, against a direct DFT."""
+    exe = str(tmp_path / 'fft512_host_check')
+    subprocess.run(['g++', '-O2', '-o', exe, os.path.join(ROOT, 'tests', 'fft512_host_check.cpp')], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == 'max_err' and float(out[1]) < 2e-4 and float(out[2]) < 1e-11, out
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-only behaviour')
@@ -52,6 +65,44 @@ def test_no_cpu_fallback():
         video(torch.zeros(1, 1, 2, 88, 88), lengths=[2])
     with pytest.raises(RuntimeError):
         audio.extract_embedding(torch.zeros(1, 24, 100))
+
+
+@pytest.mark.parametrize('feat_type,F,nsamp,lengths,pad', [
+    ('mfcc', 24, 16000, None, 'reflect'), ('logfbank', 60, 8000, None, 'reflect'), ('fbank', 24, 8000, None, 'reflect'),
+    ('mfcc', 24, 20000, [20000, 12345, 300], 'reflect'), ('stft', 257, 8000, None, 'reflect'),
+    ('stft', 257, 8000, None, 'constant'), ('stft', 257, 20000, [20000, 12345, 700], 'reflect')])
+def test_frontend_kernel_source_on_cpu_threads(tmp_path, feat_type, F, nsamp, lengths, pad):
+    """The generation-2 front-end kernels are compiled FROM THEIR CUDA SOURCE for the CPU (one OS thread per CUDA
+    thread, tests/frontend_cpu_emul.cpp) and compared with the oracle: framing, FFT, mel/DCT tables, ragged lengths,
+    stft padding, CMVN and the bf16 channels-last copy are all checked without a GPU."""
+    from oracle import frontend_np
+    from deeplip_b200 import synth
+    exe = str(tmp_path / 'emul')
+    subprocess.run(['g++', '-std=c++20', '-O2', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes', '-o', exe,
+                    os.path.join(ROOT, 'tests', 'frontend_cpu_emul.cpp')], check=True)
+    B = 2 if lengths is None else len(lengths)
+    wav = synth.speech_like_audio(list(range(B)), nsamp=nsamp, seed=1).astype(np.float32)
+    wav.tofile(str(tmp_path / 'wav.f32'))
+    lf = '-'
+    if lengths is not None:
+        lf = str(tmp_path / 'len.i32')
+        np.asarray(lengths, np.int32).tofile(lf)
+    kind = {'mfcc': 0, 'fbank': 1, 'logfbank': 2, 'stft': 3}[feat_type]
+    out = subprocess.run([exe, str(kind), str(F), str(nsamp), str(B), '0' if pad == 'reflect' else '1', '1',
+                          str(tmp_path / 'wav.f32'), lf, str(tmp_path / 'out.bin')], check=True, capture_output=True,
+                         text=True).stdout.split()
+    T, ld = int(out[1]), int(out[3])
+    raw = np.fromfile(str(tmp_path / 'out.bin'), dtype=np.uint8)
+    f32 = raw[:B * F * T * 4].view(np.float32).reshape(B, F, T)
+    bf = (raw[B * F * T * 4:].view(np.uint16).reshape(B, T, ld).astype(np.uint32) << 16).view(np.float32)
+    for i in range(B):
+        n = nsamp if lengths is None else lengths[i]
+        ref = frontend_np.extract_feature(wav[i, :n].astype(np.float64), 16000, feat_type,
+                                          dict(num_cep=F, num_bin=F, pad_mode=pad)).T
+        assert np.abs(f32[i][:, :ref.shape[1]] - ref).max() < 2e-3
+        assert np.all(f32[i][:, ref.shape[1]:] == 0)                     # padding frames of a ragged batch
+        assert np.abs(bf[i, :ref.shape[1], :F].T - ref).max() < 5e-2
+        assert np.all(bf[i, ref.shape[1]:, :] == 0) and np.all(bf[i, :, F:] == 0)
 
 
 def test_trial_list_parsing_matches_oracle(tmp_path):
