@@ -16,6 +16,7 @@ int require_sm100();
 int opt_pair();            // tuning switches (dl_set_option): CTA-pair kernels on / off
 int opt_dbg();
 int opt_frontend();        // 2 = register-resident radix-8 FFT front end (default), 1 = first-generation kernels
+int opt_prepass();         // 2 = one block per frame, aligned word loads (default), 1 = first-generation stem pre-pass
 int opt_stft_pad();        // stft centre padding: 0 reflect (librosa < 0.10), 1 zeros (librosa >= 0.10)
 int opt_tap_share();     // pair kernel shares one operand-A box across horizontal taps (guarded-linear mode)
 int opt_pair_resident();   // resident weight-half variant of the pair kernel on / off                          // DL_OK or DL_ERR_UNSUPPORTED

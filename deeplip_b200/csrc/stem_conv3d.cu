@@ -17,6 +17,7 @@
 // Roofline: tensor pipe; algorithmic work 2*Ho*Wo*64*245 flop per frame (DESIGN.md "Kernels").
 #include "dl_host.cuh"
 #include "dl_ptx.cuh"
+#include "stem_prepass.cuh"
 
 namespace dl {
 
@@ -465,7 +466,14 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   const int rows = H + 8, pitch = p.strip_pitch;
   // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
   const int dh = is_u8 ? (Hraw - H) / 2 : 0, dw = is_u8 ? (Wraw - W) / 2 : 0;
-  {
+  if (opt_prepass() >= 2) {
+    const int aligned4 = (Wraw % 4 == 0 && ((uintptr_t)x & 3) == 0) ? 1 : 0;
+    stem_prepass2_kernel<<<(unsigned)(B * T), 256, 0, cs>>>(
+        x, is_u8, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f, rows,
+        pitch, aligned4, static_cast<uint16_t*>(workspace));
+    st = check_launch("stem_prepass2_kernel");
+    if (st != DL_OK) return st;
+  } else {
     const long long n = (long long)B * T * rows * (pitch / 8);
     stem_prepass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(
         x, is_u8, B * T, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f,

@@ -1,0 +1,67 @@
+// Stem pre-pass, generation 2 (V1 fused: x/255, centre crop, (x-mean)/std; models/video_models/dataloaders.py:19-24):
+// uint8 crops or normalised f32 frames -> zero-bordered bf16 frames xp (frames, H+8, pitch), row iy+3, column ix+3.
+// One block per frame; a thread writes 8 consecutive columns (16 B) from three aligned 32-bit loads of the raw row
+// (funnel-shifted to the crop offset) -- no 64-bit index divisions, 2.7x fewer load instructions than generation 1.
+// Free of CUDA-runtime dependencies so that tests/frontend_cpu_emul.cpp can run this source on CPU threads.
+// The includer provides: pack_bf16x2(float, float), __ldg, __funnelshift_r, uint4.
+#pragma once
+#include <stdint.h>
+
+namespace dl {
+
+__global__ void __launch_bounds__(256) stem_prepass2_kernel(const void* __restrict__ x, int is_u8, int H, int W, int Hraw,
+                                                            int Wraw, int dh, int dw, float u8_scale, float u8_bias,
+                                                            int rows, int pitch, int aligned4, uint16_t* __restrict__ xp) {
+  const int f = blockIdx.x;
+  const int groups = pitch >> 3;
+  const int n = rows * groups;
+  uint16_t* of = xp + (size_t)f * rows * pitch;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int row = i / groups, g = i - row * groups;
+    const int iy = row - 3, ix0 = g * 8 - 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (iy >= 0 && iy < H) {
+      if (is_u8) {
+        const uint8_t* src = static_cast<const uint8_t*>(x) + ((size_t)f * Hraw + (iy + dh)) * Wraw;
+        const int c0 = ix0 + dw;                     // raw column of element 0 (may be negative)
+        if (aligned4) {
+          const int wb = c0 & ~3, sh = 8 * (c0 - wb);
+          uint32_t w[3];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int wc = wb + 4 * q;
+            w[q] = (wc >= 0 && wc < Wraw) ? __ldg(reinterpret_cast<const uint32_t*>(src + wc)) : 0u;
+          }
+          const uint32_t lo = __funnelshift_r(w[0], w[1], sh), hi = __funnelshift_r(w[1], w[2], sh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t u = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu;
+            const int ix = ix0 + j;
+            if (ix >= 0 && ix < W) v[j] = fmaf((float)u, u8_scale, u8_bias);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ix = ix0 + j;
+            if (ix >= 0 && ix < W) v[j] = fmaf((float)__ldg(src + c0 + j), u8_scale, u8_bias);
+          }
+        }
+      } else {
+        const float* src = static_cast<const float*>(x) + ((size_t)f * H + iy) * W;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ix = ix0 + j;
+          if (ix >= 0 && ix < W) v[j] = __ldg(src + ix);
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(of + (size_t)row * pitch + g * 8) = o;
+  }
+}
+
+}  // namespace dl

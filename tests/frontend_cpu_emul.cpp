@@ -4,6 +4,8 @@
 // oracle/frontend_np.py); it checks index arithmetic, framing, tables and staging -- not memory-model behaviour.
 //   usage: frontend_cpu_emul kind F nsamp B pad_mode cmvn wav.f32 lengths.i32|- out.bin
 //   out.bin = feat_f32 (B,F,T) float32 followed by feat_bf16 (B,T,ld) uint16, ld = ceil64(F)
+//   usage: frontend_cpu_emul prepass is_u8 frames H W Hraw Wraw in.bin out.bin     (stem_prepass.cuh; mean .421 std .165)
+//   out.bin = (frames, H+8, pitch) uint16 bf16, pitch = ceil8(W+8)
 #include <algorithm>
 #include <barrier>
 #include <cmath>
@@ -31,6 +33,9 @@ inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return
 using std::max;
 using std::min;
 template <typename T> inline T __ldg(const T* p) { return *p; }
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+  return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31));
+}
 
 struct BlockCtx {
   std::barrier<> all{256};
@@ -66,6 +71,7 @@ alignas(16) float rows[64 * 1024];
 }  // namespace dl
 
 #include "../deeplip_b200/csrc/frontend_gen2.cuh"
+#include "../deeplip_b200/csrc/stem_prepass.cuh"
 
 template <typename Fn>
 static void launch(int gx, int gy, Fn fn) {
@@ -86,9 +92,35 @@ static void launch(int gx, int gy, Fn fn) {
     }
 }
 
+static int prepass_main(char** a) {
+  const int is_u8 = atoi(a[2]), frames = atoi(a[3]), H = atoi(a[4]), W = atoi(a[5]), Hraw = atoi(a[6]), Wraw = atoi(a[7]);
+  const int rows = H + 8, pitch = (W + 8 + 7) / 8 * 8;
+  const size_t nin = (size_t)frames * Hraw * Wraw * (is_u8 ? 1 : 4);
+  std::vector<uint8_t> in(nin + 4);
+  FILE* f = fopen(a[8], "rb");
+  if (!f || fread(in.data(), 1, nin, f) != nin) return 3;
+  fclose(f);
+  std::vector<uint16_t> out((size_t)frames * rows * pitch, 0x7fc0);
+  const float mean = 0.421f, std_ = 0.165f;
+  const int dh = is_u8 ? (Hraw - H) / 2 : 0, dw = is_u8 ? (Wraw - W) / 2 : 0;
+  const void* x = in.data();
+  uint16_t* xp = out.data();
+  const int aligned4 = (Wraw % 4 == 0 && ((uintptr_t)x & 3) == 0) ? 1 : 0;
+  launch(frames, 1, [&] {
+    dl::stem_prepass2_kernel(x, is_u8, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std_) : 1.0f,
+                             is_u8 ? -mean / std_ : 0.0f, rows, pitch, aligned4, xp);
+  });
+  f = fopen(a[9], "wb");
+  fwrite(out.data(), 2, out.size(), f);
+  fclose(f);
+  printf("rows %d pitch %d aligned %d\n", rows, pitch, aligned4);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   using namespace dl;
   if (argc != 10) return 2;
+  if (!strcmp(argv[1], "prepass")) return prepass_main(argv);
   const int kind = atoi(argv[1]), F = atoi(argv[2]), nsamp = atoi(argv[3]), B = atoi(argv[4]), pad = atoi(argv[5]),
             cmvn = atoi(argv[6]);
   const bool stft = kind == 3;

@@ -203,6 +203,15 @@ def stem_case(B=2, T=6, H=88, W=88, u8=False, seed=0):
                            sd['frontend3D.1.running_var'])
     y = ops.stem_conv3d(xin, w, s.to(DEV), h.to(DEV), sd['frontend3D.2.weight'].to(DEV), crop=(H, W))
     torch.cuda.synchronize()
+    # the two pre-pass generations (dl_set_option("prepass")) must agree bit for bit
+    from deeplip_b200 import _lib
+    _lib.set_option('prepass', 1)
+    try:
+        y1 = ops.stem_conv3d(xin, w, s.to(DEV), h.to(DEV), sd['frontend3D.2.weight'].to(DEV), crop=(H, W))
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option('prepass', 2)
+    assert torch.equal(y.view(torch.int16), y1.view(torch.int16)), 'pre-pass generations differ'
     out = {'rel': rel_err(y, ref)}
     d = (y.float().cpu() - ref).abs()
     out['worst'] = [int(v) for v in np.unravel_index(int(d.argmax()), d.shape)]
