@@ -63,16 +63,17 @@ __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restri
   for (int i = 0; i < 8; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
   int n = 0;
   if (c0 < C) {
-    // 4 time steps (4 independent 16-byte loads) in flight per lane: the kernel is pure streaming
-    for (int tb = warp; tb < len; tb += 32) {
-      uint4 v4[4];
+    // 8 time steps (8 independent 16-byte loads) in flight per lane: the kernel is pure streaming and at 2-3 blocks
+    // per SM needs that much to cover the HBM latency (same accumulation order as with 4)
+    for (int tb = warp; tb < len; tb += 64) {
+      uint4 v4[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int t = tb + 8 * u;
         if (t < len) v4[u] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * ldx + c0));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int t = tb + 8 * u;
         if (t >= len) break;
         const uint4 v = v4[u];

@@ -430,7 +430,7 @@ extern "C" long long dl_stem_workspace_bytes(int B, int T, int H, int W) {
 extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
                                             float mean, float std, const void* w_packed, const float* scale,
                                             const float* shift, const float* slope, void* y, int out_img_rows,
-                                            void* workspace, void* stream) {
+                                            const int32_t* lengths, void* workspace, void* stream) {
   using namespace dl;
   DL_CHECK_ARG(x && w_packed && scale && shift && slope && y && workspace, "stem: null pointer");
   DL_CHECK_ARG(B > 0 && T > 0, "stem: empty batch");
@@ -466,11 +466,11 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   const int rows = H + 8, pitch = p.strip_pitch;
   // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
   const int dh = is_u8 ? (Hraw - H) / 2 : 0, dw = is_u8 ? (Wraw - W) / 2 : 0;
-  if (opt_prepass() >= 2) {
+  if (opt_prepass() >= 2 || lengths) {
     const int aligned4 = (Wraw % 4 == 0 && ((uintptr_t)x & 3) == 0) ? 1 : 0;
     stem_prepass2_kernel<<<(unsigned)(B * T), 256, 0, cs>>>(
         x, is_u8, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f, rows,
-        pitch, aligned4, static_cast<uint16_t*>(workspace));
+        pitch, aligned4, T, lengths, static_cast<uint16_t*>(workspace));
     st = check_launch("stem_prepass2_kernel");
     if (st != DL_OK) return st;
   } else {

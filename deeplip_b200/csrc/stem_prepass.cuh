@@ -2,6 +2,7 @@
 // uint8 crops or normalised f32 frames -> zero-bordered bf16 frames xp (frames, H+8, pitch), row iy+3, column ix+3.
 // One block per frame; a thread writes 8 consecutive columns (16 B) from three aligned 32-bit loads of the raw row
 // (funnel-shifted to the crop offset) -- no 64-bit index divisions, 2.7x fewer load instructions than generation 1.
+// `lengths` (may be NULL): valid frames per clip of T frames; later frames are written as zeros.
 // Free of CUDA-runtime dependencies so that tests/frontend_cpu_emul.cpp can run this source on CPU threads.
 // The includer provides: pack_bf16x2(float, float), __ldg, __funnelshift_r, uint4.
 #pragma once
@@ -11,8 +12,14 @@ namespace dl {
 
 __global__ void __launch_bounds__(256) stem_prepass2_kernel(const void* __restrict__ x, int is_u8, int H, int W, int Hraw,
                                                             int Wraw, int dh, int dw, float u8_scale, float u8_bias,
-                                                            int rows, int pitch, int aligned4, uint16_t* __restrict__ xp) {
+                                                            int rows, int pitch, int aligned4, int T,
+                                                            const int32_t* __restrict__ lengths,
+                                                            uint16_t* __restrict__ xp) {
   const int f = blockIdx.x;
+  // ragged batches (pad_packed_collate, models/video_models/dataset.py:123-139): the reference pads AFTER its
+  // preprocessing, i.e. with normalised zeros -- frames at or beyond the clip's length become all-zero here, whatever
+  // the raw padding bytes are (a raw 0 would normalise to -2.55)
+  const bool dead = lengths != nullptr && (f % T) >= lengths[f / T];
   const int groups = pitch >> 3;
   const int n = rows * groups;
   uint16_t* of = xp + (size_t)f * rows * pitch;
@@ -22,7 +29,7 @@ __global__ void __launch_bounds__(256) stem_prepass2_kernel(const void* __restri
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (iy >= 0 && iy < H) {
+    if (iy >= 0 && iy < H && !dead) {
       if (is_u8) {
         const uint8_t* src = static_cast<const uint8_t*>(x) + ((size_t)f * Hraw + (iy + dh)) * Wraw;
         const int c0 = ix0 + dw;                     // raw column of element 0 (may be negative)

@@ -85,10 +85,13 @@ def nct_to_ntc_bf16(x, ld=None):
 
 
 # ------------------------------------------------------------------ K2
-def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std=0.165, out=None):
+def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std=0.165, out=None, lengths=None):
     """x: (B,T,H,W) f32 normalised frames, or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T, H/4, W/4, 64) bf16.
-    out: optional pre-zeroed (B*T, rows >= H/4, W/4, 64) buffer in the stacked-rows layout."""
-    _need_cuda(x, w_packed, scale, shift, slope)
+    out: optional pre-zeroed (B*T, rows >= H/4, W/4, 64) buffer in the stacked-rows layout.
+    lengths: int32 CUDA (B,) valid frames per clip; later frames are treated as zero normalised frames."""
+    _need_cuda(x, w_packed, scale, shift, slope, lengths)
+    if lengths is not None:
+        assert lengths.dtype == torch.int32 and lengths.numel() == x.shape[0]
     x = x.contiguous()
     B, T = x.shape[0], x.shape[1]
     if x.dtype == torch.uint8:
@@ -108,7 +111,7 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
     ws = _workspace(x.device, _lib.lib().dl_stem_workspace_bytes(B, T, H, W))
     st = _lib.lib().dl_stem_conv3d_bn_prelu_pool(_ptr(x), is_u8, B, T, H, W, Hraw, Wraw, float(mean), float(std),
                                                  _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope), _ptr(y),
-                                                 y.shape[1], _ptr(ws), _stream())
+                                                 y.shape[1], _ptr(lengths), _ptr(ws), _stream())
     _lib.check(st, 'dl_stem_conv3d_bn_prelu_pool')
     return y
 

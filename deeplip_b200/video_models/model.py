@@ -84,8 +84,10 @@ class Lipreading(nn.Module):
             self._pk = pk
         return self._pk
 
-    def trunk_maps(self, x):
-        """x: (B,T,H,W) f32 normalised frames or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T,3,3,512) bf16."""
+    def trunk_maps(self, x, lengths=None):
+        """x: (B,T,H,W) f32 normalised frames or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T,3,3,512) bf16.
+        lengths (int32 CUDA, optional): frames at or beyond a clip's length enter the stem as zero normalised
+        frames (what pad_packed_collate produces), whatever the padding bytes of a raw u8 batch are."""
         if self.training:
             raise RuntimeError('deeplip_b200.Lipreading is inference-only: call .eval() (BN uses running stats)')
         pk = self._packed()
@@ -94,9 +96,9 @@ class Lipreading(nn.Module):
         if self.trunk.halo_enabled(W // 4):
             # stem writes straight into the stacked-rows layout layer1's halo kernel consumes
             buf = self.trunk.stacked_buffers(B * T, H // 4, W // 4, x.device, 2 * len(self.trunk.layer1) + 1)[-1]
-            ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], out=buf)
+            ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], out=buf, lengths=lengths)
             return self.trunk.forward_nhwc(buf, stacked_H=H // 4)
-        y = ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'])
+        y = ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], lengths=lengths)
         return self.trunk.forward_nhwc(y)
 
     def forward(self, x, lengths=None):
@@ -112,6 +114,6 @@ class Lipreading(nn.Module):
         """Fused form of train_fusion.py:400: mean over the (valid) frames of each clip -> (B,512).
         x as in trunk_maps; lengths: int32 CUDA tensor of valid frame counts (zero-padded tails)."""
         B, T = x.shape[0], x.shape[1]
-        y = self.trunk_maps(x)
+        y = self.trunk_maps(x, lengths)
         _, mean = ops.frame_pool_temporal_mean(y, B, T, lengths=lengths, want_frames=False, want_mean=True)
         return mean

@@ -75,14 +75,19 @@ int dl_nct_to_ntc_bf16(const float* x, int B, int C, int T, void* y, int ldc, vo
  *     y: (B*T, out_img_rows, W/4, 64) bf16 channels-last; out_img_rows >= H/4 is the row pitch of one
  *     frame (0 = H/4).  Rows H/4 .. out_img_rows-1 are not written ("stacked rows" layout of
  *     dl_conv3x3_c64_halo_bf16: the caller keeps them zero).
+ *     lengths: valid frames per clip (device int32[B], may be NULL): frames t >= lengths[b] are taken as
+ *     all-zero NORMALISED frames, the reference's pad-after-preprocessing convention for ragged batches
+ *     (pad_packed_collate, models/video_models/dataset.py:123-139) -- needed for raw u8 input, where no
+ *     padding byte normalises to zero.
  *     workspace: caller-owned scratch of dl_stem_workspace_bytes(B, T, H, W) bytes (the normalised,
  *     zero-bordered bf16 frames the TMA unit streams from; this library never allocates).
+ *     dl_set_option("prepass", 1) selects the first-generation pre-pass kernel (A/B measurements; no lengths).
  */
 long long dl_stem_workspace_bytes(int B, int T, int H, int W);
 int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
                                  float mean, float std, const void* w_packed, const float* scale,
                                  const float* shift, const float* slope, void* y, int out_img_rows,
-                                 void* workspace, void* stream);
+                                 const int32_t* lengths, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3/K5/K7  implicit-GEMM convolution on tcgen05 tensor cores (TMA im2col operand A, TMA tiled

@@ -106,9 +106,14 @@ static int prepass_main(char** a) {
   const void* x = in.data();
   uint16_t* xp = out.data();
   const int aligned4 = (Wraw % 4 == 0 && ((uintptr_t)x & 3) == 0) ? 1 : 0;
+  // frames = clips x 2; with 4 frames the second clip is ragged (length 1): its frame 1 must come out as zeros
+  const int Tclip = 2;
+  std::vector<int32_t> lv(frames / 2 + 1, 2);
+  const int32_t* lens = nullptr;
+  if (frames == 4) { lv[1] = 1; lens = lv.data(); }
   launch(frames, 1, [&] {
     dl::stem_prepass2_kernel(x, is_u8, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std_) : 1.0f,
-                             is_u8 ? -mean / std_ : 0.0f, rows, pitch, aligned4, xp);
+                             is_u8 ? -mean / std_ : 0.0f, rows, pitch, aligned4, Tclip, lens, xp);
   });
   f = fopen(a[9], "wb");
   fwrite(out.data(), 2, out.size(), f);

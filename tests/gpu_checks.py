@@ -571,6 +571,47 @@ def pipeline_case(B=4, T=8, nsamp=24000, seed=1):
     return out
 
 
+def tcd_timit_ragged_case(durations=(3.0, 6.44, 10.0), seed=3):
+    """BASELINE configs[4]: TCD-TIMIT-shaped long, variable-length utterances (3-10 s -> 75..250 lip frames at
+    25 fps, 48 000..160 000 samples) in ONE padded batch with `lengths` (the reference's pad_packed_collate
+    convention, models/video_models/dataset.py:123-139).  Each utterance of the ragged batch must equal the same
+    utterance run alone, and the longest one must match the fp32 oracle chain."""
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    audio, video = build_models(DEV, seed=seed)
+    ex = AVExtractor(audio, video)
+    B = len(durations)
+    Tv = [int(round(25 * d)) for d in durations]
+    ns = [int(16000 * d) for d in durations]
+    Tm, nm = max(Tv), max(ns)
+    spk = list(range(1, B + 1))
+    wav = synth.speech_like_audio(spk, nsamp=nm, seed=seed)
+    raw = synth.lip_crops_u8(spk, T=Tm, seed=seed)
+    for i in range(B):                                   # zero-padded tails, like the collate function
+        wav[i, ns[i]:] = 0
+        raw[i, Tv[i]:] = 0
+    wl = torch.tensor(ns, dtype=torch.int32, device=DEV)
+    vl = torch.tensor(Tv, dtype=torch.int32, device=DEV)
+    rag = ex.extract(torch.from_numpy(wav).to(DEV), torch.from_numpy(raw).to(DEV), wl, vl)
+    out = {'alone_abs': 0.0}
+    for i in range(B):
+        alone = ex.extract(torch.from_numpy(wav[i:i + 1, :ns[i]].copy()).to(DEV),
+                           torch.from_numpy(raw[i:i + 1, :Tv[i]].copy()).to(DEV))
+        out['alone_abs'] = max(out['alone_abs'], float((rag[i] - alone[0]).abs().max()))
+    torch.cuda.synchronize()
+    i = int(np.argmax(Tv))
+    o = synth.audio_opts('etdnn', 'statistic')
+    sda, sdv = synth.make_audio_state_dict(o, seed=seed), synth.make_video_state_dict(seed=seed)
+    with torch.no_grad():
+        feat = torch.from_numpy(frontend_np.extract_feature(wav[i, :ns[i]].astype(np.float64)).T)[None]
+        xv, _ = models_ref.speaker_extract_embedding(sda, feat, o)
+        x = models_ref.video_preprocess(torch.from_numpy(raw[i, :Tv[i]]))[None, None]
+        em = models_ref.temporal_mean(models_ref.lipreading_features(sdv, x))
+        ref = models_ref.concat_fusion(xv, em)
+    out['emb_cos_longest'] = float(cosine_rows(rag[i:i + 1], ref).min())
+    assert out['alone_abs'] < 1e-4 and out['emb_cos_longest'] > 0.999, out
+    return out
+
+
 def determinism_case(B=8, T=10, reps=25, seed=1):
     """Bitwise run-to-run determinism of the video path under back-to-back launches (no host sync in
     between).  Guards the smem hand-offs between generic-proxy readers and TMA refills: a missing proxy

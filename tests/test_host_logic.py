@@ -105,16 +105,17 @@ def test_frontend_kernel_source_on_cpu_threads(tmp_path, feat_type, F, nsamp, le
         assert np.all(bf[i, ref.shape[1]:, :] == 0) and np.all(bf[i, :, F:] == 0)
 
 
-@pytest.mark.parametrize('is_u8,H,W,Hraw,Wraw', [(1, 88, 88, 96, 96), (1, 88, 88, 90, 90), (1, 64, 64, 100, 100),
-                                                 (1, 88, 88, 88, 88), (0, 88, 88, 88, 88), (0, 32, 36, 32, 36)])
-def test_stem_prepass_kernel_source_on_cpu_threads(tmp_path, is_u8, H, W, Hraw, Wraw):
+@pytest.mark.parametrize('is_u8,H,W,Hraw,Wraw,frames', [(1, 88, 88, 96, 96, 2), (1, 88, 88, 90, 90, 2),
+                                                        (1, 64, 64, 100, 100, 2), (1, 88, 88, 88, 88, 2),
+                                                        (0, 88, 88, 88, 88, 2), (0, 32, 36, 32, 36, 2),
+                                                        (1, 88, 88, 96, 96, 4), (0, 32, 32, 32, 32, 4)])
+def test_stem_prepass_kernel_source_on_cpu_threads(tmp_path, is_u8, H, W, Hraw, Wraw, frames):
     """stem_prepass2_kernel (V1 fused: /255, centre crop, mean/std, zero border, bf16) run from its CUDA source on
     CPU threads: aligned-word and byte load paths, crop offsets that make the word base negative, f32 input."""
     exe = str(tmp_path / 'emul')
     subprocess.run(['g++', '-std=c++20', '-O2', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes', '-o', exe,
                     os.path.join(ROOT, 'tests', 'frontend_cpu_emul.cpp')], check=True)
     rng = np.random.default_rng(0)
-    frames = 2
     if is_u8:
         x = rng.integers(0, 256, (frames, Hraw, Wraw), dtype=np.uint8)
         dh, dw = (Hraw - H) // 2, (Wraw - W) // 2          # CenterCrop, models/video_models/preprocess.py:88-90
@@ -130,6 +131,8 @@ def test_stem_prepass_kernel_source_on_cpu_threads(tmp_path, is_u8, H, W, Hraw, 
            ).view(np.float32)
     exp = np.zeros_like(got)
     exp[:, 3:3 + H, 3:3 + W] = ref
+    if frames == 4:          # the harness runs 4 frames as two clips of T = 2 with lengths (2, 1): a ragged batch whose
+        exp[3] = 0           # padding frame must enter the stem as NORMALISED zeros (pad_packed_collate convention)
     assert (np.abs(got - exp) / np.maximum(1, np.abs(exp))).max() < 5e-3          # bf16 rounding
     border = np.ones_like(got, dtype=bool)
     border[:, 3:3 + H, 3:3 + W] = False
