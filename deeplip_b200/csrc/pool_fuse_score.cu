@@ -15,7 +15,7 @@ struct Welford8 {
   float mean[8], m2[8];
 };
 
-template <bool kAttn>
+template <bool kAttn, int kMlp>
 __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restrict__ x, const float* __restrict__ logits,
                                                         int T, int C, int ldx, const int32_t* __restrict__ lengths,
                                                         float* __restrict__ out_f32, uint16_t* __restrict__ out_bf16,
@@ -63,17 +63,17 @@ __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restri
   for (int i = 0; i < 8; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
   int n = 0;
   if (c0 < C) {
-    // 8 time steps (8 independent 16-byte loads) in flight per lane: the kernel is pure streaming and at 2-3 blocks
-    // per SM needs that much to cover the HBM latency (same accumulation order as with 4)
-    for (int tb = warp; tb < len; tb += 64) {
-      uint4 v4[8];
+    // kMlp time steps (independent 16-byte loads) in flight per lane: the kernel is pure streaming (same accumulation
+    // order for every kMlp)
+    for (int tb = warp; tb < len; tb += 8 * kMlp) {
+      uint4 v4[kMlp];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kMlp; ++u) {
         const int t = tb + 8 * u;
         if (t < len) v4[u] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * ldx + c0));
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kMlp; ++u) {
         const int t = tb + 8 * u;
         if (t >= len) break;
         const uint4 v = v4[u];
@@ -400,8 +400,12 @@ extern "C" int dl_stat_pool(const void* x, int B, int T, int C, int ldx, const i
   DL_CHECK_ARG(!out_bf16 || ld_out >= 2 * C, "stat_pool: ld_out < 2C");
   dim3 grid((C + 255) / 256, B);
   const size_t smem = 8 * 256 * 2 * sizeof(float);
-  stat_pool_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
+  if (opt_statpool_mlp() == 4)
+    stat_pool_kernel<false, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
+  else
+    stat_pool_kernel<false, 8><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
   return check_launch("stat_pool_kernel");
 }
 
@@ -413,10 +417,10 @@ extern "C" int dl_attn_stat_pool(const void* x, const float* logits, int B, int 
   dim3 grid((C + 255) / 256, B);
   const size_t smem = (8 * 256 * 2 + T) * sizeof(float);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(stat_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(stat_pool_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "attn_stat_pool smem: %s", cudaGetErrorString(e));
   }
-  stat_pool_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  stat_pool_kernel<true, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(
       (const uint16_t*)x, logits, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
   return check_launch("attn_stat_pool_kernel");
 }

@@ -6,6 +6,9 @@
 //   out.bin = feat_f32 (B,F,T) float32 followed by feat_bf16 (B,T,ld) uint16, ld = ceil64(F)
 //   usage: frontend_cpu_emul prepass is_u8 frames H W Hraw Wraw in.bin out.bin     (stem_prepass.cuh; mean .421 std .165)
 //   out.bin = (frames, H+8, pitch) uint16 bf16, pitch = ceil8(W+8)
+//   usage: frontend_cpu_emul linear M C Cout ldx ldw with_bf16 with_scale2 in.bin out.bin     (linear_small.cuh)
+//   in.bin = x (M,ldx) u16 | w (Cout,ldw) u16 | scale, shift, slope, scale2, shift2 (Cout f32 each); f32_slope = 0.2
+//   out.bin = y (M,Cout) u16 | yf (M,Cout) f32
 #include <algorithm>
 #include <barrier>
 #include <cmath>
@@ -38,10 +41,10 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 }
 
 struct BlockCtx {
-  std::barrier<> all{256};
+  std::barrier<> all;
   std::vector<std::unique_ptr<std::barrier<>>> warp;
   float xch[8][32];
-  BlockCtx() { for (int i = 0; i < 8; ++i) warp.emplace_back(new std::barrier<>(32)); }
+  explicit BlockCtx(int nthreads) : all(nthreads) { for (int i = 0; i < 8; ++i) warp.emplace_back(new std::barrier<>(32)); }
 };
 thread_local BlockCtx* g_ctx;
 inline void __syncthreads() { g_ctx->all.arrive_and_wait(); }
@@ -66,22 +69,26 @@ inline uint32_t bf16_rn(float f) {
   return u >> 16;
 }
 inline uint32_t pack_bf16x2(float lo, float hi) { return bf16_rn(lo) | (bf16_rn(hi) << 16); }
+inline float bf16_lo(uint32_t v) { v <<= 16; float f; memcpy(&f, &v, 4); return f; }
+inline float bf16_hi(uint32_t v) { v &= 0xffff0000u; float f; memcpy(&f, &v, 4); return f; }
 alignas(16) float smf[64 * 1024];      // the kernels' dynamic shared memory
 alignas(16) float rows[64 * 1024];
+alignas(16) float lin_part[4096];
 }  // namespace dl
 
 #include "../deeplip_b200/csrc/frontend_gen2.cuh"
 #include "../deeplip_b200/csrc/stem_prepass.cuh"
+#include "../deeplip_b200/csrc/linear_small.cuh"
 
 template <typename Fn>
-static void launch(int gx, int gy, Fn fn) {
+static void launch(int gx, int gy, Fn fn, int nthreads = 256) {
   gridDim = Idx3{gx, gy, 1};
-  blockDim = Idx3{256, 1, 1};
+  blockDim = Idx3{nthreads, 1, 1};
   for (int by = 0; by < gy; ++by)
     for (int bx = 0; bx < gx; ++bx) {
-      BlockCtx ctx;
+      BlockCtx ctx(nthreads);
       std::vector<std::thread> th;
-      for (int t = 0; t < 256; ++t)
+      for (int t = 0; t < nthreads; ++t)
         th.emplace_back([&, t] {
           threadIdx = Idx3{t, 0, 0};
           blockIdx = Idx3{bx, by, 0};
@@ -122,8 +129,36 @@ static int prepass_main(char** a) {
   return 0;
 }
 
+static int linear_main(char** a) {
+  using namespace dl;
+  const int M = atoi(a[2]), C = atoi(a[3]), Cout = atoi(a[4]), ldx = atoi(a[5]), ldw = atoi(a[6]), wb = atoi(a[7]),
+            ws2 = atoi(a[8]);
+  std::vector<uint16_t> x((size_t)M * ldx), w((size_t)Cout * ldw), y((size_t)M * Cout, 0x7fc0);
+  std::vector<float> prm((size_t)5 * Cout), yf((size_t)M * Cout, -777.f);
+  FILE* f = fopen(a[9], "rb");
+  if (!f || fread(x.data(), 2, x.size(), f) != x.size() || fread(w.data(), 2, w.size(), f) != w.size() ||
+      fread(prm.data(), 4, prm.size(), f) != prm.size()) return 3;
+  fclose(f);
+  LinearSmallParams p{};
+  p.x = x.data(); p.w = w.data(); p.M = M; p.C = C; p.ldx = ldx; p.ldw = ldw; p.Cout = Cout;
+  p.scale = prm.data(); p.shift = prm.data() + Cout; p.slope = prm.data() + 2 * Cout;
+  p.y = wb ? y.data() : nullptr; p.ldy = Cout;
+  p.scale2 = ws2 ? prm.data() + 3 * Cout : nullptr; p.shift2 = ws2 ? prm.data() + 4 * Cout : nullptr;
+  p.f32_slope = 0.2f; p.yf = yf.data(); p.ldf = Cout;
+  const int grid = (Cout + kLinCh - 1) / kLinCh;
+  if (M <= 32) launch(grid, 1, [&] { linear_small_kernel<1>(p); }, 32 * kLinKs);
+  else if (M <= 64) launch(grid, 1, [&] { linear_small_kernel<2>(p); }, 32 * kLinKs);
+  else launch(grid, 1, [&] { linear_small_kernel<4>(p); }, 32 * kLinKs);
+  f = fopen(a[10], "wb");
+  fwrite(y.data(), 2, y.size(), f);
+  fwrite(yf.data(), 4, yf.size(), f);
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   using namespace dl;
+  if (argc == 11 && !strcmp(argv[1], "linear")) return linear_main(argv);
   if (argc != 10) return 2;
   if (!strcmp(argv[1], "prepass")) return prepass_main(argv);
   const int kind = atoi(argv[1]), F = atoi(argv[2]), nsamp = atoi(argv[3]), B = atoi(argv[4]), pad = atoi(argv[5]),

@@ -139,6 +139,39 @@ def test_stem_prepass_kernel_source_on_cpu_threads(tmp_path, is_u8, H, W, Hraw, 
     assert np.all(got[border] == 0)
 
 
+@pytest.mark.parametrize('M,C,Cout,wb,ws2', [(64, 3000, 512, 1, 1), (64, 512, 512, 0, 1), (3, 1024, 24, 1, 0),
+                                             (100, 512, 8, 1, 1), (33, 72, 24, 1, 1)])
+def test_linear_small_kernel_source_on_cpu_threads(tmp_path, M, C, Cout, wb, ws2):
+    """linear_small_kernel (fc heads, tdnn.py:89-101) from its CUDA source on CPU threads vs a float64 product of the
+    same bf16 operands: K split over warps, rows per lane 1/2/4, both outputs and their epilogues."""
+    exe = str(tmp_path / 'emul')
+    subprocess.run(['g++', '-std=c++20', '-O2', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes', '-o', exe,
+                    os.path.join(ROOT, 'tests', 'frontend_cpu_emul.cpp')], check=True)
+    rng = np.random.default_rng(0)
+    ldx, ldw = (C + 63) // 64 * 64 + 8, (C + 63) // 64 * 64
+    x = torch.from_numpy(rng.standard_normal((M, ldx)).astype(np.float32)).to(torch.bfloat16)
+    w = torch.from_numpy((rng.standard_normal((Cout, ldw)) / np.sqrt(C)).astype(np.float32)).to(torch.bfloat16)
+    prm = rng.standard_normal((5, Cout)).astype(np.float32)          # scale, shift, slope, scale2, shift2
+    prm[2] = np.abs(prm[2]) * 0.3
+    with open(tmp_path / 'in.bin', 'wb') as f:
+        f.write(x.view(torch.int16).numpy().tobytes())
+        f.write(w.view(torch.int16).numpy().tobytes())
+        f.write(prm.tobytes())
+    subprocess.run([exe, 'linear', str(M), str(C), str(Cout), str(ldx), str(ldw), str(wb), str(ws2),
+                    str(tmp_path / 'in.bin'), str(tmp_path / 'out.bin')], check=True)
+    raw = np.fromfile(str(tmp_path / 'out.bin'), np.uint8)
+    y = (raw[:M * Cout * 2].view(np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(M, Cout)
+    yf = raw[M * Cout * 2:].view(np.float32).reshape(M, Cout)
+    acc = x[:, :C].double().numpy() @ w[:, :C].double().numpy().T         # columns >= C of x are ignored
+    o2 = acc * prm[3] + prm[4] if ws2 else acc
+    o2 = np.where(o2 > 0, o2, o2 * 0.2)
+    assert np.abs(yf - o2).max() < 1e-4
+    if wb:
+        v = acc * prm[0] + prm[1]
+        v = np.where(v > 0, v, v * prm[2])
+        assert (np.abs(y - v) / np.maximum(1, np.abs(v))).max() < 5e-3
+
+
 def test_trial_list_parsing_matches_oracle(tmp_path):
     from deeplip_b200.trials import TrialList
     from oracle import scoring_ref

@@ -65,3 +65,34 @@ ms = t_ms(lambda: audio.embed_ntc(a1[1]))
 print('E-TDNN + pooling + heads B=64 %8.1f us' % (ms * 1e3))
 ms = t_ms(lambda: video.utterance_embedding(raw))
 print('video branch B=64 %8.1f us' % (ms * 1e3))
+
+# ---- heads: linear_small_kernel vs the tensor-core igemm; stat pool loads in flight; host -> device bandwidth
+pooled = torch.randn(64, 3008, device=dev).to(torch.bfloat16)
+pk_a = audio._packed()
+E = audio.embedding_dim
+for sl in (0, 1):
+    _lib.set_option('small_linear', sl)
+    ms1 = t_ms(lambda: ops.conv_igemm(pooled.view(64, 1, 1, -1), pk_a['w1'], pooled.shape[1], E, scale=pk_a['s1'],
+                                      shift=pk_a['h1'], slope=pk_a['lrelu'], want_f32=True, scale2=pk_a['one'],
+                                      shift2=pk_a['b1']))
+    h = torch.randn(64, 1, 1, E, device=dev).to(torch.bfloat16)
+    ms2 = t_ms(lambda: ops.conv_igemm(h, pk_a['w2'], E, E, want_bf16=False, want_f32=True, scale2=pk_a['one'],
+                                      shift2=pk_a['b2']))
+    print('heads small_linear=%d: fc1 %6.1f us  fc2 %6.1f us' % (sl, ms1 * 1e3, ms2 * 1e3))
+_lib.set_option('small_linear', 1)
+for mlp in (4, 8):
+    _lib.set_option('statpool_mlp', mlp)
+    ms = t_ms(lambda: ops.stat_pool(xs, 1500))
+    print('stat_pool loads in flight %d: %6.1f us' % (mlp, ms * 1e3))
+_lib.set_option('statpool_mlp', 8)
+hraw = torch.empty((64, 75, 96, 96), dtype=torch.uint8).pin_memory()
+draw = torch.empty_like(hraw, device=dev)
+for _ in range(3):
+    draw.copy_(hraw, non_blocking=True)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    draw.copy_(hraw, non_blocking=True)
+b.record(); torch.cuda.synchronize()
+print('H2D pinned 44 MB: %.2f ms each = %.1f GB/s' % (a.elapsed_time(b) / 10, hraw.numel() * 10 / a.elapsed_time(b) / 1e6))
