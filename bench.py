@@ -242,7 +242,7 @@ def run_ours(args, rank, world, local):
     ms, launches = timed(args.steps, from_host=False)
     value = args.steps * n_total / (ms / 1e3)
 
-    timed_e2e(2)
+    timed_e2e(args.steps)        # warm-up at full length: staging slots, pinned output pool, allocator high-water mark
     ms_e2e = timed_e2e(args.steps)
     # keep every GPU busy for ~1 s more so the clock sampler sees the loaded state (same count on all ranks:
     # step() contains the collective)

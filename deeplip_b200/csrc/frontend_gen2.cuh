@@ -80,29 +80,36 @@ __global__ void __launch_bounds__(256, 2) frontend_frames2_kernel(const float* _
     if (tid < tb.nfilt + 2) sbins[tid] = tb.bins[tid];
     if (tid < tb.nfilt + 1) sinvw[tid] = tb.inv_width[tid];
   }
+  // ---- stage the block's samples.  Every thread issues ALL its global loads before it touches one of them (the loop
+  // used to wait out one DRAM round trip per iteration: a third of the kernel's stall samples); the raw samples rest
+  // in the FFT scratch, which is idle until the frames are built.
   const float* x = wav + (size_t)b * nsamp;
-  if (kStft) {
-    // librosa.stft(center=True): frame t covers samples [160 t - 256, 160 t + 256) of the padded signal
-    const int c0 = tblk * kFrameStep - kNfft / 2;
-    for (int i = tid; i < kChunk; i += 256) {
-      int s = c0 + i;
-      if (tb.pad_mode == 0) {
+  float* rawb = reinterpret_cast<float*>(S);               // rawb[i] = x[c0 + i - 1]
+  constexpr int kPer = (kChunk + 1 + 255) / 256;
+  const int c0 = kStft ? tblk * kFrameStep - kNfft / 2 : tblk * kFrameStep;
+  {
+    float v[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + 256 * j;
+      int s = c0 + i - 1;
+      if (kStft && tb.pad_mode == 0) {                     // librosa reflect padding (no edge repeat)
         if (s < 0) s = -s;
         if (s >= len) s = 2 * (len - 1) - s;
       }
-      ybuf[i] = (s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+      v[j] = (i <= kChunk && s >= 0 && s < len) ? __ldg(x + s) : 0.f;
     }
-  } else {
-    const int c0 = tblk * kFrameStep;
-    for (int i = tid; i < kChunk; i += 256) {
-      const int s = c0 + i;
-      float v = 0.f;
-      if (s < len) {
-        const float cur = __ldg(x + s);
-        v = (s == 0) ? cur : cur - kPreemph * __ldg(x + s - 1);
-      }
-      ybuf[i] = v;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + 256 * j;
+      if (i <= kChunk) rawb[i] = v[j];
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < kChunk; i += 256) {
+    // stft (librosa.stft, center=True): frame t covers samples [160 t - 256, 160 t + 256) of the padded signal;
+    // mfcc / fbank: pre-emphasis y[s] = x[s] - 0.97 x[s-1], y[0] = x[0] (rawb holds 0 for s - 1 < 0), zeros from `len` on
+    ybuf[i] = kStft ? rawb[i + 1] : (c0 + i < len ? rawb[i + 1] - kPreemph * rawb[i] : 0.f);
   }
   __syncthreads();
 

@@ -273,7 +273,9 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   DL_CHECK_ARG(M < (1ll << 31) - 256, "conv_igemm: too many output pixels");
   // ---- a handful of rows through a 1x1 filter (the fc heads: one row per utterance) is latency, not throughput:
   // linear_small_kernel spreads it over Cout/4 blocks instead of one or two tensor-core CTAs
-  if (opt_small_linear() && M <= 128 && d->R == 1 && d->S == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
+  // (only where one "pixel" is one batch item, P Q == 1, and whatever the batch size up to 4096, so that an utterance
+  // gets the same summation order alone and inside a batch)
+  if (opt_small_linear() && M <= 4096 && P * Q == 1 && d->R == 1 && d->S == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
       d->pad_w == 0 && !lin && !residual && d->C % 8 == 0 && d->out_img_rows == 0 &&
       (d->img_rows == 0 || d->img_rows == d->H) && (d->img_cols == 0 || d->img_cols == d->W) &&
       (((uintptr_t)x | (uintptr_t)w_packed) & 15) == 0) {
@@ -283,11 +285,10 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
     lp.scale = scale; lp.shift = shift; lp.slope = slope;
     lp.y = static_cast<uint16_t*>(y); lp.ldy = d->ldy;
     lp.scale2 = scale2; lp.shift2 = shift2; lp.f32_slope = d->f32_slope; lp.yf = y_f32; lp.ldf = d->ldf;
-    const int grid = (d->Cout + kLinCh - 1) / kLinCh;
+    const int gx = (d->Cout + kLinCh - 1) / kLinCh;
     cudaStream_t cs = (cudaStream_t)stream;
-    if (M <= 32) linear_small_kernel<1><<<grid, 32 * kLinKs, linear_small_smem_bytes(1), cs>>>(lp);
-    else if (M <= 64) linear_small_kernel<2><<<grid, 32 * kLinKs, linear_small_smem_bytes(2), cs>>>(lp);
-    else linear_small_kernel<4><<<grid, 32 * kLinKs, linear_small_smem_bytes(4), cs>>>(lp);
+    if (M <= 32) linear_small_kernel<1><<<dim3(gx, 1), 32 * kLinKs, linear_small_smem_bytes(1), cs>>>(lp);
+    else linear_small_kernel<2><<<dim3(gx, (unsigned)((M + 63) / 64)), 32 * kLinKs, linear_small_smem_bytes(2), cs>>>(lp);
     return check_launch("linear_small_kernel");
   }
   IgemmParams p;

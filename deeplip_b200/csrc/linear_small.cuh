@@ -29,18 +29,20 @@ struct LinearSmallParams {
 };
 
 constexpr int kLinCh = 4;       // output channels per warp (and per block)
-constexpr int kLinKs = 4;       // K splits = warps per block; partial sums meet in shared memory in a fixed order
+constexpr int kLinKs = 16;      // K splits = warps per block; partial sums meet in shared memory in a fixed order
 
 constexpr int linear_small_smem_bytes(int rpl) { return kLinKs * kLinCh * 32 * rpl * 4; }
 
-// grid (ceil(Cout / 4)); block 128 = 4 warps, warp ks accumulates K chunks [ks * cpk, (ks + 1) * cpk) of the block's
-// 4 channels for RPL rows per lane (M <= 32 RPL); x chunks are loaded once per lane and reused for the 4 channels.
+// grid (ceil(Cout / 4), ceil(M / (32 RPL))); block 512 = 16 warps, warp ks accumulates K chunks [ks * cpk, (ks + 1) * cpk)
+// of the block's 4 channels for RPL rows per lane; x chunks are loaded once per lane and reused for the 4 channels.
+// The loop is a chain of L2 round trips, so its length (K / 8 / 16 chunks per warp) is what the kernel costs.
 template <int RPL>
 __global__ void __launch_bounds__(32 * kLinKs) linear_small_kernel(LinearSmallParams p) {
   extern __shared__ __align__(16) float lin_part[];      // [kLinKs][kLinCh][32 RPL] (dynamic: linear_small_smem_bytes)
   constexpr int kRows = 32 * RPL;
   const int ks = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * kLinCh;
+  const int m0 = blockIdx.y * kRows;
   const uint16_t* wr[kLinCh];
 #pragma unroll
   for (int j = 0; j < kLinCh; ++j) wr[j] = p.w + (size_t)(c0 + j < p.Cout ? c0 + j : c0) * p.ldw;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(32 * kLinKs) linear_small_kernel(LinearSmallPa
   float acc[RPL][kLinCh];
 #pragma unroll
   for (int r = 0; r < RPL; ++r) {
-    const int m = lane + 32 * r;
+    const int m = m0 + lane + 32 * r;
     xr[r] = p.x + (size_t)(m < p.M ? m : 0) * p.ldx;      // rows beyond M compute on row 0 and are not stored
 #pragma unroll
     for (int j = 0; j < kLinCh; ++j) acc[r][j] = 0.f;
@@ -84,13 +86,15 @@ __global__ void __launch_bounds__(32 * kLinKs) linear_small_kernel(LinearSmallPa
 #pragma unroll
     for (int j = 0; j < kLinCh; ++j) lin_part[(ks * kLinCh + j) * kRows + lane + 32 * r] = acc[r][j];
   __syncthreads();
-  // ---- epilogue: thread t <-> (channel j = t / 32 .. , row); 128 threads cover 4 channels x 32 rows per round
+  // ---- epilogue: thread <-> (channel, row) pairs of the block; K partials summed in a fixed order
   for (int i = threadIdx.x; i < kLinCh * 32 * RPL; i += 32 * kLinKs) {
-    const int j = i / (32 * RPL), m = i - j * (32 * RPL);
-    const int c = c0 + j;
+    const int j = i / kRows, ml = i - j * kRows;
+    const int c = c0 + j, m = m0 + ml;
     if (m >= p.M || c >= p.Cout) continue;
-    const float* pj = lin_part + j * kRows + m;
-    const float a = ((pj[0] + pj[kLinCh * kRows]) + pj[2 * kLinCh * kRows]) + pj[3 * kLinCh * kRows];
+    const float* pj = lin_part + j * kRows + ml;
+    float a = pj[0];
+#pragma unroll
+    for (int q = 1; q < kLinKs; ++q) a += pj[q * kLinCh * kRows];
     if (p.yf != nullptr) {
       float o = p.scale2 != nullptr ? fmaf(a, __ldg(p.scale2 + c), __ldg(p.shift2 + c)) : a;
       o = o > 0.f ? o : o * p.f32_slope;

@@ -116,6 +116,7 @@ class HostPipeline:
         self._ready = [torch.cuda.Event() for _ in range(slots)]
         self._ready_wav = [torch.cuda.Event() for _ in range(slots)]
         self._free = [torch.cuda.Event() for _ in range(slots)]
+        self._out_pool = None       # pinned output rows, grown on demand and kept: cudaHostAlloc costs tens of ms
 
     def _upload(self, k, wav_h, vid_h):
         slot = k % self.slots
@@ -135,7 +136,7 @@ class HostPipeline:
     def run(self, batches, post=None):
         """batches: sequence of (wav_host (B,nsamp) f32 pinned, video_host (B,T,H,W) u8/f32 pinned).
         Returns the list of fused embeddings as pinned host tensors (valid after the final synchronize,
-        which this method performs)."""
+        which this method performs, and until the next run(): they are views of one pinned pool this object keeps)."""
         batches = list(batches)
         main = torch.cuda.current_stream(self.device)
         for ev in self._free:
@@ -160,8 +161,12 @@ class HostPipeline:
             self._free[slot].record(main)
             if post is not None:
                 emb = post(emb)
-            if pool is None:       # one pinned allocation per run (cudaHostAlloc per step would serialise the pipeline)
-                pool = torch.empty((len(batches),) + tuple(emb.shape), dtype=emb.dtype, pin_memory=True)
+            if pool is None:       # one pinned pool, kept across runs (cudaHostAlloc per step would serialise the pipeline)
+                need = (len(batches),) + tuple(emb.shape)
+                pool = self._out_pool
+                if pool is None or pool.dtype != emb.dtype or tuple(pool.shape[1:]) != need[1:] or pool.shape[0] < need[0]:
+                    pool = torch.empty(need, dtype=emb.dtype, pin_memory=True)
+                    self._out_pool = pool
             h = pool[k]
             h.copy_(emb, non_blocking=True)
             outs.append(h)

@@ -43,8 +43,8 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 struct BlockCtx {
   std::barrier<> all;
   std::vector<std::unique_ptr<std::barrier<>>> warp;
-  float xch[8][32];
-  explicit BlockCtx(int nthreads) : all(nthreads) { for (int i = 0; i < 8; ++i) warp.emplace_back(new std::barrier<>(32)); }
+  float xch[16][32];
+  explicit BlockCtx(int nthreads) : all(nthreads) { for (int i = 0; i < 16; ++i) warp.emplace_back(new std::barrier<>(32)); }
 };
 thread_local BlockCtx* g_ctx;
 inline void __syncthreads() { g_ctx->all.arrive_and_wait(); }
@@ -73,7 +73,7 @@ inline float bf16_lo(uint32_t v) { v <<= 16; float f; memcpy(&f, &v, 4); return 
 inline float bf16_hi(uint32_t v) { v &= 0xffff0000u; float f; memcpy(&f, &v, 4); return f; }
 alignas(16) float smf[64 * 1024];      // the kernels' dynamic shared memory
 alignas(16) float rows[64 * 1024];
-alignas(16) float lin_part[4096];
+alignas(16) float lin_part[16 * 4 * 64];
 }  // namespace dl
 
 #include "../deeplip_b200/csrc/frontend_gen2.cuh"
@@ -147,8 +147,7 @@ static int linear_main(char** a) {
   p.f32_slope = 0.2f; p.yf = yf.data(); p.ldf = Cout;
   const int grid = (Cout + kLinCh - 1) / kLinCh;
   if (M <= 32) launch(grid, 1, [&] { linear_small_kernel<1>(p); }, 32 * kLinKs);
-  else if (M <= 64) launch(grid, 1, [&] { linear_small_kernel<2>(p); }, 32 * kLinKs);
-  else launch(grid, 1, [&] { linear_small_kernel<4>(p); }, 32 * kLinKs);
+  else launch(grid, (M + 63) / 64, [&] { linear_small_kernel<2>(p); }, 32 * kLinKs);
   f = fopen(a[10], "wb");
   fwrite(y.data(), 2, y.size(), f);
   fwrite(yf.data(), 4, yf.size(), f);

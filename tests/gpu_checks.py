@@ -23,8 +23,8 @@ def rel_err(a, b):
 
 def conv_case(N, H, W, C, Cout, R, S, stride=1, pad=0, dil=(1, 1), residual=False, f32=False, seed=0, ld=None,
               tol=1.5e-2, small_linear=1):
-    """small_linear: dl_set_option("small_linear") -- 1 routes 1x1 layers with <= 128 rows to linear_small_kernel,
-    0 keeps them on the tensor-core igemm."""
+    """small_linear: dl_set_option("small_linear") -- 1 routes fc layers (P Q == 1, up to 4096 rows) to
+    linear_small_kernel, 0 keeps them on the tensor-core igemm."""
     from deeplip_b200 import _lib
     _lib.set_option('small_linear', small_linear)
     try:
@@ -192,6 +192,7 @@ CONV_CASES = {
     'fc_3000_512_b64': dict(N=64, H=1, W=1, C=3000, Cout=512, R=1, S=1, f32=True),
     'fc_512_512_b100': dict(N=100, H=1, W=1, C=512, Cout=512, R=1, S=1, f32=True),
     'fc_1024_512_b33_ld': dict(N=33, H=1, W=1, C=1024, Cout=504, R=1, S=1, f32=True, ld=1088),
+    'fc_512_512_b300': dict(N=300, H=1, W=1, C=512, Cout=512, R=1, S=1, f32=True),
     'conv1x1_small_map': dict(N=2, H=3, W=5, C=64, Cout=128, R=1, S=1),
     'many_tiles': dict(N=64, H=22, W=22, C=64, Cout=64, R=3, S=3, stride=1, pad=1, residual=True),
     'pair_128': dict(N=300, H=11, W=11, C=128, Cout=128, R=3, S=3, stride=1, pad=1, residual=True),

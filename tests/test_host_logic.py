@@ -140,10 +140,10 @@ def test_stem_prepass_kernel_source_on_cpu_threads(tmp_path, is_u8, H, W, Hraw, 
 
 
 @pytest.mark.parametrize('M,C,Cout,wb,ws2', [(64, 3000, 512, 1, 1), (64, 512, 512, 0, 1), (3, 1024, 24, 1, 0),
-                                             (100, 512, 8, 1, 1), (33, 72, 24, 1, 1)])
+                                             (100, 512, 8, 1, 1), (33, 72, 24, 1, 1), (150, 64, 8, 1, 1)])
 def test_linear_small_kernel_source_on_cpu_threads(tmp_path, M, C, Cout, wb, ws2):
     """linear_small_kernel (fc heads, tdnn.py:89-101) from its CUDA source on CPU threads vs a float64 product of the
-    same bf16 operands: K split over warps, rows per lane 1/2/4, both outputs and their epilogues."""
+    same bf16 operands: K split over 16 warps, 1 / 2 rows per lane, row groups on grid.y, both outputs and epilogues."""
     exe = str(tmp_path / 'emul')
     subprocess.run(['g++', '-std=c++20', '-O2', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes', '-o', exe,
                     os.path.join(ROOT, 'tests', 'frontend_cpu_emul.cpp')], check=True)

@@ -84,7 +84,7 @@ for mlp in (4, 8):
     _lib.set_option('statpool_mlp', mlp)
     ms = t_ms(lambda: ops.stat_pool(xs, 1500))
     print('stat_pool loads in flight %d: %6.1f us' % (mlp, ms * 1e3))
-_lib.set_option('statpool_mlp', 8)
+_lib.set_option('statpool_mlp', 4)
 hraw = torch.empty((64, 75, 96, 96), dtype=torch.uint8).pin_memory()
 draw = torch.empty_like(hraw, device=dev)
 for _ in range(3):
