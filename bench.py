@@ -279,7 +279,7 @@ def run_ours(args, rank, world, local):
     trunk_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
     trunk_tflops = GFLOP_TRUNK_PER_UTT * B / trunk_ms          # GFLOP / ms == TFLOP/s
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r1_trunk_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r1m_trunk_traffic.json')
     if os.path.exists(tpath) and B == 64:          # dram bytes per launch from the committed ncu capture
         tj = json.load(open(tpath))
         traffic = tj['trunk_dram_bytes_per_step'] / tj['trunk_conv_launches']
@@ -287,7 +287,7 @@ def run_ours(args, rank, world, local):
                 'bound': 'tensor',
                 'achieved': trunk_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': trunk_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
-                'traffic_note': 'avg DRAM bytes per trunk launch (ncu dram__bytes_read+write, profiles/r1_step_traffic.txt)',
+                'traffic_note': 'avg DRAM bytes per trunk launch (ncu dram__bytes_read+write, profiles/r1m_step_traffic.txt)',
                 'peak_src': peaks['src'] + ' (sustained bf16 cuBLAS)', 'launches': 19,
                 'avg_launch_ms': trunk_ms / 19, 'flop_per_launch': GFLOP_TRUNK_PER_UTT * B * 1e9 / 19}
     # stem + audio, for the record
