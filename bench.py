@@ -34,6 +34,27 @@ GFLOP_AUDIO_PER_UTT = 2.550 + 0.0036
 METRIC = 'av_utterances_per_sec'
 UNIT = 'utt/s'
 
+_OUT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL: "NCCL version ..." at communicator
+    creation): keep a private copy of the real stdout for the result line and point fd 1 at stderr for everyone else."""
+    global _OUT_FD
+    if _OUT_FD is None:
+        sys.stdout.flush()
+        _OUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
 
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -152,7 +173,7 @@ def run_reference(args, rank):
                                        'train_fusion.py:386-410 (oracle/ port of the reference modules)' %
                                        (per_step, args.steps)},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, per_gpu_batch):
@@ -418,7 +439,7 @@ def run_ours(args, rank, world, local):
             'breakdown_ms': {'stem': stem_ms, 'trunk': trunk_ms, 'audio_frontend_tdnn': audio_ms},
             'hbm_kernels': hbm_kernels,
             'stem_tflops': GFLOP_STEM_PER_UTT * B / stem_ms}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -434,6 +455,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    claim_stdout()
     if args.impl == 'reference':
         run_reference(args, rank)
         return
