@@ -40,6 +40,8 @@ SIGNATURES = {
     'dl_cosine_score_trials': [_p, _i, _i, _p, _p, _i, _p, _p],
     'dl_score_fusion_trials': [_p, _i, _p, _i, _i, _p, _p, _i, _p, _p],
     'dl_gather_scores': [_p, _i, _p, _p, _i, _p, _p],
+    'dl_plda_transform': [_p, _i, _i, _p, _p, _i, _p, _p],
+    'dl_plda_llr_trials': [_p, _i, _i, _p, _p, _f, _p, _p, _i, _p, _p],
 }
 
 _lib = None

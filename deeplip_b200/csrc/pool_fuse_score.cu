@@ -4,6 +4,7 @@
 // used to combine partial results across warps.
 #include "dl_host.cuh"
 #include "dl_ptx.cuh"
+#include "plda_score.cuh"
 
 namespace dl {
 
@@ -509,4 +510,23 @@ extern "C" int dl_gather_scores(const float* S, int ld, const int32_t* rows, con
   DL_CHECK_ARG(S && rows && cols && scores && ld > 0, "gather_scores: bad argument");
   gather_scores_kernel<<<(n_trials + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, ld, rows, cols, n_trials, scores);
   return check_launch("gather_scores_kernel");
+}
+
+extern "C" int dl_plda_transform(const float* emb, int n_utt, int D, const float* M, const float* bias, int R, float* u,
+                                 void* stream) {
+  if (n_utt == 0) return DL_OK;
+  DL_CHECK_ARG(emb && M && bias && u && n_utt > 0 && D > 0, "plda_transform: bad argument");
+  DL_CHECK_ARG(R >= 1 && R <= kPldaMaxR, "plda_transform: 1 <= R <= %d relevant dimensions (got %d)", kPldaMaxR, R);
+  plda_transform_kernel<<<(n_utt + 7) / 8, 256, 0, (cudaStream_t)stream>>>(emb, n_utt, D, M, bias, R, u);
+  return check_launch("plda_transform_kernel");
+}
+
+extern "C" int dl_plda_llr_trials(const float* u, int n_utt, int R, const float* k1, const float* k2, float c0,
+                                  const int32_t* enrol, const int32_t* test, int n_trials, float* scores, void* stream) {
+  if (n_trials == 0) return DL_OK;
+  DL_CHECK_ARG(u && k1 && k2 && enrol && test && scores && n_utt > 0, "plda_llr: bad argument");
+  DL_CHECK_ARG(R >= 1 && R <= kPldaMaxR && n_trials > 0, "plda_llr: 1 <= R <= %d, n_trials >= 0", kPldaMaxR);
+  plda_llr_trials_kernel<<<(n_trials + 255) / 256, 256, 0, (cudaStream_t)stream>>>(u, n_utt, R, k1, k2, c0, enrol, test,
+                                                                                   n_trials, scores);
+  return check_launch("plda_llr_trials_kernel");
 }

@@ -151,3 +151,28 @@ def eer_cos_grid(exp_dir, trial_path='data/data_audio/trial_grid_2w.txt', root='
 def eer_cos_lomgrid(exp_dir, trial_path='data/data_audio/trial_lomgrid_2w.txt', root='exp', device='cuda'):
     """utils.py:251-266."""
     return _eer_cos_dir(exp_dir, 'test_em_lomgrid', trial_path, root, device)
+
+
+def eer_plda(trials, emb, classifier, device='cuda'):
+    """Per-trial body of eer_plda_grid / eer_plda_lomgrid (models/audio_models/utils.py:285-329), batched: PLDA
+    same/different log-likelihood ratios on the GPU (deeplip_b200.plda.Classifier), EER on the CPU."""
+    e = _dev(emb, device)
+    en = torch.from_numpy(trials.enrol_idx).to(e.device)
+    te = torch.from_numpy(trials.test_idx).to(e.device)
+    return eer_from_scores(trials.labels, classifier.score_trials(e, en, te).cpu().numpy())
+
+
+def eer_plda_grid(exp_dir, classifier, trial_path='data/trial/A_grid_trial_2w', root='exp', device='cuda'):
+    """eer_plda_grid(exp_dir) of the reference, with the fitted classifier passed in instead of joblib-loaded from
+    exp/plda.pkl (the third-party `plda` pickle cannot be read here); embeddings as the per-utterance .npy files of
+    exp/<exp_dir>/test_xv_grid (utils.py:316-317)."""
+    trials = TrialList.from_file(trial_path)
+    emb = load_embeddings(os.path.join(root, str(exp_dir), 'test_xv_grid'), trials.utts)
+    return eer_plda(trials, emb, classifier, device)
+
+
+def eer_plda_lomgrid(exp_dir, classifier, trial_path='data/trial/A_lomgrid_trial_2w', root='exp', device='cuda'):
+    """utils.py:285-305."""
+    trials = TrialList.from_file(trial_path)
+    emb = load_embeddings(os.path.join(root, str(exp_dir), 'test_xv_lomgrid'), trials.utts)
+    return eer_plda(trials, emb, classifier, device)

@@ -217,6 +217,21 @@ int dl_score_fusion_trials(const float* emb_a, int Da, const float* emb_v, int D
 int dl_gather_scores(const float* S, int ld, const int32_t* rows, const int32_t* cols, int n_trials,
                      float* scores, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * S5  PLDA trial scoring.  Replaces the per-trial body of eer_plda_grid / eer_plda_lomgrid
+ *     (models/audio_models/utils.py:285-329): `model.transform(em, 'D', 'U_model')` +
+ *     `model.calc_same_diff_log_likelihood_ratio(U_0, U_1)` of the third-party `plda` package.
+ *     dl_plda_transform: every utterance once, u[row, r] = bias[r] + sum_d emb[row, d] M[r, d]  (M: R x D f32, the
+ *       fitted PCA + A^-1 maps restricted to the R <= 32 relevant dimensions, folded by deeplip_b200/plda.py).
+ *     dl_plda_llr_trials: scores[t] = c0 + sum_r k1[r] (a_r + b_r)^2 - k2[r] (a_r^2 + b_r^2) with a = u[enrol[t]],
+ *       b = u[test[t]] (k1 = psi / (2 (2 psi + 1)), k2 = psi / (2 (psi + 1)), c0 = sum_r log(psi + 1) - log(2 psi + 1) / 2);
+ *       out-of-range indices give NaN, like dl_cosine_score_trials.
+ */
+int dl_plda_transform(const float* emb, int n_utt, int D, const float* M, const float* bias, int R, float* u,
+                      void* stream);
+int dl_plda_llr_trials(const float* u, int n_utt, int R, const float* k1, const float* k2, float c0,
+                       const int32_t* enrol, const int32_t* test, int n_trials, float* scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,9 @@
 //   usage: frontend_cpu_emul linear M C Cout ldx ldw with_bf16 with_scale2 in.bin out.bin     (linear_small.cuh)
 //   in.bin = x (M,ldx) u16 | w (Cout,ldw) u16 | scale, shift, slope, scale2, shift2 (Cout f32 each); f32_slope = 0.2
 //   out.bin = y (M,Cout) u16 | yf (M,Cout) f32
+//   usage: frontend_cpu_emul plda n_utt D R n_trials c0 in.bin out.bin - -                   (plda_score.cuh)
+//   in.bin = emb (n_utt,D) f32 | M (R,D) f32 | bias, k1, k2 (R f32 each) | enrol, test (n_trials i32 each)
+//   out.bin = u (n_utt,R) f32 | scores (n_trials) f32
 #include <algorithm>
 #include <barrier>
 #include <cmath>
@@ -79,6 +82,7 @@ alignas(16) float lin_part[16 * 4 * 64];
 #include "../deeplip_b200/csrc/frontend_gen2.cuh"
 #include "../deeplip_b200/csrc/stem_prepass.cuh"
 #include "../deeplip_b200/csrc/linear_small.cuh"
+#include "../deeplip_b200/csrc/plda_score.cuh"
 
 template <typename Fn>
 static void launch(int gx, int gy, Fn fn, int nthreads = 256) {
@@ -155,8 +159,31 @@ static int linear_main(char** a) {
   return 0;
 }
 
+static int plda_main(char** a) {
+  using namespace dl;
+  const int n_utt = atoi(a[2]), D = atoi(a[3]), R = atoi(a[4]), nt = atoi(a[5]);
+  const float c0 = (float)atof(a[6]);
+  std::vector<float> emb((size_t)n_utt * D), M((size_t)R * D), prm((size_t)3 * R), u((size_t)n_utt * R, -777.f), sc(nt, -777.f);
+  std::vector<int32_t> idx((size_t)2 * nt);
+  FILE* f = fopen(a[7], "rb");
+  if (!f || fread(emb.data(), 4, emb.size(), f) != emb.size() || fread(M.data(), 4, M.size(), f) != M.size() ||
+      fread(prm.data(), 4, prm.size(), f) != prm.size() || fread(idx.data(), 4, idx.size(), f) != idx.size()) return 3;
+  fclose(f);
+  const float *pe = emb.data(), *pm = M.data(), *pb = prm.data(), *k1 = prm.data() + R, *k2 = prm.data() + 2 * R;
+  float *pu = u.data(), *ps = sc.data();
+  const int32_t *en = idx.data(), *te = idx.data() + nt;
+  launch((n_utt + 7) / 8, 1, [&] { plda_transform_kernel(pe, n_utt, D, pm, pb, R, pu); });
+  launch((nt + 255) / 256, 1, [&] { plda_llr_trials_kernel(pu, n_utt, R, k1, k2, c0, en, te, nt, ps); });
+  f = fopen(a[8], "wb");
+  fwrite(u.data(), 4, u.size(), f);
+  fwrite(sc.data(), 4, sc.size(), f);
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   using namespace dl;
+  if (argc == 11 && !strcmp(argv[1], "plda")) return plda_main(argv);
   if (argc == 11 && !strcmp(argv[1], "linear")) return linear_main(argv);
   if (argc != 10) return 2;
   if (!strcmp(argv[1], "prepass")) return prepass_main(argv);

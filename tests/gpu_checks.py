@@ -629,6 +629,41 @@ def tcd_timit_ragged_case(durations=(3.0, 6.44, 10.0), seed=3):
     return out
 
 
+def plda_case(dim=512, n_spk=40, per=25, n_trials=20000, seed=0):
+    """PLDA trial scoring on a trial_grid-sized list against the oracle's per-trial loop
+    (a sample of it: the loop is the reference's 2 590-trials/s path) and its vectorised closed form."""
+    from deeplip_b200.plda import Classifier
+    from oracle import plda_ref
+    rng = np.random.default_rng(seed)
+    spk = np.repeat(np.arange(n_spk), per)
+    X = synth.structured_embeddings(spk.tolist(), dim=dim, seed=3).astype(np.float64)
+    test_spk = np.repeat(np.arange(100, 133), 30)
+    E = synth.structured_embeddings(test_spk.tolist(), dim=dim, seed=5).astype(np.float32)
+    en = rng.integers(0, len(E), n_trials).astype(np.int32)
+    te = rng.integers(0, len(E), n_trials).astype(np.int32)
+    clf = Classifier().fit_model(X, spk, 20)
+    got = clf.score_trials(torch.from_numpy(E).to(DEV), torch.from_numpy(en).to(DEV), torch.from_numpy(te).to(DEV))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy().astype(np.float64)
+    mo = plda_ref.fit(X, spk, 20)
+    ref = plda_ref.plda_scores_loop(mo, E, en[:500], te[:500])
+    scale = max(1.0, float(np.abs(ref).max()))
+    out = {'llr_abs': float(np.abs(got[:500] - ref).max()), 'scale': scale}
+    u = plda_ref.transform_D_to_U_model(mo, E)
+    psi = mo['psi'][mo['relevant']]
+    a, b = u[en], u[te]
+    full = (np.log(psi + 1) - 0.5 * np.log(2 * psi + 1) + 0.5 * psi * (a + b) ** 2 / (2 * psi + 1)
+            - 0.5 * psi * (a * a + b * b) / (psi + 1)).sum(1)
+    out['llr_abs_all'] = float(np.abs(got - full).max())
+    lab = (test_spk[en] == test_spk[te]).astype(int)
+    e_got, e_ref = scoring_ref.eer_from_scores(lab, got)[0], scoring_ref.eer_from_scores(lab, full)[0]
+    out['eer_abs'] = abs(float(e_got) - float(e_ref))
+    assert out['llr_abs'] < 2e-3 * scale and out['llr_abs_all'] < 2e-3 * scale and out['eer_abs'] < 5e-4, out
+    assert clf.score_trials(torch.from_numpy(E).to(DEV), torch.zeros(0, dtype=torch.int32, device=DEV),
+                            torch.zeros(0, dtype=torch.int32, device=DEV)).numel() == 0
+    return out
+
+
 def determinism_case(B=8, T=10, reps=25, seed=1):
     """Bitwise run-to-run determinism of the video path under back-to-back launches (no host sync in
     between).  Guards the smem hand-offs between generic-proxy readers and TMA refills: a missing proxy

@@ -57,6 +57,10 @@ def test_av_pipeline_and_ragged_batch():
     G.pipeline_case()
 
 
+def test_plda_trial_scoring_vs_oracle():
+    G.plda_case()
+
+
 def test_tcd_timit_shaped_ragged_long_utterances():
     G.tcd_timit_ragged_case()
 

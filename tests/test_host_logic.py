@@ -172,6 +172,62 @@ def test_linear_small_kernel_source_on_cpu_threads(tmp_path, M, C, Cout, wb, ws2
         assert (np.abs(y - v) / np.maximum(1, np.abs(v))).max() < 5e-3
 
 
+def _plda_fixture(dim=128, n_spk=30, per=20, n_trials=400):
+    from deeplip_b200 import synth
+    rng = np.random.default_rng(0)
+    spk = np.repeat(np.arange(n_spk), per)
+    X = synth.structured_embeddings(spk.tolist(), dim=dim, seed=3).astype(np.float64)
+    test_spk = np.repeat(np.arange(100, 112), 6)
+    E = synth.structured_embeddings(test_spk.tolist(), dim=dim, seed=5).astype(np.float32)
+    en = rng.integers(0, len(E), n_trials).astype(np.int32)
+    te = rng.integers(0, len(E), n_trials).astype(np.int32)
+    return X, spk, E, test_spk, en, te
+
+
+def test_plda_host_fit_and_kernel_source_against_oracle(tmp_path):
+    """PLDA: the product's fit (deeplip_b200/plda.py: exact-SVD PCA, folded affine map, closed-form
+    LLR constants) against the oracle's restatement of the `plda` package (general marginal likelihoods, per-trial
+    loop), and the two scoring kernels run from their CUDA source on CPU threads."""
+    from oracle import plda_ref, scoring_ref
+    from deeplip_b200.plda import Classifier
+    X, spk, E, test_spk, en, te = _plda_fixture()
+    mo = plda_ref.fit(X, spk, 20)
+    ref = plda_ref.plda_scores_loop(mo, E, en, te)
+    # oracle sanity: symmetric in its two arguments, targets score higher, EER is low on speaker-structured data
+    assert np.abs(ref - plda_ref.plda_scores_loop(mo, E, te, en)).max() < 1e-9
+    lab = (test_spk[en] == test_spk[te]).astype(int)
+    assert ref[lab == 1].mean() > ref[lab == 0].mean()
+    assert scoring_ref.eer_from_scores(lab, ref)[0] < 0.2
+    m = Classifier().fit_model(X, spk, 20).model
+    R, D = m['M'].shape
+    assert R == len(mo['relevant'])
+    u = E.astype(np.float64) @ m['M'].T + m['bias']
+    # U is defined up to a sign per dimension (eigenvector signs); the scores do not depend on it
+    assert np.abs(np.abs(u) - np.abs(plda_ref.transform_D_to_U_model(mo, E))).max() < 1e-8
+    a, b = u[en], u[te]
+    closed = m['c0'] + ((a + b) ** 2 * m['k1'] - (a * a + b * b) * m['k2']).sum(1)
+    assert np.abs(closed - ref).max() < 1e-9
+    # the kernels, from source
+    exe = str(tmp_path / 'emul')
+    subprocess.run(['g++', '-std=c++20', '-O2', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes', '-o', exe,
+                    os.path.join(ROOT, 'tests', 'frontend_cpu_emul.cpp')], check=True)
+    en2, te2 = en.copy(), te.copy()
+    en2[7] = len(E)                                     # out-of-range index -> NaN score
+    with open(tmp_path / 'in.bin', 'wb') as f:
+        for arr in (E, m['M'], m['bias'], m['k1'], m['k2']):
+            f.write(np.ascontiguousarray(arr, dtype=np.float32).tobytes())
+        f.write(en2.tobytes())
+        f.write(te2.tobytes())
+    subprocess.run([exe, 'plda', str(len(E)), str(D), str(R), str(len(en)), repr(m['c0']), str(tmp_path / 'in.bin'),
+                    str(tmp_path / 'out.bin'), '-', '-'], check=True)
+    raw = np.fromfile(str(tmp_path / 'out.bin'), np.float32)
+    ug, sg = raw[:len(E) * R].reshape(len(E), R), raw[len(E) * R:]
+    assert np.abs(ug - u).max() < 1e-3 * max(1.0, np.abs(u).max())
+    assert np.isnan(sg[7])
+    ok = np.arange(len(en)) != 7
+    assert np.abs(sg[ok] - ref[ok]).max() < 2e-3 * max(1.0, np.abs(ref).max())
+
+
 def test_trial_list_parsing_matches_oracle(tmp_path):
     from deeplip_b200.trials import TrialList
     from oracle import scoring_ref
