@@ -629,6 +629,32 @@ def tcd_timit_ragged_case(durations=(3.0, 6.44, 10.0), seed=3):
     return out
 
 
+def full_size_batch_invariance_case(B=256, sub=64, seed=11):
+    """BASELINE configs[2] size (batch 256 of GRID-shaped utterances: 75 x 96x96 u8 crops + 3 s of audio) through a
+    size-independent property: every utterance's fused embedding in the batch of 256 is bit-identical to the one it
+    gets in a batch of 64 (same kernels, same per-element summation order, no cross-utterance arithmetic), and two
+    runs of the full batch are bit-identical."""
+    import bench
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    audio, video = build_models(DEV, seed=1)
+    ex = AVExtractor(audio, video)
+    raws, wavs = [], []
+    for k in range(B // sub):
+        r, w = bench.synth_batch(sub, seed=seed + k)
+        raws.append(torch.from_numpy(r))
+        wavs.append(torch.from_numpy(w))
+    raw, wav = torch.cat(raws).to(DEV), torch.cat(wavs).to(DEV)
+    big = ex.extract(wav, raw).clone()
+    again = ex.extract(wav, raw).clone()
+    parts = torch.cat([ex.extract(wav[i:i + sub].contiguous(), raw[i:i + sub].contiguous()).clone()
+                       for i in range(0, B, sub)])
+    torch.cuda.synchronize()
+    out = {'rerun_equal': bool(torch.equal(big, again)), 'sub_batches_equal': bool(torch.equal(big, parts)),
+           'finite': bool(torch.isfinite(big).all()), 'max_abs_diff': float((big - parts).abs().max())}
+    assert out['rerun_equal'] and out['finite'] and out['max_abs_diff'] < 1e-5, out
+    return out
+
+
 def plda_case(dim=512, n_spk=40, per=25, n_trials=20000, seed=0):
     """PLDA trial scoring on a trial_grid-sized list against the oracle's per-trial loop
     (a sample of it: the loop is the reference's 2 590-trials/s path) and its vectorised closed form."""

@@ -57,6 +57,10 @@ def test_av_pipeline_and_ragged_batch():
     G.pipeline_case()
 
 
+def test_full_size_batch_256_is_batch_invariant():
+    G.full_size_batch_invariance_case()
+
+
 def test_plda_trial_scoring_vs_oracle():
     G.plda_case()
 
