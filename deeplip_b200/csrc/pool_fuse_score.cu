@@ -16,15 +16,19 @@ struct Welford8 {
   float mean[8], m2[8];
 };
 
-template <bool kAttn, int kMlp>
+template <bool kAttn, int kMlp, int kSlab>
 __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restrict__ x, const float* __restrict__ logits,
                                                         int T, int C, int ldx, const int32_t* __restrict__ lengths,
                                                         float* __restrict__ out_f32, uint16_t* __restrict__ out_bf16,
                                                         int ld_out) {
-  extern __shared__ float sm[];   // kAttn: alpha[T] ; then 8 warps x 256 ch x 2 partials
+  // kSlab channels per block (256: a warp per time step, 8 "virtual warps" stride over time; 128: a half warp per
+  // time step, 16 virtual warps -- twice the blocks for the same bytes, better balance over 148 SMs)
+  constexpr int kVW = 8 * (256 / kSlab), kLanes = kSlab / 8;
+  extern __shared__ float sm[];   // kAttn: alpha[T] ; then kVW virtual warps x kSlab ch x 2 partials
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int vw = threadIdx.x / kLanes, vl = threadIdx.x % kLanes;
+  const int c0 = blockIdx.x * kSlab + vl * 8;
   int len = lengths ? lengths[b] : T;
   len = max(1, min(len, T));
   const uint16_t* xb = x + (size_t)b * T * ldx;
@@ -66,16 +70,16 @@ __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restri
   if (c0 < C) {
     // kMlp time steps (independent 16-byte loads) in flight per lane: the kernel is pure streaming (same accumulation
     // order for every kMlp)
-    for (int tb = warp; tb < len; tb += 8 * kMlp) {
+    for (int tb = vw; tb < len; tb += kVW * kMlp) {
       uint4 v4[kMlp];
 #pragma unroll
       for (int u = 0; u < kMlp; ++u) {
-        const int t = tb + 8 * u;
+        const int t = tb + kVW * u;
         if (t < len) v4[u] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * ldx + c0));
       }
 #pragma unroll
       for (int u = 0; u < kMlp; ++u) {
-        const int t = tb + 8 * u;
+        const int t = tb + kVW * u;
         if (t >= len) break;
         const uint4 v = v4[u];
         float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
@@ -97,29 +101,29 @@ __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restri
       }
     }
   }
-  // combine the 8 warps
-  float* p0 = part + (warp * 256 + lane * 8) * 2;
+  // combine the virtual warps
+  float* p0 = part + (vw * kSlab + vl * 8) * 2;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { p0[2 * i] = a0[i]; p0[2 * i + 1] = a1[i]; }
-  __shared__ int cnt[8];
-  if (lane == 0) cnt[warp] = n;
+  __shared__ int cnt[kVW];
+  if (vl == 0) cnt[vw] = n;
   __syncthreads();
-  const int cl = threadIdx.x;          // one thread per channel of this block's 256
-  const int c = blockIdx.x * 256 + cl;
-  if (c < C) {
+  const int cl = threadIdx.x;          // one thread per channel of this block's slab
+  const int c = blockIdx.x * kSlab + cl;
+  if (cl < kSlab && c < C) {
     float mean, sd;
     if (kAttn) {
       float s1 = 0.f, s2 = 0.f;
-      for (int w = 0; w < 8; ++w) { s1 += part[(w * 256 + cl) * 2]; s2 += part[(w * 256 + cl) * 2 + 1]; }
+      for (int w = 0; w < kVW; ++w) { s1 += part[(w * kSlab + cl) * 2]; s2 += part[(w * kSlab + cl) * 2 + 1]; }
       mean = s1;
       sd = sqrtf(s2 - s1 * s1);        // no clamp, like the reference (pooling.py:105)
     } else {
       float m = 0.f, m2 = 0.f;
       int nn = 0;
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < kVW; ++w) {
         const int nw = cnt[w];
         if (nw == 0) continue;
-        const float mw = part[(w * 256 + cl) * 2], m2w = part[(w * 256 + cl) * 2 + 1];
+        const float mw = part[(w * kSlab + cl) * 2], m2w = part[(w * kSlab + cl) * 2 + 1];
         const int nt = nn + nw;
         const float d = mw - m;
         m += d * ((float)nw / (float)nt);
@@ -156,6 +160,9 @@ __global__ void attn_logits_kernel(const float* __restrict__ hf, int rows, int H
 // ------------------------------------------------------------------------------------------------
 // Per-frame spatial mean, then mean over the valid frames of each utterance.  Block = (utterance, 64-channel
 // slab): 8 channel-threads (8 channels = 16 B each) x 32 frame groups; deterministic smem reduction.
+// kHW > 0: the map size is known at compile time and all its loads are issued before the first add (a 3x3 map is nine
+// independent 16-byte loads in flight per thread instead of one); kHW = 0: any HW.  Same summation order either way.
+template <int kHW>
 __global__ void __launch_bounds__(256) frame_pool_kernel(const uint16_t* __restrict__ x, int T, int HW, int C,
                                                          const int32_t* __restrict__ lengths,
                                                          float* __restrict__ frame_feats,
@@ -175,10 +182,22 @@ __global__ void __launch_bounds__(256) frame_pool_kernel(const uint16_t* __restr
     for (int t = g; t < T; t += 32) {
       const uint16_t* xf = x + ((size_t)(b * T + t) * HW) * C + c;
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int px = 0; px < HW; ++px) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(xf + (size_t)px * C));
-        f[0] += bf16_lo(v.x); f[1] += bf16_hi(v.x); f[2] += bf16_lo(v.y); f[3] += bf16_hi(v.y);
-        f[4] += bf16_lo(v.z); f[5] += bf16_hi(v.z); f[6] += bf16_lo(v.w); f[7] += bf16_hi(v.w);
+      if (kHW > 0) {
+        uint4 vv[kHW > 0 ? kHW : 1];
+#pragma unroll
+        for (int px = 0; px < kHW; ++px) vv[px] = __ldg(reinterpret_cast<const uint4*>(xf + (size_t)px * C));
+#pragma unroll
+        for (int px = 0; px < kHW; ++px) {
+          const uint4 v = vv[px];
+          f[0] += bf16_lo(v.x); f[1] += bf16_hi(v.x); f[2] += bf16_lo(v.y); f[3] += bf16_hi(v.y);
+          f[4] += bf16_lo(v.z); f[5] += bf16_hi(v.z); f[6] += bf16_lo(v.w); f[7] += bf16_hi(v.w);
+        }
+      } else {
+        for (int px = 0; px < HW; ++px) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(xf + (size_t)px * C));
+          f[0] += bf16_lo(v.x); f[1] += bf16_hi(v.x); f[2] += bf16_lo(v.y); f[3] += bf16_hi(v.y);
+          f[4] += bf16_lo(v.z); f[5] += bf16_hi(v.z); f[6] += bf16_lo(v.w); f[7] += bf16_hi(v.w);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] *= inv_hw;
@@ -399,13 +418,18 @@ extern "C" int dl_stat_pool(const void* x, int B, int T, int C, int ldx, const i
   DL_CHECK_ARG(B > 0 && T > 0 && C > 0 && ldx % 8 == 0 && ldx >= C, "stat_pool: bad shape B=%d T=%d C=%d ldx=%d", B,
                T, C, ldx);
   DL_CHECK_ARG(!out_bf16 || ld_out >= 2 * C, "stat_pool: ld_out < 2C");
-  dim3 grid((C + 255) / 256, B);
   const size_t smem = 8 * 256 * 2 * sizeof(float);
+  if (opt_statpool_slab() == 128) {
+    stat_pool_kernel<false, 4, 128><<<dim3((C + 127) / 128, B), 256, smem, (cudaStream_t)stream>>>(
+        (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
+    return check_launch("stat_pool_kernel");
+  }
+  dim3 grid((C + 255) / 256, B);
   if (opt_statpool_mlp() == 4)
-    stat_pool_kernel<false, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(
+    stat_pool_kernel<false, 4, 256><<<grid, 256, smem, (cudaStream_t)stream>>>(
         (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
   else
-    stat_pool_kernel<false, 8><<<grid, 256, smem, (cudaStream_t)stream>>>(
+    stat_pool_kernel<false, 8, 256><<<grid, 256, smem, (cudaStream_t)stream>>>(
         (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
   return check_launch("stat_pool_kernel");
 }
@@ -418,10 +442,10 @@ extern "C" int dl_attn_stat_pool(const void* x, const float* logits, int B, int 
   dim3 grid((C + 255) / 256, B);
   const size_t smem = (8 * 256 * 2 + T) * sizeof(float);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(stat_pool_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(stat_pool_kernel<true, 4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "attn_stat_pool smem: %s", cudaGetErrorString(e));
   }
-  stat_pool_kernel<true, 4><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  stat_pool_kernel<true, 4, 256><<<grid, 256, smem, (cudaStream_t)stream>>>(
       (const uint16_t*)x, logits, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
   return check_launch("attn_stat_pool_kernel");
 }
@@ -438,8 +462,12 @@ extern "C" int dl_frame_pool_temporal_mean(const void* x, int B, int T, int HW, 
   DL_CHECK_ARG(x && (frame_feats || utt_mean), "frame_pool: null pointer");
   DL_CHECK_ARG(B > 0 && T > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 2048, "frame_pool: bad shape");
   dim3 grid(B, (C + 63) / 64);
-  frame_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, T, HW, C, lengths, frame_feats,
-                                                            utt_mean);
+  if (HW == 9)         // the 3x3 maps ResNet-18 leaves of an 88x88 crop
+    frame_pool_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, T, HW, C, lengths, frame_feats,
+                                                                 utt_mean);
+  else
+    frame_pool_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, T, HW, C, lengths, frame_feats,
+                                                                 utt_mean);
   return check_launch("frame_pool_kernel");
 }
 

@@ -273,7 +273,7 @@ def frame_pool_case(B=3, T=7, HW=9, C=512, seed=0):
     g = torch.Generator().manual_seed(seed)
     x = bf16r(torch.randn(B * T, HW, C, generator=g))
     lengths = [T, max(1, T - 2), max(1, T // 2)][:B]
-    ff, um = ops.frame_pool_temporal_mean(x.view(B * T, 3, 3, C).to(DEV).to(torch.bfloat16), B, T,
+    ff, um = ops.frame_pool_temporal_mean(x.view(B * T, HW, 1, C).to(DEV).to(torch.bfloat16), B, T,
                                           lengths=torch.tensor(lengths, dtype=torch.int32, device=DEV))
     torch.cuda.synchronize()
     ref_f = x.mean(dim=1).view(B, T, C)

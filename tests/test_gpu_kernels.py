@@ -56,8 +56,9 @@ def test_stem(kw):
     G.stem_case(**kw)
 
 
-def test_stat_pool():
-    G.stat_pool_case()
+@pytest.mark.parametrize('kw', [dict(), dict(B=2, T=50, C=512, lengths=[50, 7]), dict(B=1, T=3, C=24)])
+def test_stat_pool(kw):
+    G.stat_pool_case(**kw)
     G.stat_pool_case(B=3, T=100, C=520, lengths=[100, 37, 2])
     G.stat_pool_case(B=1, T=2, C=8)
 
@@ -66,8 +67,9 @@ def test_attn_stat_pool():
     G.attn_pool_case()
 
 
-def test_frame_pool_temporal_mean():
-    G.frame_pool_case()
+@pytest.mark.parametrize('kw', [dict(), dict(HW=4, C=128), dict(B=2, T=40, HW=36, C=64)])
+def test_frame_pool_temporal_mean(kw):
+    G.frame_pool_case(**kw)
     G.frame_pool_case(B=1, T=1)
 
 
