@@ -170,7 +170,7 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 
 namespace dl {
 static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1}, g_opt_dbg{0}, g_opt_tap_share{1}, g_opt_frontend{2},
-    g_opt_stft_pad{0}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{128};
+    g_opt_stft_pad{0}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{256};
 int opt_pair() { return g_opt_pair.load(std::memory_order_relaxed); }
 int opt_pair_resident() { return g_opt_pair_resident.load(std::memory_order_relaxed); }
 int opt_tap_share() { return g_opt_tap_share.load(std::memory_order_relaxed); }

@@ -19,7 +19,7 @@ int opt_frontend();        // 2 = register-resident radix-8 FFT front end (defau
 int opt_prepass();         // 2 = one block per frame, aligned word loads (default), 1 = first-generation stem pre-pass
 int opt_small_linear();    // 1 = fc layers (P Q == 1, <= 4096 rows) run on linear_small_kernel (default), 0 = igemm
 int opt_statpool_mlp();    // stat pool: 16-byte loads in flight per lane, 4 (default; measured faster) or 8
-int opt_statpool_slab();   // stat pool: channels per block, 128 (default: half a warp per time step) or 256
+int opt_statpool_slab();   // stat pool: channels per block, 256 (default) or 128 (half a warp per time step; measured slower)
 int opt_stft_pad();        // stft centre padding: 0 reflect (librosa < 0.10), 1 zeros (librosa >= 0.10)
 int opt_tap_share();     // pair kernel shares one operand-A box across horizontal taps (guarded-linear mode)
 int opt_pair_resident();   // resident weight-half variant of the pair kernel on / off                          // DL_OK or DL_ERR_UNSUPPORTED

@@ -89,7 +89,7 @@ for slab in (256, 128):
     _lib.set_option('statpool_slab', slab)
     ms = t_ms(lambda: ops.stat_pool(xs, 1500))
     print('stat_pool slab %d: %6.1f us  %7.1f GB/s' % (slab, ms * 1e3, 64 * 1504 * 277 * 2 / ms / 1e6))
-_lib.set_option('statpool_slab', 128)
+_lib.set_option('statpool_slab', 256)
 hraw = torch.empty((64, 75, 96, 96), dtype=torch.uint8).pin_memory()
 draw = torch.empty_like(hraw, device=dev)
 for _ in range(3):
