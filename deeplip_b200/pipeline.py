@@ -118,15 +118,21 @@ class HostPipeline:
         self._free = [torch.cuda.Event() for _ in range(slots)]
         self._out_pool = None       # pinned output rows, grown on demand and kept: cudaHostAlloc costs tens of ms
 
-    def _upload(self, k, wav_h, vid_h):
+    def _upload(self, k, wav_h, vid_h, wav_len_h=None, vid_len_h=None):
         slot = k % self.slots
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._free[slot])          # kernels that read this slot are done
             st = self._stage[slot]
             if st is None or st[0].shape != wav_h.shape or st[1].shape != vid_h.shape or st[1].dtype != vid_h.dtype:
-                st = (torch.empty(wav_h.shape, dtype=wav_h.dtype, device=self.device),
-                      torch.empty(vid_h.shape, dtype=vid_h.dtype, device=self.device))
+                st = [torch.empty(wav_h.shape, dtype=wav_h.dtype, device=self.device),
+                      torch.empty(vid_h.shape, dtype=vid_h.dtype, device=self.device),
+                      torch.empty((wav_h.shape[0],), dtype=torch.int32, device=self.device),
+                      torch.empty((wav_h.shape[0],), dtype=torch.int32, device=self.device), False]
                 self._stage[slot] = st
+            st[4] = wav_len_h is not None
+            if st[4]:                                              # ragged batch: the two length vectors ride along
+                st[2].copy_(wav_len_h, non_blocking=True)
+                st[3].copy_(vid_len_h, non_blocking=True)
             st[0].copy_(wav_h, non_blocking=True)
             self._ready_wav[slot].record(self.copy_stream)         # the audio branch starts while the crops still upload
             st[1].copy_(vid_h, non_blocking=True)
@@ -134,10 +140,15 @@ class HostPipeline:
 
     @torch.no_grad()
     def run(self, batches, post=None):
-        """batches: sequence of (wav_host (B,nsamp) f32 pinned, video_host (B,T,H,W) u8/f32 pinned).
-        Returns the list of fused embeddings as pinned host tensors (valid after the final synchronize,
-        which this method performs, and until the next run(): they are views of one pinned pool this object keeps)."""
+        """batches: sequence of (wav_host (B,nsamp) f32 pinned, video_host (B,T,H,W) u8/f32 pinned) or, for ragged
+        batches (zero-padded tails, pad_packed_collate convention), (wav, video, wav_lengths, video_lengths) with the
+        lengths as pinned int32 host vectors.  Returns the list of fused embeddings as pinned host tensors (valid after
+        the final synchronize, which this method performs, and until the next run(): they are views of one pinned pool
+        this object keeps)."""
         batches = list(batches)
+        for bt in batches:
+            if len(bt) not in (2, 4):
+                raise ValueError('HostPipeline batches are (wav, video) or (wav, video, wav_lengths, video_lengths)')
         main = torch.cuda.current_stream(self.device)
         for ev in self._free:
             ev.record(main)
@@ -149,15 +160,17 @@ class HostPipeline:
             slot = k % self.slots
             if k + 1 < len(batches):
                 self._upload(k + 1, *batches[k + 1])
-            wav_d, vid_d = self._stage[slot]
+            wav_d, vid_d, wl_d, vl_d, ragged = self._stage[slot]
+            if not ragged:
+                wl_d = vl_d = None
             if self.ex.fusion in ('audio', 'video'):
                 main.wait_event(self._ready[slot])
-                emb = self.ex.extract(wav_d, vid_d)
+                emb = self.ex.extract(wav_d, vid_d, wl_d, vl_d)
             else:                  # same arithmetic as AVExtractor.extract, split at the two upload events
                 main.wait_event(self._ready_wav[slot])
-                xv = self.ex.audio_embedding(wav_d)
+                xv = self.ex.audio_embedding(wav_d, wl_d)
                 main.wait_event(self._ready[slot])
-                emb = self.ex.fuse(xv, self.ex.video_embedding(vid_d))
+                emb = self.ex.fuse(xv, self.ex.video_embedding(vid_d, vl_d))
             self._free[slot].record(main)
             if post is not None:
                 emb = post(emb)

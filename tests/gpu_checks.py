@@ -584,6 +584,13 @@ def pipeline_case(B=4, T=8, nsamp=24000, seed=1):
     outs = HostPipeline(ex, DEV).run([(hw, hv), (hw, hv), (hw, hv)])
     out['host_pipeline_abs'] = max(float((o.to(DEV) - got).abs().max()) for o in outs)
     assert out['host_pipeline_abs'] == 0.0, out
+    # ... and with lengths riding along (ragged batch from the host), alternating with a dense batch
+    hw2, hv2 = torch.from_numpy(wav2).pin_memory(), raw_f.pin_memory()
+    outs = HostPipeline(ex, DEV).run([(hw2, hv2, wl.cpu().pin_memory(), vl.cpu().pin_memory()), (hw, hv),
+                                      (hw2, hv2, wl.cpu().pin_memory(), vl.cpu().pin_memory())])
+    out['host_pipeline_ragged_abs'] = max(float((outs[0].to(DEV) - rag).abs().max()), float((outs[2].to(DEV) - rag).abs().max()),
+                                          float((outs[1].to(DEV) - got).abs().max()))
+    assert out['host_pipeline_ragged_abs'] == 0.0, out
     assert out['emb_cos_min'] > 0.999 and out['score_abs'] < 1e-3 and out['ragged_abs'] < 1e-5, out
     return out
 
