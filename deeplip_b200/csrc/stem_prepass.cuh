@@ -36,28 +36,17 @@ __global__ void __launch_bounds__(256) stem_prepass2_kernel(const void* __restri
         if (aligned4) {
           const int wb = c0 & ~3, sh = 8 * (c0 - wb);
           uint32_t w[3];
-          if (wb >= 0 && wb + 12 <= Wraw) {             // the three words lie inside the raw row (the usual case)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) w[q] = __ldg(reinterpret_cast<const uint32_t*>(src + wb) + q);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const int wc = wb + 4 * q;
-              w[q] = (wc >= 0 && wc < Wraw) ? __ldg(reinterpret_cast<const uint32_t*>(src + wc)) : 0u;
-            }
+          for (int q = 0; q < 3; ++q) {
+            const int wc = wb + 4 * q;
+            w[q] = (wc >= 0 && wc < Wraw) ? __ldg(reinterpret_cast<const uint32_t*>(src + wc)) : 0u;
           }
           const uint32_t lo = __funnelshift_r(w[0], w[1], sh), hi = __funnelshift_r(w[1], w[2], sh);
-          if (ix0 >= 0 && ix0 + 8 <= W) {               // interior group: no per-element bounds
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[j] = fmaf((float)(((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu), u8_scale, u8_bias);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t u = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu;
-              const int ix = ix0 + j;
-              if (ix >= 0 && ix < W) v[j] = fmaf((float)u, u8_scale, u8_bias);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t u = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu;
+            const int ix = ix0 + j;
+            if (ix >= 0 && ix < W) v[j] = fmaf((float)u, u8_scale, u8_bias);
           }
         } else {
 #pragma unroll
