@@ -19,6 +19,11 @@ USE_HALO = os.environ.get('DL_USE_HALO', '1') != '0'
 # horizontal taps.  Off by default: since the tensor-issue fix it runs level with the im2col kernel
 # (4.13 vs 4.12 ms per step) while doing 19 % more MMAs.
 USE_GUARDED = os.environ.get('DL_USE_GUARDED', '0') != '0'
+# layer2's entry block: its 3x3 stride-2 conv and its 1x1 stride-2 downsample conv read the same pixels (the 1x1 window
+# is the centre tap of the 3x3 one), so they run as ONE 64 -> 256 conv (channels [0,128) conv1, [128,256) the skip with
+# zero weights off the centre tap): the 297 MB layer1 map is read once instead of twice and the tiles are 256 wide.
+# Bit-identical results (the extra products are exact zeros).
+FUSE_L2_ENTRY = os.environ.get('DL_FUSE_L2_ENTRY', '1') != '0'
 
 
 def conv3x3(in_planes, out_planes, stride=1):
@@ -76,6 +81,16 @@ class BasicBlock(nn.Module):
                 pk['sd'], pk['hd'] = packing.fold_bn(dbn.weight.detach(), dbn.bias.detach(), dbn.running_mean,
                                                      dbn.running_var, eps=dbn.eps)
                 pk['ad'] = torch.ones(self.planes, device=dev)       # identity activation on the skip
+                if self.stride == 2 and self.inplanes % 64 == 0:
+                    # conv1 and the skip as one conv of 2 x planes outputs: the skip's weights sit on the centre tap
+                    kb = (self.inplanes + 63) // 64 * 64
+                    wf = torch.zeros((2 * self.planes, 9 * kb), device=dev, dtype=pk['w1'].dtype)
+                    wf[:self.planes] = pk['w1']
+                    wf[self.planes:, 4 * kb:5 * kb] = pk['wd']
+                    pk['wf'] = wf.contiguous()
+                    pk['sf'] = torch.cat([pk['s1'], pk['sd']]).contiguous()
+                    pk['hf'] = torch.cat([pk['h1'], pk['hd']]).contiguous()
+                    pk['af'] = torch.cat([pk['a1'], pk['ad']]).contiguous()
             self._pk = pk
         return self._pk
 
@@ -111,6 +126,27 @@ class BasicBlock(nn.Module):
             res = x
         ops.conv_igemm_lin(mid, pk['w2'], self.planes, self.planes, (P, Q), 3, 3, (1, 1), (1, 1),
                            pk['s2'], pk['h2'], pk['a2'], residual=res, out=out)
+        return out
+
+    def forward_fused_entry(self, x, H, W, out):
+        """Entry block with conv1 and the skip as one conv (see FUSE_L2_ENTRY).  x: (N, img_rows >= H, W, inplanes);
+        out: caller-owned (N, P, Q, 2 planes) buffer; returns it with the block output in channels [0, planes)."""
+        pk = self._packed()
+        both, _ = ops.conv_igemm(x, pk['wf'], self.inplanes, 2 * self.planes, 3, 3, (2, 2), (1, 1), (1, 1),
+                                 pk['sf'], pk['hf'], pk['af'], H=H, W=W)             # [conv1 | skip], pitch 2 planes
+        ops.conv_igemm(both, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1), pk['s2'], pk['h2'],
+                       pk['a2'], residual=both, residual_channel_offset=self.planes, out=out)
+        return out
+
+    def forward_pitched(self, x, out):
+        """Identity-skip block on activations that live in the first `planes` channels of wider buffers (x, out:
+        (N, P, Q, ld >= planes), the pitch the fused entry block leaves behind)."""
+        pk = self._packed()
+        assert self.downsample is None and self.stride == 1 and x.shape == out.shape
+        mid, _ = ops.conv_igemm(x, pk['w1'], self.inplanes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1),
+                                pk['s1'], pk['h1'], pk['a1'])
+        ops.conv_igemm(mid, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1), pk['s2'], pk['h2'],
+                       pk['a2'], residual=x, out=out)
         return out
 
     def forward_nhwc(self, x, H=None, W=None):
@@ -199,6 +235,20 @@ class ResNet(nn.Module):
                 l2[0].downsample is not None and all(b.downsample is None and b.stride == 1 for b in list(l2)[1:]) and
                 l3[0].downsample is not None)
 
+    def fused_entry_enabled(self):
+        l2 = self.layer2
+        return (FUSE_L2_ENTRY and l2[0].downsample is not None and l2[0].stride == 2 and l2[0].inplanes % 64 == 0 and
+                all(b.downsample is None and b.stride == 1 for b in list(l2)[1:]) and
+                self.layer3[0].downsample is not None)
+
+    def pitched_buffers(self, N, P, Q, ld, device):
+        """Two persistent (N, P, Q, ld) activation buffers (only the first ld/2 channels carry block outputs)."""
+        key = (N, P, Q, ld, str(device))
+        if getattr(self, '_pit_key', None) != key:
+            self._pit = [torch.zeros((N, P, Q, ld), device=device, dtype=torch.bfloat16) for _ in range(2)]
+            self._pit_key = key
+        return self._pit
+
     def guarded_buffers(self, N, P, Q, device):
         """Persistent zeroed (N, P+1, Q+1, 128) buffers; the kernels never write the guard row / column."""
         key = (N, P, Q, str(device))
@@ -238,6 +288,13 @@ class ResNet(nn.Module):
                     x = blk.forward_guarded(x, P, Q, (free[0], None, free[1]), x_guarded=True)
                 x = self.layer3[0].forward_nhwc(x, H=P, W=Q)
                 rest = list(self.layer3)[1:]
+            elif self.fused_entry_enabled():
+                a, b = self.pitched_buffers(N, P, Q, 2 * self.layer2[0].planes, x.device)
+                x = self.layer2[0].forward_fused_entry(x, H, W, a)
+                for blk in list(self.layer2)[1:]:
+                    a, b = b, a
+                    x = blk.forward_pitched(x, a)
+                rest = list(self.layer3)             # layer3's entry convs read 128 of the 256-channel pitch
             else:
                 x = self.layer2[0].forward_nhwc(x, H=H)
                 rest = list(self.layer2)[1:] + list(self.layer3)

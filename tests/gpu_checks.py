@@ -390,6 +390,35 @@ def video_model_case(B=2, T=6, seed=1, u8=True, speakers=None):
     return out
 
 
+def video_fused_entry_case(B=3, T=40, seed=4):
+    """layer2's entry block with conv1 and the 1x1 skip as ONE 64 -> 256 conv (skip weights on the centre tap) must
+    equal the two separate convs bit for bit, small batch (single-CTA igemm) and pair-kernel sized alike."""
+    from deeplip_b200.video_models import resnet as R
+    from deeplip_b200.video_models.model import Lipreading
+    sd = synth.make_video_state_dict(seed=seed, randomize=True)
+    m = Lipreading(relu_type='prelu', backbone_type='resnet', extract_feats=True, tcn_options=synth.TCN_OPTIONS)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    saved = R.FUSE_L2_ENTRY
+    out = {}
+    with torch.no_grad():
+        try:
+            for name, (b, t) in (('small', (1, 3)), ('large', (B, T))):
+                raw = torch.from_numpy(synth.lip_crops_u8(list(range(b)), T=t, seed=seed)).to(DEV)
+                R.FUSE_L2_ENTRY = True
+                assert m.trunk.fused_entry_enabled()
+                fused = m.trunk_maps(raw).clone()
+                R.FUSE_L2_ENTRY = False
+                plain = m.trunk_maps(raw).clone()
+                torch.cuda.synchronize()
+                out[name + '_equal'] = bool(torch.equal(fused, plain))
+                out[name + '_abs'] = float((fused.float() - plain.float()).abs().max())
+        finally:
+            R.FUSE_L2_ENTRY = saved
+    assert out['small_equal'] and out['large_equal'], out
+    return out
+
+
 def video_guarded_case(B=4, T=30, seed=2, reps=8):
     """layer2 on the guarded layout (tap-sharing CTA-pair kernel) vs the dense im2col path and the fp32 oracle;
     needs >= 114 frames for the guarded path to be taken."""

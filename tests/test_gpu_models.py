@@ -17,6 +17,10 @@ def test_video_model_vs_oracle():
     G.video_model_case()
 
 
+def test_video_fused_layer2_entry_is_bit_identical():
+    G.video_fused_entry_case()
+
+
 def test_video_guarded_layer2_path():
     G.video_guarded_case()
 

@@ -101,3 +101,10 @@ for _ in range(10):
     draw.copy_(hraw, non_blocking=True)
 b.record(); torch.cuda.synchronize()
 print('H2D pinned 44 MB: %.2f ms each = %.1f GB/s' % (a.elapsed_time(b) / 10, hraw.numel() * 10 / a.elapsed_time(b) / 1e6))
+
+from deeplip_b200.video_models import resnet as R
+for fuse in (False, True):
+    R.FUSE_L2_ENTRY = fuse
+    ms = t_ms(lambda: video.utterance_embedding(raw))
+    print('video branch B=64, layer2 entry fused=%d: %8.1f us' % (fuse, ms * 1e3))
+R.FUSE_L2_ENTRY = True
