@@ -107,6 +107,14 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int num_m_pairs = (p.num_m_blocks + 1) >> 1;
   const int total = num_m_pairs * p.num_n_blocks;
   const int num_kb = p.R * p.S * p.cchunks;
+  // centre-tap-only n blocks (p.skip_n0 >= 0) cost a ninth of the others: tiles then go n-block-major, so that every
+  // pair works through the expensive ones first and the cheap ones after instead of owning one kind (t = pair + i * pairs
+  // with an even pair count would give a pair one n block only)
+  const bool ctr_mode = !kResB && TAPS == 1 && p.skip_n0 >= 0;
+  auto tile_of = [&](int t, int& mp, int& n_blk) {
+    if (ctr_mode) { n_blk = t / num_m_pairs; mp = t - n_blk * num_m_pairs; }
+    else { mp = t / p.num_n_blocks; n_blk = t - mp * p.num_n_blocks; }
+  };
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -120,8 +128,8 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < total; t += num_pairs) {
-        const int mp = t / p.num_n_blocks;
-        const int n_blk = t - mp * p.num_n_blocks;
+        int mp, n_blk;
+        tile_of(t, mp, n_blk);
         const int m0 = (2 * mp + (int)rank) * 128;
         const int img = m0 / p.PQ;
         const int rem = m0 - img * p.PQ;
@@ -148,9 +156,12 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
           continue;
         }
-        int kb = 0;
-        for (int r = 0; r < p.R; ++r) {
-          for (int s = 0; s < p.S; ++s) {
+        const bool ctr = ctr_mode && n_blk >= p.skip_n0;
+        const int r_lo = ctr ? p.R >> 1 : 0, r_hi = ctr ? r_lo + 1 : p.R;
+        const int s_lo = ctr ? p.S >> 1 : 0, s_hi = ctr ? s_lo + 1 : p.S;
+        for (int r = r_lo; r < r_hi; ++r) {
+          for (int s = s_lo; s < s_hi; ++s) {
+            int kb = (r * p.S + s) * p.cchunks;
             for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
               mbar_wait(&empty[stage], phase ^ 1);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -198,8 +209,11 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             umma2_commit_both(&empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-        } else
-        for (int kb = 0; kb < num_kb; ++kb) {
+        } else {
+        int mp_, n_blk_;
+        tile_of(t, mp_, n_blk_);
+        const int nkb = (ctr_mode && n_blk_ >= p.skip_n0) ? p.cchunks : num_kb;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -209,6 +223,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           for (int k = 0; k < ((p.dbg & 8) ? 1 : 4); ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma2_commit_both(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
         }
         umma2_commit_both(&tfull[acc]);
         acc ^= 1;
@@ -223,8 +238,8 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < total; t += num_pairs) {
-      const int mp = t / p.num_n_blocks;
-      const int n_blk = t - mp * p.num_n_blocks;
+      int mp, n_blk;
+      tile_of(t, mp, n_blk);
       long long row = (long long)(2 * mp + (int)rank) * 128 + quarter * 32 + lane;
       const bool row_ok = igemm_map_row(p, row) && !(p.dbg & 2);
       const int cbase = n_blk * BLOCK_N;

@@ -29,6 +29,9 @@ struct IgemmParams {
   const uint16_t* residual;
   uint16_t* y;
   float* yf;
+  uint16_t* y2;        // split output: channels >= split_c go to y2[row * ldy + c - split_c] (split_c = 0: off)
+  int split_c;
+  int skip_n0;         // pair kernel: n blocks >= skip_n0 see the filter's centre tap only (-1: none)
 };
 
 // GEMM row -> row of y / residual, and whether it is stored at all.
@@ -69,6 +72,8 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const 
                                                     uint32_t tmem_acc, long long row, bool row_ok, int cbase,
                                                     int quarter, int chunk0, bool has_res, bool fast,
                                                     uint4 (&res)[4]) {
+  // split output (sibling convs in one launch): a tile lies on one side of the split (split_c % BLOCK_N == 0)
+  uint16_t* const ybase = (p.split_c > 0 && cbase >= p.split_c) ? p.y2 - p.split_c : p.y;
 #pragma unroll 1
   for (int j = chunk0; j < BLOCK_N / 32; j += 2) {
     const int c0 = cbase + j * 32;
@@ -119,7 +124,7 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const 
         o[g].z = pack_bf16x2(v[4], v[5]); o[g].w = pack_bf16x2(v[6], v[7]);
       }
       if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.y + row * p.ldy + c0);
+        uint4* dst = reinterpret_cast<uint4*>(ybase + row * p.ldy + c0);
 #pragma unroll
         for (int g = 0; g < 4; ++g) dst[g] = o[g];
       }
@@ -159,7 +164,7 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const 
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(p.y + row * p.ldy + c) = o;
+            *reinterpret_cast<uint4*>(ybase + row * p.ldy + c) = o;
           }
         }
       }

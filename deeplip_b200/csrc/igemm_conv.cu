@@ -242,7 +242,14 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   DL_CHECK_ARG(d->ldx % 8 == 0 && d->ldx >= d->C, "conv_igemm: ldx must be >= C and a multiple of 8");
   DL_CHECK_ARG(d->Cout % 8 == 0, "conv_igemm: Cout must be a multiple of 8 (pad the packed weights)");
   DL_CHECK_ARG(!y || d->Cout <= kMaxCout, "conv_igemm: the bf16 epilogue stages at most %d channels", kMaxCout);
-  DL_CHECK_ARG(!y || (d->ldy % 8 == 0 && d->ldy >= d->Cout), "conv_igemm: ldy must be >= Cout, multiple of 8");
+  const int split = d->split_channel;
+  if (split > 0) {
+    DL_CHECK_ARG(y && d->y_split && !residual && !y_f32 && !d->lin && d->out_img_rows == 0,
+                 "conv_igemm: split output needs y and y_split, no residual / f32 output / guarded layouts");
+    DL_CHECK_ARG(split % 256 == 0 && split < d->Cout && d->Cout > 128, "conv_igemm: split_channel must be a multiple of 256 below Cout");
+    DL_CHECK_ARG(d->ldy % 8 == 0 && d->ldy >= split && d->ldy >= d->Cout - split, "conv_igemm: ldy too small for the split outputs");
+  }
+  DL_CHECK_ARG(!y || split > 0 || (d->ldy % 8 == 0 && d->ldy >= d->Cout), "conv_igemm: ldy must be >= Cout, multiple of 8");
   DL_CHECK_ARG(!y_f32 || (d->ldf % 4 == 0 && d->ldf >= d->Cout), "conv_igemm: ldf must be >= Cout, multiple of 4");
   DL_CHECK_ARG(d->R >= 1 && d->S >= 1 && d->stride_h >= 1 && d->stride_w >= 1 && d->dil_h >= 1 && d->dil_w >= 1 &&
                    d->pad_h >= 0 && d->pad_w >= 0,
@@ -275,7 +282,7 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   // linear_small_kernel spreads it over Cout/4 blocks instead of one or two tensor-core CTAs
   // (only where one "pixel" is one batch item, P Q == 1, and whatever the batch size up to 4096, so that an utterance
   // gets the same summation order alone and inside a batch)
-  if (opt_small_linear() && M <= 4096 && P * Q == 1 && d->R == 1 && d->S == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
+  if (opt_small_linear() && split == 0 && M <= 4096 && P * Q == 1 && d->R == 1 && d->S == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
       d->pad_w == 0 && !lin && !residual && d->C % 8 == 0 && d->out_img_rows == 0 &&
       (d->img_rows == 0 || d->img_rows == d->H) && (d->img_cols == 0 || d->img_cols == d->W) &&
       (((uintptr_t)x | (uintptr_t)w_packed) & 15) == 0) {
@@ -308,6 +315,9 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   p.residual = static_cast<const uint16_t*>(residual);
   p.y = static_cast<uint16_t*>(y);
   p.yf = y_f32;
+  p.y2 = static_cast<uint16_t*>(d->y_split);
+  p.split_c = split > 0 ? split : 0;
+  p.skip_n0 = -1;
   p.num_m_blocks = (int)((M + 127) / 128);
 
   const int block_n = d->Cout <= 64 ? 64 : (d->Cout <= 128 ? 128 : 256);
@@ -319,6 +329,10 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   // CTA pairs (cta_group::2) for wide tiles on problems large enough to fill the chip twice over
   const bool pair = opt_pair() && block_n >= 128 && !resident && p.num_m_blocks >= 128;
   p.taps = pair ? igemm_pair_taps(p, block_n) : 1;
+  // the declared centre-tap-only channels: whole n blocks of the pair kernel skip the other K blocks (any other kernel
+  // multiplies the zero weights, same result)
+  if (split > 0 && d->split_center_only && pair && p.taps == 1 && (d->R & 1) && (d->S & 1) && split % block_n == 0)
+    p.skip_n0 = split / block_n;
   p.a_rows = 128 + (p.taps - 1) * d->dil_w;
 
   CUtensorMap mapA, mapB;

@@ -119,11 +119,14 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
 # ------------------------------------------------------------------ K3 / K5 / K7
 def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=(1, 1), scale=None, shift=None,
                slope=None, residual=None, want_bf16=True, want_f32=False, scale2=None, shift2=None,
-               f32_slope=1.0, H=None, W=None, out=None, out_channel_offset=0, residual_channel_offset=0):
+               f32_slope=1.0, H=None, W=None, out=None, out_channel_offset=0, residual_channel_offset=0, split=None):
     """x: (N,H,W,ldx) bf16 channels-last -- or (N,img_rows,img_cols,ldx) stacked / guarded with the true extents
     passed as H, W.  `out` may be a wider (channel slice) and / or guarded (N, >=P, >=Q, ld) caller-owned buffer;
     with `out`, `residual` is a buffer of out's shape read at `residual_channel_offset` (the kernel indexes the residual
     with the output's pixel pitch).
+    split=(c, center_only): sibling convs in one launch -- output channels >= c go to a second dense tensor and, with
+    center_only, are declared to have zero weights off the centre tap (dl_conv_desc.split_channel); the first return
+    value is then the pair (y[..., :c], y[..., c:]) as two dense tensors.
     Returns (y_bf16 (N,P,Q,Cout) | out | None, y_f32 (N*P*Q,Cout) | None)."""
     _need_cuda(x, w_packed, scale, shift, slope, residual, scale2, shift2)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
@@ -135,6 +138,19 @@ def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=
     ldy = Cout
     y_ptr = None
     out_rows = out_cols = 0
+    if split is not None:
+        sc, center_only = split
+        assert out is None and residual is None and not want_f32 and 0 < sc < Cout
+        ya = torch.empty((N, P, Q, sc), device=x.device, dtype=torch.bfloat16)
+        yb = torch.empty((N, P, Q, Cout - sc), device=x.device, dtype=torch.bfloat16)
+        ldy = max(sc, Cout - sc)
+        assert sc == Cout - sc, 'both halves share one pitch'
+        d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ldy, Cout,
+                     float(f32_slope), img_rows, img_cols, 0, 0, 0, 0, 0, sc, int(bool(center_only)), yb.data_ptr())
+        st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope), None,
+                                           _ptr(ya), None, None, None, C.byref(d), _stream())
+        _lib.check(st, 'dl_conv_igemm_bf16')
+        return (ya, yb), None
     if out is not None:          # write Cout channels into a slice of a wider channels-last buffer (concat for free)
         assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.dim() == 4 and out.shape[0] == N
         assert out.shape[1] >= P and out.shape[2] >= Q

@@ -128,6 +128,17 @@ class BasicBlock(nn.Module):
                            pk['s2'], pk['h2'], pk['a2'], residual=res, out=out)
         return out
 
+    def forward_fused_entry_split(self, x, H=None, W=None):
+        """Entry block of a >= 256-channel layer: conv1 and the skip as one conv whose two halves leave as two dense
+        tensors (dl_conv_desc.split_channel); the skip half is declared centre-tap-only, so the CTA-pair kernel
+        spends a ninth of a tile on it instead of a separate launch that re-reads the input map."""
+        pk = self._packed()
+        (mid, res), _ = ops.conv_igemm(x, pk['wf'], self.inplanes, 2 * self.planes, 3, 3, (2, 2), (1, 1), (1, 1),
+                                       pk['sf'], pk['hf'], pk['af'], H=H, W=W, split=(self.planes, True))
+        out, _ = ops.conv_igemm(mid, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1),
+                                pk['s2'], pk['h2'], pk['a2'], residual=res)
+        return out
+
     def forward_fused_entry(self, x, H, W, out):
         """Entry block with conv1 and the skip as one conv (see FUSE_L2_ENTRY).  x: (N, img_rows >= H, W, inplanes);
         out: caller-owned (N, P, Q, 2 planes) buffer; returns it with the block output in channels [0, planes)."""
@@ -294,7 +305,17 @@ class ResNet(nn.Module):
                 for blk in list(self.layer2)[1:]:
                     a, b = b, a
                     x = blk.forward_pitched(x, a)
-                rest = list(self.layer3)             # layer3's entry convs read 128 of the 256-channel pitch
+                # layer3 / layer4: entry blocks fused with a split output (their input may sit in a wider pitch)
+                for layer in (self.layer3, self.layer4):
+                    blocks = list(layer)
+                    if blocks[0].planes % 256 == 0 and blocks[0].stride == 2 and blocks[0].downsample is not None and \
+                            blocks[0].inplanes % 64 == 0:
+                        x = blocks[0].forward_fused_entry_split(x)
+                    else:
+                        x = blocks[0].forward_nhwc(x)
+                    for blk in blocks[1:]:
+                        x = blk.forward_nhwc(x)
+                return x
             else:
                 x = self.layer2[0].forward_nhwc(x, H=H)
                 rest = list(self.layer2)[1:] + list(self.layer3)

@@ -133,6 +133,13 @@ typedef struct dl_conv_desc {
   int lin;           /* 1 = guarded-linear operand A (tiled TMA), see above */
   int valid_h, valid_w;            /* lin = 1: extents of the stored outputs */
   int out_img_rows, out_img_cols;  /* lin = 0: pitches of y / residual (0 = dense P, Q) */
+  /* Sibling convs as one launch (0 = off): output channels c >= split_channel are stored to y_split[row * ldy +
+   * c - split_channel] instead of y (both with pitch ldy >= max(split_channel, Cout - split_channel)); with
+   * split_center_only = 1 the caller declares that those channels' weights are zero off the filter's centre tap
+   * (a 1x1 stride-s pad-0 conv riding a 3x3 stride-s pad-1 one, resnet.py:13-17 + :56-59): the CTA-pair kernel then
+   * skips their other K blocks.  Needs split_channel % 256 == 0, no residual, no f32 output, lin = 0. */
+  int split_channel, split_center_only;
+  void* y_split;
 } dl_conv_desc;
 
 int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,

@@ -391,8 +391,10 @@ def video_model_case(B=2, T=6, seed=1, u8=True, speakers=None):
 
 
 def video_fused_entry_case(B=3, T=40, seed=4):
-    """layer2's entry block with conv1 and the 1x1 skip as ONE 64 -> 256 conv (skip weights on the centre tap) must
-    equal the two separate convs bit for bit, small batch (single-CTA igemm) and pair-kernel sized alike."""
+    """Entry blocks with conv1 and the 1x1 skip as ONE conv (skip weights on the centre tap; layer2: one 256-wide tile
+    into a 256-pitch buffer, layer3/4: split output + centre-tap-only n blocks in the CTA-pair kernel) must equal the
+    separate convs bit for bit: small batch (single-CTA igemm, the centre-tap hint ignored), medium, and a batch large
+    enough (>= 1821 frames) for layer4 to run on the pair kernel."""
     from deeplip_b200.video_models import resnet as R
     from deeplip_b200.video_models.model import Lipreading
     sd = synth.make_video_state_dict(seed=seed, randomize=True)
@@ -403,7 +405,7 @@ def video_fused_entry_case(B=3, T=40, seed=4):
     out = {}
     with torch.no_grad():
         try:
-            for name, (b, t) in (('small', (1, 3)), ('large', (B, T))):
+            for name, (b, t) in (('small', (1, 3)), ('large', (B, T)), ('pair', (26, 72))):
                 raw = torch.from_numpy(synth.lip_crops_u8(list(range(b)), T=t, seed=seed)).to(DEV)
                 R.FUSE_L2_ENTRY = True
                 assert m.trunk.fused_entry_enabled()
@@ -415,7 +417,7 @@ def video_fused_entry_case(B=3, T=40, seed=4):
                 out[name + '_abs'] = float((fused.float() - plain.float()).abs().max())
         finally:
             R.FUSE_L2_ENTRY = saved
-    assert out['small_equal'] and out['large_equal'], out
+    assert out['small_equal'] and out['large_equal'] and out['pair_equal'], out
     return out
 
 
