@@ -276,7 +276,7 @@ def run_ours(args, rank, world, local):
     h2d = B * (T_FRAMES * RAW_HW * RAW_HW + NSAMP * 4)
     d2h = n_total * 1024 * 4
 
-    # ---- roofline of the dominant kernel (igemm_conv_kernel): the 19 trunk launches of one step
+    # ---- roofline of the dominant kernels: the trunk's conv launches of one step (16 with the fused entry blocks)
     peaks = measured_peaks()
     pk = video._packed()
     from deeplip_b200 import ops
@@ -290,28 +290,33 @@ def run_ours(args, rank, world, local):
         trunk_kw = {}
     torch.cuda.synchronize()
     evs = []
+    n_trunk = 0
     for i in range(max(3, min(args.steps, 10))):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
         a.record()
         video.trunk.forward_nhwc(stem_out, **trunk_kw)
         b.record()
+        n_trunk = _lib.launch_count() - l0
         evs.append((a, b))
     torch.cuda.synchronize()
     trunk_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
     trunk_tflops = GFLOP_TRUNK_PER_UTT * B / trunk_ms          # GFLOP / ms == TFLOP/s
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r1m_trunk_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r1v_trunk_traffic.json')
     if os.path.exists(tpath) and B == 64:          # dram bytes per launch from the committed ncu capture
         tj = json.load(open(tpath))
-        traffic = tj['trunk_dram_bytes_per_step'] / tj['trunk_conv_launches']
-    roofline = {'kernel': 'igemm_conv / igemm2_conv / conv3x3_halo kernels (the 19 ResNet-18 trunk conv launches of one step)',
+        traffic = tj['trunk_dram_bytes_per_step'] / max(1, n_trunk)
+    roofline = {'kernel': 'igemm_conv / igemm2_conv / conv3x3_halo kernels (the %d ResNet-18 trunk conv launches of one step; '
+                          'entry blocks run conv1 + skip as one launch)' % n_trunk,
                 'bound': 'tensor',
                 'achieved': trunk_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': trunk_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
-                'traffic_note': 'avg DRAM bytes per trunk launch (ncu dram__bytes_read+write, profiles/r1m_step_traffic.txt)',
-                'peak_src': peaks['src'] + ' (sustained bf16 cuBLAS)', 'launches': 19,
-                'avg_launch_ms': trunk_ms / 19, 'flop_per_launch': GFLOP_TRUNK_PER_UTT * B * 1e9 / 19}
+                'traffic_note': 'avg DRAM bytes per trunk launch (ncu dram__bytes_read+write, profiles/r1v_step_traffic.txt)',
+                'peak_src': peaks['src'] + ' (sustained bf16 cuBLAS)', 'launches': n_trunk,
+                'avg_launch_ms': trunk_ms / max(1, n_trunk),
+                'flop_per_launch': GFLOP_TRUNK_PER_UTT * B * 1e9 / max(1, n_trunk)}
     # stem + audio, for the record
     evs = []
     for i in range(5):
