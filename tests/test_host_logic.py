@@ -37,6 +37,13 @@ def test_argument_validation_without_touching_the_gpu():
     one = ctypes.c_void_p(16)
     assert l.dl_conv_igemm_bf16(one, one, one, one, one, None, one, None, None, None, ctypes.byref(d), None) == -1
     assert b'ldx' in l.dl_last_error()
+    d2 = _lib.ConvDesc(1, 8, 8, 64, 64, 512, 3, 3, 2, 2, 1, 1, 1, 1, 256, 512, 1.0)
+    d2.split_channel, d2.y_split = 128, 16                     # sibling-conv split must fall on a 256-channel boundary
+    assert l.dl_conv_igemm_bf16(one, one, one, one, one, None, one, None, None, None, ctypes.byref(d2), None) == -1
+    assert b'split_channel' in l.dl_last_error()
+    d2.split_channel, d2.y_split = 256, 0                      # ... and needs the second output
+    assert l.dl_conv_igemm_bf16(one, one, one, one, one, None, one, None, None, None, ctypes.byref(d2), None) == -1
+    assert b'y_split' in l.dl_last_error()
     assert l.dl_frontend_features(one, None, 1, 48000, 0, 24, 1, None, 64, one, 298, None) == -1
     assert b'299' in l.dl_last_error()
     assert l.dl_frontend_features(one, None, 1, 48000, 3, 257, 1, None, 320, one, 299, None) == -1      # stft framing
