@@ -667,6 +667,31 @@ def tcd_timit_ragged_case(durations=(3.0, 6.44, 10.0), seed=3):
     return out
 
 
+def graphed_extractor_case(B=4, T=8, nsamp=24000, seed=2):
+    """GraphedExtractor: the whole step captured into one CUDA graph replays to the same bits as the eager launches,
+    for the captured batch and for new data of the same shape."""
+    from deeplip_b200.pipeline import AVExtractor, GraphedExtractor, build_models
+    audio, video = build_models(DEV, seed=1)
+    ex = AVExtractor(audio, video)
+    spk = list(range(B))
+    wav = torch.from_numpy(synth.speech_like_audio(spk, nsamp=nsamp, seed=seed)).to(DEV)
+    raw = torch.from_numpy(synth.lip_crops_u8(spk, T=T, seed=seed)).to(DEV)
+    wav2 = torch.from_numpy(synth.speech_like_audio(spk, nsamp=nsamp, seed=seed + 1)).to(DEV)
+    raw2 = torch.from_numpy(synth.lip_crops_u8(spk, T=T, seed=seed + 1)).to(DEV)
+    ref, ref2 = ex.extract(wav, raw).clone(), ex.extract(wav2, raw2).clone()
+    g = GraphedExtractor(ex, wav, raw)
+    out = {'same_batch': bool(torch.equal(g.extract(wav, raw), ref))}
+    out['new_batch'] = bool(torch.equal(g.extract(wav2, raw2), ref2))
+    torch.cuda.synchronize()
+    try:
+        g.extract(wav[:2], raw[:2])
+        out['shape_check'] = False
+    except RuntimeError:
+        out['shape_check'] = True
+    assert all(out.values()), out
+    return out
+
+
 def full_size_batch_invariance_case(B=256, sub=64, seed=11):
     """BASELINE configs[2] size (batch 256 of GRID-shaped utterances: 75 x 96x96 u8 crops + 3 s of audio) through a
     size-independent property: every utterance's fused embedding in the batch of 256 is bit-identical to the one it

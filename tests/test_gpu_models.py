@@ -61,6 +61,10 @@ def test_av_pipeline_and_ragged_batch():
     G.pipeline_case()
 
 
+def test_graphed_extractor_replays_bit_identically():
+    G.graphed_extractor_case()
+
+
 def test_full_size_batch_256_is_batch_invariant():
     G.full_size_batch_invariance_case()
 
