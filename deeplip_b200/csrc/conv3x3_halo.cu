@@ -89,8 +89,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_launch();
-  griddep_wait();                     // prologue done under the previous kernel's tail; its outputs are visible from here
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -276,6 +274,6 @@ extern "C" int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, con
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.total_tiles < grid) grid = p.total_tiles;
-  launch_pdl(conv3x3_halo_kernel, dim3(grid), dim3(kHaloThreads), kHaloSmem, (cudaStream_t)stream, mapX, mapW, mapY, p);
+  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, (cudaStream_t)stream>>>(mapX, mapW, mapY, p);
   return check_launch("conv3x3_halo_kernel");
 }

@@ -46,28 +46,5 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 
 }  // namespace dl
 
-namespace dl {
-int opt_pdl();             // 1 = launch with programmatic stream serialization (default), 0 = ordinary launches
-
-// Launch `kernel` so that it may overlap its prologue with the tail of the previous kernel in the stream (see
-// griddep_wait / griddep_launch in dl_ptx.cuh).  Every kernel launched through here calls griddep_wait() before it
-// touches data produced by earlier kernels.
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = opt_pdl() ? 1 : 0;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-}  // namespace dl
-
 #define DL_CHECK_ARG(cond, ...) \
   do { if (!(cond)) return dl::fail(DL_ERR_INVALID, __VA_ARGS__); } while (0)

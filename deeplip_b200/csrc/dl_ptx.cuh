@@ -211,15 +211,6 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- small helpers
-// Programmatic dependent launch (kernels launched through dl::launch_pdl): a kernel may be scheduled while its
-// predecessor in the stream is still draining -- as soon as every CTA of the predecessor has executed
-// griddep_launch() (or exited) and an SM has room -- and runs its prologue (barrier init, TMEM allocation, parameter
-// staging) there; griddep_wait() then blocks until the predecessor has completed and its writes are visible.  Nothing
-// before griddep_wait() may read what an earlier kernel wrote, nor write what an earlier kernel reads.  Both are no-ops
-// in a kernel launched the ordinary way.
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -264,8 +264,8 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
     if (st != DL_OK) return st;
     dim3 grid((T + kBlkFrames - 1) / kBlkFrames, B);
     const size_t smem = (size_t)frames2_smem_floats(F) * 4;
-    if (stft) launch_pdl(frontend_frames2_kernel<true>, grid, dim3(256), smem, s, wav, lengths, nsamp, T, tb, feat_f32);
-    else launch_pdl(frontend_frames2_kernel<false>, grid, dim3(256), smem, s, wav, lengths, nsamp, T, tb, feat_f32);
+    if (stft) frontend_frames2_kernel<true><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
+    else frontend_frames2_kernel<false><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
     st = check_launch("frontend_frames2_kernel");
   } else {
     st = upload_twiddles();
@@ -278,8 +278,8 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
   const size_t csmem = (size_t)8 * T * 4;
   const bool bf16_ok = !feat_bf16 || (ld_bf16 % 8 == 0 && ld_bf16 >= (F + 7) / 8 * 8 && ((uintptr_t)feat_bf16 & 15) == 0);
   if (gen >= 2 && csmem <= (size_t)kCmvn2MaxSmem && bf16_ok) {
-    launch_pdl(frontend_cmvn2_kernel, dim3(B, (F + 7) / 8), dim3(256), csmem, s, feat_f32, lengths, nsamp, T, F, cmvn,
-               stft ? 1 : 0, (uint16_t*)feat_bf16, ld_bf16);
+    frontend_cmvn2_kernel<<<dim3(B, (F + 7) / 8), 256, csmem, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, stft ? 1 : 0,
+                                                                  (uint16_t*)feat_bf16, ld_bf16);
     return check_launch("frontend_cmvn2_kernel");
   }
   DL_CHECK_ARG(!stft, "frontend: stft needs ld_bf16 %% 8 == 0, a 16-byte aligned feat_bf16 and T <= %d", kCmvn2MaxSmem / 32);

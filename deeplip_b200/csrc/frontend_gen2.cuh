@@ -1,8 +1,7 @@
 // Generation-2 audio front end kernels (K1) and the host code that fills their tables.  Kept in a header with no CUDA
 // runtime dependency beyond the usual built-ins so that tests/frontend_cpu_emul.cpp can compile THIS SOURCE for the CPU
 // (one OS thread per CUDA thread, barriers for __syncthreads / __syncwarp) and check it against the oracle without a GPU.
-// The includer provides: warp_sum(float), pack_bf16x2(float, float), __ldg, uint4 / make_uint4, min / max,
-// griddep_wait() / griddep_launch() (programmatic dependent launch, dl_ptx.cuh; no-ops on the CPU).
+// The includer provides: warp_sum(float), pack_bf16x2(float, float), __ldg, uint4 / make_uint4, min / max.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -81,8 +80,6 @@ __global__ void __launch_bounds__(256, 2) frontend_frames2_kernel(const float* _
     if (tid < tb.nfilt + 2) sbins[tid] = tb.bins[tid];
     if (tid < tb.nfilt + 1) sinvw[tid] = tb.inv_width[tid];
   }
-  griddep_launch();
-  griddep_wait();          // the tables above are constants; the samples may come from the previous kernel / copy
   // ---- stage the block's samples.  Every thread issues ALL its global loads before it touches one of them (the loop
   // used to wait out one DRAM round trip per iteration: a third of the kernel's stall samples); the raw samples rest
   // in the FFT scratch, which is idle until the frames are built.
@@ -258,8 +255,6 @@ __global__ void __launch_bounds__(256) frontend_cmvn2_kernel(float* __restrict__
                                                              int nsamp, int T, int F, int cmvn, int stft,
                                                              uint16_t* __restrict__ out_bf16, int ld) {
   extern __shared__ __align__(16) float rows[];      // [8][T]
-  griddep_launch();
-  griddep_wait();
   const int b = blockIdx.x, f0 = blockIdx.y * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = lengths ? max(0, min(lengths[b], nsamp)) : nsamp;

@@ -102,8 +102,6 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   cluster_sync_all();                 // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_launch();
-  griddep_wait();                     // prologue done under the previous kernel's tail; its outputs are visible from here
 
   // super tiles: (pair of consecutive m blocks) x n block
   const int num_m_pairs = (p.num_m_blocks + 1) >> 1;
@@ -285,7 +283,7 @@ static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const
   if (pairs <= 0) pairs = 74;
   if (super_tiles < pairs) pairs = super_tiles;
   if ((p.dbg & 64) && pairs > 1) pairs /= 2;          // measurement aid: half the SMs (per-SM vs chip-wide ingest)
-  launch_pdl(igemm2_conv_kernel<BLOCK_N, kResB, TAPS>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, p);
+  igemm2_conv_kernel<BLOCK_N, kResB, TAPS><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
   return check_launch("igemm2_conv_kernel");
 }
 

@@ -94,8 +94,6 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_launch();
-  griddep_wait();                     // prologue done under the previous kernel's tail; its outputs are visible from here
 
   const int total_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_kb = p.R * p.S * p.cchunks;
@@ -221,7 +219,7 @@ static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (tiles < grid) grid = tiles;
-  launch_pdl(igemm_conv_kernel<BLOCK_N, kResB>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, p);
+  igemm_conv_kernel<BLOCK_N, kResB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
   return check_launch("igemm_conv_kernel");
 }
 
@@ -296,8 +294,8 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
     lp.scale2 = scale2; lp.shift2 = shift2; lp.f32_slope = d->f32_slope; lp.yf = y_f32; lp.ldf = d->ldf;
     const int gx = (d->Cout + kLinCh - 1) / kLinCh;
     cudaStream_t cs = (cudaStream_t)stream;
-    if (M <= 32) launch_pdl(linear_small_kernel<1>, dim3(gx, 1), dim3(32 * kLinKs), linear_small_smem_bytes(1), cs, lp);
-    else launch_pdl(linear_small_kernel<2>, dim3(gx, (unsigned)((M + 63) / 64)), dim3(32 * kLinKs), linear_small_smem_bytes(2), cs, lp);
+    if (M <= 32) linear_small_kernel<1><<<dim3(gx, 1), 32 * kLinKs, linear_small_smem_bytes(1), cs>>>(lp);
+    else linear_small_kernel<2><<<dim3(gx, (unsigned)((M + 63) / 64)), 32 * kLinKs, linear_small_smem_bytes(2), cs>>>(lp);
     return check_launch("linear_small_kernel");
   }
   IgemmParams p;

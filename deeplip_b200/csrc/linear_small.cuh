@@ -6,7 +6,7 @@
 // own rows of x (one 16-byte chunk feeds 4 channels), there is no cross-lane reduction and the summation order is
 // fixed (bitwise reproducible).  Same epilogue contract as the igemm kernels.
 // Free of CUDA-runtime dependencies so that tests/frontend_cpu_emul.cpp can run this source on CPU threads.
-// The includer provides: bf16_lo / bf16_hi (uint32 -> float), pack_bf16x2, __ldg, uint4, min, griddep_wait / griddep_launch.
+// The includer provides: bf16_lo / bf16_hi (uint32 -> float), pack_bf16x2, __ldg, uint4, min.
 #pragma once
 #include <stdint.h>
 
@@ -40,8 +40,6 @@ template <int RPL>
 __global__ void __launch_bounds__(32 * kLinKs) linear_small_kernel(LinearSmallParams p) {
   extern __shared__ __align__(16) float lin_part[];      // [kLinKs][kLinCh][32 RPL] (dynamic: linear_small_smem_bytes)
   constexpr int kRows = 32 * RPL;
-  griddep_launch();
-  griddep_wait();
   const int ks = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * kLinCh;
   const int m0 = blockIdx.y * kRows;

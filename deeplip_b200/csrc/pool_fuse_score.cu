@@ -24,8 +24,6 @@ __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restri
   // kSlab channels per block (256: a warp per time step, 8 "virtual warps" stride over time; 128: a half warp per
   // time step, 16 virtual warps -- twice the blocks for the same bytes, better balance over 148 SMs)
   constexpr int kVW = 8 * (256 / kSlab), kLanes = kSlab / 8;
-  griddep_launch();
-  griddep_wait();
   extern __shared__ float sm[];   // kAttn: alpha[T] ; then kVW virtual warps x kSlab ch x 2 partials
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,8 +168,6 @@ __global__ void __launch_bounds__(256) frame_pool_kernel(const uint16_t* __restr
                                                          float* __restrict__ frame_feats,
                                                          float* __restrict__ utt_mean) {
   __shared__ float sm[32][64];
-  griddep_launch();
-  griddep_wait();
   const int b = blockIdx.x;
   const int cb = blockIdx.y * 64;
   const int ct = threadIdx.x & 7, g = threadIdx.x >> 3;
@@ -241,8 +237,6 @@ __device__ __forceinline__ void row_stats(const float* r, int D, int lane, bool 
 __global__ void znorm_concat_kernel(const float* __restrict__ a, int Da, const float* __restrict__ v, int Dv, int B,
                                     int biased, int video_first, int l2norm, float* __restrict__ out,
                                     uint16_t* __restrict__ out_bf16) {
-  griddep_launch();
-  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = threadIdx.x & 31;
@@ -426,17 +420,17 @@ extern "C" int dl_stat_pool(const void* x, int B, int T, int C, int ldx, const i
   DL_CHECK_ARG(!out_bf16 || ld_out >= 2 * C, "stat_pool: ld_out < 2C");
   const size_t smem = 8 * 256 * 2 * sizeof(float);
   if (opt_statpool_slab() == 128) {
-    launch_pdl(stat_pool_kernel<false, 4, 128>, dim3((C + 127) / 128, B), dim3(256), smem, (cudaStream_t)stream,
-               (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
+    stat_pool_kernel<false, 4, 128><<<dim3((C + 127) / 128, B), 256, smem, (cudaStream_t)stream>>>(
+        (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
     return check_launch("stat_pool_kernel");
   }
   dim3 grid((C + 255) / 256, B);
   if (opt_statpool_mlp() == 4)
-    launch_pdl(stat_pool_kernel<false, 4, 256>, grid, dim3(256), smem, (cudaStream_t)stream,
-               (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
+    stat_pool_kernel<false, 4, 256><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
   else
-    launch_pdl(stat_pool_kernel<false, 8, 256>, grid, dim3(256), smem, (cudaStream_t)stream,
-               (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
+    stat_pool_kernel<false, 8, 256><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (const uint16_t*)x, nullptr, T, C, ldx, lengths, out_f32, (uint16_t*)out_bf16, ld_out);
   return check_launch("stat_pool_kernel");
 }
 
@@ -469,19 +463,19 @@ extern "C" int dl_frame_pool_temporal_mean(const void* x, int B, int T, int HW, 
   DL_CHECK_ARG(B > 0 && T > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 2048, "frame_pool: bad shape");
   dim3 grid(B, (C + 63) / 64);
   if (HW == 9)         // the 3x3 maps ResNet-18 leaves of an 88x88 crop
-    launch_pdl(frame_pool_kernel<9>, grid, dim3(256), 0, (cudaStream_t)stream, (const uint16_t*)x, T, HW, C, lengths,
-               frame_feats, utt_mean);
+    frame_pool_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, T, HW, C, lengths, frame_feats,
+                                                                 utt_mean);
   else
-    launch_pdl(frame_pool_kernel<0>, grid, dim3(256), 0, (cudaStream_t)stream, (const uint16_t*)x, T, HW, C, lengths,
-               frame_feats, utt_mean);
+    frame_pool_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, T, HW, C, lengths, frame_feats,
+                                                                 utt_mean);
   return check_launch("frame_pool_kernel");
 }
 
 extern "C" int dl_znorm_concat(const float* a, int Da, const float* v, int Dv, int B, int biased, int video_first,
                                int l2norm, float* out, void* out_bf16, void* stream) {
   DL_CHECK_ARG(a && v && (out || out_bf16) && B > 0 && Da > 1 && Dv > 1, "znorm_concat: bad argument");
-  launch_pdl(znorm_concat_kernel, dim3((B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, a, Da, v, Dv, B, biased,
-             video_first, l2norm, out, (uint16_t*)out_bf16);
+  znorm_concat_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a, Da, v, Dv, B, biased, video_first, l2norm, out,
+                                                                    (uint16_t*)out_bf16);
   return check_launch("znorm_concat_kernel");
 }
 

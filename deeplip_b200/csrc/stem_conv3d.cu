@@ -127,8 +127,6 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_launch();
-  griddep_wait();                     // the pre-pass (previous kernel) has written the frames the strips come from
 
   if (warp >= 10) {
     // =============================================================== builders: operand A from the staged strip
@@ -470,7 +468,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   const int dh = is_u8 ? (Hraw - H) / 2 : 0, dw = is_u8 ? (Wraw - W) / 2 : 0;
   if (opt_prepass() >= 2 || lengths) {
     const int aligned4 = (Wraw % 4 == 0 && ((uintptr_t)x & 3) == 0) ? 1 : 0;
-    launch_pdl(stem_prepass2_kernel, dim3((unsigned)(B * T)), dim3(256), 0, cs,
+    stem_prepass2_kernel<<<(unsigned)(B * T), 256, 0, cs>>>(
         x, is_u8, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f, rows,
         pitch, aligned4, T, lengths, static_cast<uint16_t*>(workspace));
     st = check_launch("stem_prepass2_kernel");
@@ -503,6 +501,6 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  launch_pdl(stem_conv3d_kernel, dim3(grid), dim3(kStemThreads), smem, cs, mapW, mapX, p);
+  stem_conv3d_kernel<<<grid, kStemThreads, smem, cs>>>(mapW, mapX, p);
   return check_launch("stem_conv3d_kernel");
 }

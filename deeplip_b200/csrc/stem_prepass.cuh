@@ -4,7 +4,7 @@
 // (funnel-shifted to the crop offset) -- no 64-bit index divisions, 2.7x fewer load instructions than generation 1.
 // `lengths` (may be NULL): valid frames per clip of T frames; later frames are written as zeros.
 // Free of CUDA-runtime dependencies so that tests/frontend_cpu_emul.cpp can run this source on CPU threads.
-// The includer provides: pack_bf16x2(float, float), __ldg, __funnelshift_r, uint4, griddep_wait / griddep_launch.
+// The includer provides: pack_bf16x2(float, float), __ldg, __funnelshift_r, uint4.
 #pragma once
 #include <stdint.h>
 
@@ -15,8 +15,6 @@ __global__ void __launch_bounds__(256) stem_prepass2_kernel(const void* __restri
                                                             int rows, int pitch, int aligned4, int T,
                                                             const int32_t* __restrict__ lengths,
                                                             uint16_t* __restrict__ xp) {
-  griddep_launch();
-  griddep_wait();
   const int f = blockIdx.x;
   // ragged batches (pad_packed_collate, models/video_models/dataset.py:123-139): the reference pads AFTER its
   // preprocessing, i.e. with normalised zeros -- frames at or beyond the clip's length become all-zero here, whatever

@@ -35,9 +35,7 @@ const char* dl_last_error(void);
  * (smem-resident weight half in the pair kernel, default 1), "tap_share" (one operand-A box per filter row in
  * the guarded-linear pair kernel, default 1), "frontend" (2 = register-resident FFT front end, 1 = first generation),
  * "prepass" (2 | 1, stem pre-pass generation), "small_linear" (1 = fc layers on linear_small_kernel, 0 = igemm),
- * "statpool_mlp" (4 | 8 loads in flight), "pdl" (1 = kernels are launched with programmatic stream serialization and run
- * their prologue under the previous kernel's tail, 0 = ordinary launches), "stft_pad" (0 reflect | 1 zeros: a convention,
- * not a tuning switch).
+ * "statpool_mlp" (4 | 8 loads in flight), "stft_pad" (0 reflect | 1 zeros: a convention, not a tuning switch).
  * Results agree to fp32 summation order either way.
  * "dbg" (default 0) is a measurement aid only: bits 1/2/4 drop the residual / stores / whole epilogue of the
  * pair kernel, 8 issues one MMA in four, 16/32 idle the stem's builders / epilogue (tools/epi_try.py,

@@ -51,10 +51,6 @@ struct BlockCtx {
 };
 thread_local BlockCtx* g_ctx;
 inline void __syncthreads() { g_ctx->all.arrive_and_wait(); }
-namespace dl {
-inline void griddep_wait() {}          // programmatic dependent launch: nothing to wait for on the CPU
-inline void griddep_launch() {}
-}  // namespace dl
 inline void __syncwarp() { g_ctx->warp[threadIdx.x >> 5]->arrive_and_wait(); }
 
 namespace dl {
