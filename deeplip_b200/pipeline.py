@@ -5,7 +5,7 @@ Reference order per utterance (train_fusion.py:386-417):
     wav -> MFCC + CMVN (DataLoader worker)        -> model_audio.extract_embedding -> xv_audio (1,512)
     clips -> /255, centre crop, (x-.421)/.165     -> model_video per clip -> mean over frames -> mean over clips
     feature_normalize x2 -> cat([audio, video])   -> np.save
-Here a whole batch of utterances goes through the same arithmetic in ~45 kernel launches, nothing
+Here a whole batch of utterances goes through the same arithmetic in 35 kernel launches, nothing
 leaves the device, and ragged batches carry `lengths` (zero-padded tails are exact for the video
 branch; the audio branch masks its pooling).
 """
@@ -67,7 +67,7 @@ class AVExtractor:
 
 
 class GraphedExtractor:
-    """The whole extraction step (~38 kernel launches) captured once into a CUDA graph and replayed:
+    """The whole extraction step (35 kernel launches) captured once into a CUDA graph and replayed:
     static input / output buffers, no per-launch host work.  Shapes are fixed at capture time."""
 
     def __init__(self, extractor, wav_example, video_example, warmup=2):
