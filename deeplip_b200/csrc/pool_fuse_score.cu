@@ -12,10 +12,6 @@ namespace dl {
 // Statistics pooling over time, channels-last bf16 input.  Block = 8 warps; a warp reads 256 channels
 // (32 lanes x 8 bf16 = 16 B per lane) of one time step per iteration; the 8 warps stride over time and
 // are merged with Chan's parallel-variance update.  Optional attention weights (softmax over time).
-struct Welford8 {
-  float mean[8], m2[8];
-};
-
 template <bool kAttn, int kMlp, int kSlab>
 __global__ void __launch_bounds__(256) stat_pool_kernel(const uint16_t* __restrict__ x, const float* __restrict__ logits,
                                                         int T, int C, int ldx, const int32_t* __restrict__ lengths,

@@ -12,7 +12,6 @@ branch; the audio branch masks its pooling).
 import torch
 
 from . import ops
-from .fusion_models import model_fusion as fusion_mod
 
 
 class AVExtractor:
