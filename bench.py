@@ -146,6 +146,18 @@ def oracle_av_extract(raw, wav, sda, sdv, aopts):
     return torch.cat(outs)
 
 
+def oracle_av_extract_batched(raw, wav, sda, sdv, aopts):
+    """The same restatement as ONE batched call (BASELINE configs[0]: "CPU batch 8"): the reference modules accept a
+    batch, its extraction loop just never passes one."""
+    from oracle import frontend_np, models_ref
+    with torch.no_grad():
+        feat = torch.from_numpy(np.stack([frontend_np.extract_feature(w.astype(np.float64)).T for w in wav]))
+        xv, _ = models_ref.speaker_extract_embedding(sda, feat, aopts)
+        x = torch.stack([models_ref.video_preprocess(torch.from_numpy(r)) for r in raw])[:, None]
+        em = models_ref.lipreading_features(sdv, x).mean(dim=1)
+        return models_ref.concat_fusion(xv, em)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -427,7 +439,13 @@ def run_ours(args, rank, world, local):
         got = ex.extract(devb[0][1][:n].contiguous(), devb[0][0][:n].contiguous()).cpu().double()
         ref = torch.cat(ref_rows).double()
         cos = ((got * ref).sum(1) / (got.norm(dim=1) * ref.norm(dim=1))).min().item()
+        nb = min(8, B)                                   # configs[0]'s "CPU batch 8": one batched call
+        tb0 = time.perf_counter()
+        ref_b = oracle_av_extract_batched(raw[:nb], wav[:nb], sda, sdv, aopts)
+        dtb = time.perf_counter() - tb0
         cpu = {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'batched_b8_value': nb / dtb,
+               'batched_b8_max_abs_vs_loop': float((ref_b.double() - ref[:nb]).abs().max()) if n >= nb else None,
                'sample': '%d of the %d utterances of batch 0, per-utterance B=1 loop (train_fusion.py:386-410) '
                          'through oracle/ (torch fp32 CPU + NumPy MFCC)' % (n, B),
                'parity_min_cosine_vs_gpu': cos}
