@@ -236,7 +236,8 @@ static int upload_tables() {
 }  // namespace dl
 
 extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
-                                    int cmvn, void* feat_bf16, int ld_bf16, float* feat_f32, int T, void* stream) {
+                                    int cmvn, int delta, void* feat_bf16, int ld_bf16, float* feat_f32, int T,
+                                    void* stream) {
   using namespace dl;
   DL_CHECK_ARG(wav && feat_f32, "frontend: wav and feat_f32 are required");
   DL_CHECK_ARG(B > 0 && nsamp > 0, "frontend: empty batch");
@@ -251,8 +252,11 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
   const int Texp = stft ? 1 + nsamp / kFrameStep
                         : (nsamp <= kFrameLen ? 1 : 1 + (nsamp - kFrameLen + kFrameStep - 1) / kFrameStep);
   DL_CHECK_ARG(T == Texp, "frontend: T=%d but %d samples give %d frames", T, nsamp, Texp);
-  DL_CHECK_ARG(!feat_bf16 || ld_bf16 >= F, "frontend: ld_bf16 < F");
+  DL_CHECK_ARG(delta >= 0 && delta <= 2, "frontend: delta order must be 0, 1 or 2");
+  const int Fout = F * (1 + delta);
+  DL_CHECK_ARG(!feat_bf16 || ld_bf16 >= Fout, "frontend: ld_bf16 < F (1 + delta)");
   const int gen = opt_frontend();
+  DL_CHECK_ARG(delta == 0 || gen >= 2, "frontend: delta features need the generation-2 kernels");
   DL_CHECK_ARG(!stft || gen >= 2, "frontend: stft needs the generation-2 kernels (dl_set_option(\"frontend\", 2))");
 
   FrontendTables tb;
@@ -264,8 +268,8 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
     if (st != DL_OK) return st;
     dim3 grid((T + kBlkFrames - 1) / kBlkFrames, B);
     const size_t smem = (size_t)frames2_smem_floats(F) * 4;
-    if (stft) frontend_frames2_kernel<true><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
-    else frontend_frames2_kernel<false><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32);
+    if (stft) frontend_frames2_kernel<true><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32, Fout);
+    else frontend_frames2_kernel<false><<<grid, 256, smem, s>>>(wav, lengths, nsamp, T, tb, feat_f32, Fout);
     st = check_launch("frontend_frames2_kernel");
   } else {
     st = upload_twiddles();
@@ -276,12 +280,13 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
   }
   if (st != DL_OK) return st;
   const size_t csmem = (size_t)8 * T * 4;
-  const bool bf16_ok = !feat_bf16 || (ld_bf16 % 8 == 0 && ld_bf16 >= (F + 7) / 8 * 8 && ((uintptr_t)feat_bf16 & 15) == 0);
+  const bool bf16_ok = !feat_bf16 || (ld_bf16 % 8 == 0 && ld_bf16 >= (Fout + 7) / 8 * 8 && ((uintptr_t)feat_bf16 & 15) == 0);
   if (gen >= 2 && csmem <= (size_t)kCmvn2MaxSmem && bf16_ok) {
-    frontend_cmvn2_kernel<<<dim3(B, (F + 7) / 8), 256, csmem, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, stft ? 1 : 0,
+    frontend_cmvn2_kernel<<<dim3(B, (F + 7) / 8), 256, csmem, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, stft ? 1 : 0, delta,
                                                                   (uint16_t*)feat_bf16, ld_bf16);
     return check_launch("frontend_cmvn2_kernel");
   }
+  DL_CHECK_ARG(delta == 0, "frontend: delta features need ld_bf16 %% 8 == 0 >= ceil8(F (1 + delta)), a 16-byte aligned feat_bf16 and T <= %d", kCmvn2MaxSmem / 32);
   DL_CHECK_ARG(!stft, "frontend: stft needs ld_bf16 %% 8 == 0, a 16-byte aligned feat_bf16 and T <= %d", kCmvn2MaxSmem / 32);
   frontend_cmvn_kernel<<<dim3(B, (F + 7) / 8), 256, 0, s>>>(feat_f32, lengths, nsamp, T, F, cmvn, (uint16_t*)feat_bf16, ld_bf16);
   return check_launch("frontend_cmvn_kernel");

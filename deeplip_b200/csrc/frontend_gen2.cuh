@@ -45,11 +45,13 @@ __host__ __device__ constexpr int frames2_smem_floats(int F) {
 
 // grid (ceil(T/16), B); block 256 = 8 warps.  The block stages its 2912 (pre-emphasised / reflect-padded) samples in
 // shared memory once; each warp transforms frames t0, t0+1 as ONE complex FFT held in registers (16 points per lane,
-// three radix-8 passes); results of the 16 frames are staged and leave as 64-byte row segments of feat (B, F, T) f32.
+// three radix-8 passes); results of the 16 frames are staged and leave as 64-byte row segments of rows [0, F) of
+// feat (B, feat_rows, T) f32.
 template <bool kStft>
 __global__ void __launch_bounds__(256, 2) frontend_frames2_kernel(const float* __restrict__ wav,
                                                                   const int32_t* __restrict__ lengths, int nsamp, int T,
-                                                                  FrontendTables tb, float* __restrict__ feat) {
+                                                                  FrontendTables tb, float* __restrict__ feat,
+                                                                  int feat_rows) {
   extern __shared__ __align__(16) float smf[];
   Cx<float>* S = reinterpret_cast<Cx<float>*>(smf);            // 8 warps x 576
   Cx<float>* tw = S + 8 * kFftScratch;                         // 512
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(256, 2) frontend_frames2_kernel(const float* _
     }
   }
   __syncthreads();
-  float* out = feat + (size_t)b * F * T;
+  float* out = feat + (size_t)b * feat_rows * T;          // feat_rows = F (1 + delta order): rows of one utterance
   for (int i = tid; i < F * kBlkFrames; i += 256) {
     const int f = i >> 4, tt = i & 15;
     if (tblk + tt < T) out[(size_t)f * T + tblk + tt] = ostage[f * kOPitch + tt];
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(256, 2) frontend_frames2_kernel(const float* _
 // statistics and the two outputs -- f32 rows in place and 16-byte (8-channel) pieces of the channels-last bf16 copy the
 // TDNN consumes.  Same summation order as frontend_cmvn_kernel (bitwise identical results).
 __global__ void __launch_bounds__(256) frontend_cmvn2_kernel(float* __restrict__ feat, const int32_t* __restrict__ lengths,
-                                                             int nsamp, int T, int F, int cmvn, int stft,
+                                                             int nsamp, int T, int F, int cmvn, int stft, int delta,
                                                              uint16_t* __restrict__ out_bf16, int ld) {
   extern __shared__ __align__(16) float rows[];      // [8][T]
   const int b = blockIdx.x, f0 = blockIdx.y * 8;
@@ -260,10 +262,11 @@ __global__ void __launch_bounds__(256) frontend_cmvn2_kernel(float* __restrict__
   const int len = lengths ? max(0, min(lengths[b], nsamp)) : nsamp;
   int nfr = stft ? 1 + len / kFrameStep : (len <= kFrameLen ? 1 : 1 + (len - kFrameLen + kFrameStep - 1) / kFrameStep);
   nfr = min(nfr, T);
+  const int Fout = F * (1 + delta);                  // rows of one utterance: [feat | delta(feat, 1) | delta(feat, 2)]
   const int f = f0 + warp;
   float* srow = rows + warp * T;
   if (f < F) {
-    float* row = feat + ((size_t)b * F + f) * T;
+    float* row = feat + ((size_t)b * Fout + f) * T;
     float s = 0.f;
     for (int t = lane; t < T; t += 32) {
       const float v = row[t];
@@ -287,20 +290,52 @@ __global__ void __launch_bounds__(256) frontend_cmvn2_kernel(float* __restrict__
     for (int t = lane; t < T; t += 32) srow[t] = 0.f;
   }
   __syncthreads();
-  if (out_bf16) {
-    uint16_t* ob = out_bf16 + (size_t)b * T * ld;
-    for (int t = threadIdx.x; t < T; t += 256) {
-      uint4 o;
-      o.x = pack_bf16x2(rows[t], rows[T + t]);
-      o.y = pack_bf16x2(rows[2 * T + t], rows[3 * T + t]);
-      o.z = pack_bf16x2(rows[4 * T + t], rows[5 * T + t]);
-      o.w = pack_bf16x2(rows[6 * T + t], rows[7 * T + t]);
-      *reinterpret_cast<uint4*>(ob + (size_t)t * ld + f0) = o;
+  uint16_t* ob = out_bf16 ? out_bf16 + (size_t)b * T * ld : nullptr;
+  if (delta > 0 && f < F) {
+    // python_speech_features.delta(feat, N) of the NORMALISED features, N = 1 and N = 2 (`_delta`, datasets.py:217-225):
+    // sum_n n (f[t+n] - f[t-n]) / (2 sum_n n^2) with the edges repeated; the padding frames of a ragged batch stay zero
+    for (int k = 1; k <= delta; ++k) {
+      float* drow = feat + ((size_t)b * Fout + k * F + f) * T;
+      for (int t = lane; t < T; t += 32) {
+        float d = 0.f;
+        if (t < nfr) {
+          const float p1 = srow[min(t + 1, nfr - 1)], m1 = srow[max(t - 1, 0)];
+          if (k == 1) d = (p1 - m1) * 0.5f;
+          else d = ((p1 - m1) + 2.f * (srow[min(t + 2, nfr - 1)] - srow[max(t - 2, 0)])) * 0.1f;
+        }
+        drow[t] = d;
+        if (ob) ob[(size_t)t * ld + k * F + f] = (uint16_t)(pack_bf16x2(d, 0.f) & 0xffffu);
+      }
     }
-    const int g0 = (F + 7) >> 3, ng = (ld >> 3) - g0;          // zero the padded channel groups
+  }
+  if (ob) {
+    if (delta == 0 || f0 + 8 <= F) {                 // 8 channels of one frame per 16-byte store
+      for (int t = threadIdx.x; t < T; t += 256) {
+        uint4 o;
+        o.x = pack_bf16x2(rows[t], rows[T + t]);
+        o.y = pack_bf16x2(rows[2 * T + t], rows[3 * T + t]);
+        o.z = pack_bf16x2(rows[4 * T + t], rows[5 * T + t]);
+        o.w = pack_bf16x2(rows[6 * T + t], rows[7 * T + t]);
+        *reinterpret_cast<uint4*>(ob + (size_t)t * ld + f0) = o;
+      }
+    } else {                                         // partial last group next to the delta channels: element stores
+      for (int i = threadIdx.x; i < T * (F - f0); i += 256) {
+        const int t = i / (F - f0), r = i - t * (F - f0);
+        ob[(size_t)t * ld + f0 + r] = (uint16_t)(pack_bf16x2(rows[r * T + t], 0.f) & 0xffffu);
+      }
+    }
+    // zero the padded channels: whole groups of 8 from ceil8(Fout) on (with delta, also the tail of Fout's own group)
+    const int g0 = (Fout + 7) >> 3, ng = (ld >> 3) - g0;
     for (int i = blockIdx.y * 256 + threadIdx.x; i < T * ng; i += 256 * gridDim.y) {
       const int t = i / ng, g = g0 + i - t * ng;
       *reinterpret_cast<uint4*>(ob + (size_t)t * ld + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (delta > 0 && blockIdx.y == 0) {
+      const int tail = min(ld, g0 * 8) - Fout;
+      for (int i = threadIdx.x; i < T * tail; i += 256) {
+        const int t = i / tail;
+        ob[(size_t)t * ld + Fout + (i - t * tail)] = 0;
+      }
     }
   }
 }

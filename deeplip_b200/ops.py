@@ -54,9 +54,10 @@ def num_frames(nsamp, frame_len=400, step=160, feat_type='mfcc'):
 FEAT_KINDS = {'mfcc': 0, 'fbank': 1, 'logfbank': 2, 'stft': 3}
 
 
-def frontend_features(wav, feat_type='mfcc', n_feat=24, cmvn=True, lengths=None, ld=None):
+def frontend_features(wav, feat_type='mfcc', n_feat=24, cmvn=True, lengths=None, ld=None, delta=False):
     """wav (B, nsamp) f32 -> (feat_f32 (B,F,T), feat_bf16 (B,T,ld)).  feat_type 'stft' (n_fft 512, hop 160,
-    Hann 400; models/fusion_models/datasets.py:237-241) has n_feat = 257."""
+    Hann 400; models/fusion_models/datasets.py:237-241) has n_feat = 257.  delta (True = the reference's order 2, or
+    0 / 1 / 2): `_delta` (:217-225) appends delta(feat, 1) and delta(feat, 2): F becomes n_feat * (1 + order)."""
     _need_cuda(wav, lengths)
     if feat_type not in FEAT_KINDS:
         raise NotImplementedError('Other features are not implemented!')      # datasets.py:243
@@ -65,11 +66,13 @@ def frontend_features(wav, feat_type='mfcc', n_feat=24, cmvn=True, lengths=None,
     if feat_type == 'stft':
         n_feat = 257
     T = num_frames(nsamp, feat_type=feat_type)
-    ld = ld or ceil_to(n_feat, 64)
-    f32 = torch.empty((B, n_feat, T), device=wav.device, dtype=torch.float32)
+    order = 2 if delta is True else int(delta)
+    n_out = n_feat * (1 + order)
+    ld = ld or ceil_to(n_out, 64)
+    f32 = torch.empty((B, n_out, T), device=wav.device, dtype=torch.float32)
     b16 = torch.empty((B, T, ld), device=wav.device, dtype=torch.bfloat16)
     st = _lib.lib().dl_frontend_features(_ptr(wav), _ptr(lengths), B, nsamp, FEAT_KINDS[feat_type], n_feat,
-                                         int(bool(cmvn)), _ptr(b16), ld, _ptr(f32), T, _stream())
+                                         int(bool(cmvn)), order, _ptr(b16), ld, _ptr(f32), T, _stream())
     _lib.check(st, 'dl_frontend_features')
     return f32, b16
 

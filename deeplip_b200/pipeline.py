@@ -18,16 +18,16 @@ class AVExtractor:
     FUSIONS = ('concat', 'concat_np', 'linear', 'lowfer', 'audio', 'video')
 
     def __init__(self, audio_model, video_model, fusion='concat', fusion_model=None, feat_type='mfcc',
-                 n_feat=24, cmvn=True, l2norm=False):
+                 n_feat=24, cmvn=True, l2norm=False, delta=False):
         if fusion not in self.FUSIONS:
             raise NotImplementedError('fusion %r (have %s)' % (fusion, ', '.join(self.FUSIONS)))
         self.audio, self.video = audio_model, video_model
         self.fusion, self.fusion_model = fusion, fusion_model
-        self.feat_type, self.n_feat, self.cmvn, self.l2norm = feat_type, n_feat, cmvn, l2norm
+        self.feat_type, self.n_feat, self.cmvn, self.l2norm, self.delta = feat_type, n_feat, cmvn, l2norm, delta
 
     def audio_embedding(self, wav, wav_lengths=None):
         """wav (B,nsamp) f32 CUDA -> xv (B,E) f32 (LMCL convention: 2nd fc output, train_fusion.py:390)."""
-        _, feat = ops.frontend_features(wav, self.feat_type, self.n_feat, self.cmvn, lengths=wav_lengths)
+        _, feat = ops.frontend_features(wav, self.feat_type, self.n_feat, self.cmvn, lengths=wav_lengths, delta=self.delta)
         frames = None
         if wav_lengths is not None:
             if self.feat_type == 'stft':

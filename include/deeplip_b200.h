@@ -54,6 +54,9 @@ long long dl_launch_count(void);
  *           3 = stft(n_fft=512, hop 160, periodic Hann 400 centred in 512, center=True): F = 257 rows of
  *               log1p|S|; the centre padding is librosa's pre-0.10 default `reflect` unless
  *               dl_set_option("stft_pad", 1) selects zeros (librosa >= 0.10).
+ *     delta: 0, or the order of `_delta` (datasets.py:217-225; the reference always uses 2): python_speech_features.
+ *       delta(feat, N) for N = 1 .. delta of the (normalised) features is appended, feat_f32 is then
+ *       (B, F (1 + delta), T) = [feat | delta N=1 | delta N=2] and feat_bf16 carries the same F (1 + delta) channels.
  *     lengths: per-utterance valid sample counts (device int32, may be NULL = nsamp for all);
  *     T must equal 1 + ceil((nsamp - 400) / 160) for the padded length nsamp (16 kHz, 25/10 ms), or
  *     1 + nsamp / 160 for kind 3.
@@ -61,7 +64,7 @@ long long dl_launch_count(void);
  *     kinds 0-2 only), kept for A/B measurements; the default (2) holds the FFT in registers.
  */
 int dl_frontend_features(const float* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
-                         int cmvn, void* feat_bf16, int ld_bf16, float* feat_f32, int T, void* stream);
+                         int cmvn, int delta, void* feat_bf16, int ld_bf16, float* feat_f32, int T, void* stream);
 
 /* (B, C, T) f32 -> (B, T, ldc) bf16 channels-last, zero padded: the layout change in front of the
  * TDNN for callers that bring their own features (models/audio_models/tdnn.py:89 input). */

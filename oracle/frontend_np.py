@@ -132,6 +132,20 @@ def stft_logmag(sig, n_fft=512, hop=160, win_length=400, pad_mode='reflect'):
     return np.log1p(np.abs(np.fft.rfft(y[idx] * win[None, :], n_fft, axis=1)))
 
 
+def delta(feat, N):
+    """python_speech_features.delta: sum_n n (f[t+n] - f[t-n]) / (2 sum_n n^2), edges repeated."""
+    denom = 2.0 * sum(i * i for i in range(1, N + 1))
+    padded = np.pad(feat, ((N, N), (0, 0)), mode='edge')
+    w = np.arange(-N, N + 1, dtype=np.float64)
+    return np.stack([w @ padded[t:t + 2 * N + 1] for t in range(feat.shape[0])]) / denom
+
+
+def delta_stack(feat, order=2):
+    """models/fusion_models/datasets.py:217-225 (`_delta`): [feat, delta(feat, 1), delta(feat, 2)] side by side."""
+    parts = [feat] + [delta(feat, n) for n in range(1, order + 1)]
+    return np.hstack(parts)
+
+
 def cmvn(feat):
     """models/fusion_models/datasets.py:214-215 (biased std, +2e-12)."""
     return (feat - feat.mean(axis=0)) / (feat.std(axis=0) + 2e-12)
@@ -156,5 +170,5 @@ def extract_feature(sig, rate=16000, feat_type='mfcc', opts=None):
     if o['normalize']:
         f = cmvn(f)
     if o['delta']:
-        raise NotImplementedError("delta features are off in every shipped config")
+        f = delta_stack(f, 2 if o['delta'] is True else int(o['delta']))
     return f.astype(np.float32)

@@ -2,8 +2,8 @@
 // per CUDA thread, std::barrier for __syncthreads / __syncwarp, an exchange buffer for the warp shuffles.  Test
 // infrastructure only (tests/test_host_logic.py::test_frontend_kernel_source_on_cpu_threads compares the output with
 // oracle/frontend_np.py); it checks index arithmetic, framing, tables and staging -- not memory-model behaviour.
-//   usage: frontend_cpu_emul kind F nsamp B pad_mode cmvn wav.f32 lengths.i32|- out.bin
-//   out.bin = feat_f32 (B,F,T) float32 followed by feat_bf16 (B,T,ld) uint16, ld = ceil64(F)
+//   usage: frontend_cpu_emul kind F nsamp B pad_mode cmvn+10*delta wav.f32 lengths.i32|- out.bin
+//   out.bin = feat_f32 (B,Fout,T) float32 followed by feat_bf16 (B,T,ld) uint16, Fout = F (1 + delta), ld = ceil64(Fout)
 //   usage: frontend_cpu_emul prepass is_u8 frames H W Hraw Wraw in.bin out.bin     (stem_prepass.cuh; mean .421 std .165)
 //   out.bin = (frames, H+8, pitch) uint16 bf16, pitch = ceil8(W+8)
 //   usage: frontend_cpu_emul linear M C Cout ldx ldw with_bf16 with_scale2 in.bin out.bin     (linear_small.cuh)
@@ -188,12 +188,12 @@ int main(int argc, char** argv) {
   if (argc != 10) return 2;
   if (!strcmp(argv[1], "prepass")) return prepass_main(argv);
   const int kind = atoi(argv[1]), F = atoi(argv[2]), nsamp = atoi(argv[3]), B = atoi(argv[4]), pad = atoi(argv[5]),
-            cmvn = atoi(argv[6]);
+            cmvn = atoi(argv[6]) % 10, delta = atoi(argv[6]) / 10, Fout = F * (1 + delta);
   const bool stft = kind == 3;
   const int T = stft ? 1 + nsamp / kFrameStep
                      : (nsamp <= kFrameLen ? 1 : 1 + (nsamp - kFrameLen + kFrameStep - 1) / kFrameStep);
-  const int ld = (F + 63) / 64 * 64;
-  std::vector<float> wav((size_t)B * nsamp), feat((size_t)B * F * T, -777.f);
+  const int ld = (Fout + 63) / 64 * 64;
+  std::vector<float> wav((size_t)B * nsamp), feat((size_t)B * Fout * T, -777.f);
   std::vector<uint16_t> b16((size_t)B * T * ld, 0x7fc0);
   std::vector<int32_t> len(B);
   FILE* f = fopen(argv[7], "rb");
@@ -213,9 +213,9 @@ int main(int argc, char** argv) {
   const float* w = wav.data();
   float* ft = feat.data();
   uint16_t* ob = b16.data();
-  if (stft) launch((T + kBlkFrames - 1) / kBlkFrames, B, [&] { frontend_frames2_kernel<true>(w, lengths, nsamp, T, tb, ft); });
-  else launch((T + kBlkFrames - 1) / kBlkFrames, B, [&] { frontend_frames2_kernel<false>(w, lengths, nsamp, T, tb, ft); });
-  launch(B, (F + 7) / 8, [&] { frontend_cmvn2_kernel(ft, lengths, nsamp, T, F, cmvn, stft ? 1 : 0, ob, ld); });
+  if (stft) launch((T + kBlkFrames - 1) / kBlkFrames, B, [&] { frontend_frames2_kernel<true>(w, lengths, nsamp, T, tb, ft, Fout); });
+  else launch((T + kBlkFrames - 1) / kBlkFrames, B, [&] { frontend_frames2_kernel<false>(w, lengths, nsamp, T, tb, ft, Fout); });
+  launch(B, (F + 7) / 8, [&] { frontend_cmvn2_kernel(ft, lengths, nsamp, T, F, cmvn, stft ? 1 : 0, delta, ob, ld); });
   f = fopen(argv[9], "wb");
   fwrite(feat.data(), 4, feat.size(), f);
   fwrite(b16.data(), 2, b16.size(), f);

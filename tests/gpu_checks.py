@@ -328,7 +328,8 @@ def scoring_case(n_utt=500, D=1024, n_trials=3000, seed=0):
     return out
 
 
-def frontend_case(B=3, nsamp=16000, feat_type='mfcc', n_feat=24, seed=0, lengths=None, gen=2, stft_pad='reflect'):
+def frontend_case(B=3, nsamp=16000, feat_type='mfcc', n_feat=24, seed=0, lengths=None, gen=2, stft_pad='reflect',
+                  delta=0):
     """K1 against oracle/frontend_np.py; gen selects the kernel generation (dl_set_option("frontend"))."""
     from deeplip_b200 import _lib
     wav = synth.speech_like_audio(list(range(B)), nsamp=nsamp, seed=seed + 1)
@@ -336,16 +337,17 @@ def frontend_case(B=3, nsamp=16000, feat_type='mfcc', n_feat=24, seed=0, lengths
     _lib.set_option('frontend', gen)
     _lib.set_option('stft_pad', 0 if stft_pad == 'reflect' else 1)
     try:
-        f32, b16 = ops.frontend_features(torch.from_numpy(wav).to(DEV), feat_type, n_feat, lengths=ln)
+        f32, b16 = ops.frontend_features(torch.from_numpy(wav).to(DEV), feat_type, n_feat, lengths=ln, delta=delta)
         torch.cuda.synchronize()
     finally:
         _lib.set_option('frontend', 2)
         _lib.set_option('stft_pad', 0)
     if feat_type == 'stft':
         n_feat = 257
+    opts = dict(num_cep=n_feat, num_bin=n_feat, pad_mode=stft_pad, delta=delta)
+    n_feat = n_feat * (1 + (2 if delta is True else int(delta)))          # rows incl. the delta features
     assert f32.shape[1] == n_feat and b16.shape[2] % 64 == 0
     assert float(b16[:, :, n_feat:].float().abs().max()) == 0.0 if b16.shape[2] > n_feat else True
-    opts = dict(num_cep=n_feat, num_bin=n_feat, pad_mode=stft_pad)
     out = {'abs': 0.0}
     for i in range(B):
         n = nsamp if lengths is None else lengths[i]

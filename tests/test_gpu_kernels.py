@@ -95,6 +95,9 @@ def test_scoring_empty_list():
                                 dict(feat_type='stft'), dict(feat_type='stft', stft_pad='constant', B=2, nsamp=48000),
                                 dict(feat_type='stft', B=3, nsamp=20000, lengths=[20000, 12345, 700]),
                                 dict(B=2, nsamp=160000, lengths=[160000, 51234]),
-                                dict(feat_type='logfbank', n_feat=60, B=2, nsamp=30000, lengths=[401, 30000])])
+                                dict(feat_type='logfbank', n_feat=60, B=2, nsamp=30000, lengths=[401, 30000]),
+                                dict(delta=True, B=3, nsamp=20000, lengths=[20000, 12345, 300]),
+                                dict(delta=2, feat_type='logfbank', n_feat=60), dict(delta=1, n_feat=13),
+                                dict(delta=True, feat_type='stft', B=2, nsamp=8000)])
 def test_frontend(kw):
     G.frontend_case(**kw)

@@ -44,12 +44,14 @@ def test_argument_validation_without_touching_the_gpu():
     d2.split_channel, d2.y_split = 256, 0                      # ... and needs the second output
     assert l.dl_conv_igemm_bf16(one, one, one, one, one, None, one, None, None, None, ctypes.byref(d2), None) == -1
     assert b'y_split' in l.dl_last_error()
-    assert l.dl_frontend_features(one, None, 1, 48000, 0, 24, 1, None, 64, one, 298, None) == -1
+    assert l.dl_frontend_features(one, None, 1, 48000, 0, 24, 1, 0, None, 64, one, 298, None) == -1
     assert b'299' in l.dl_last_error()
-    assert l.dl_frontend_features(one, None, 1, 48000, 3, 257, 1, None, 320, one, 299, None) == -1      # stft framing
+    assert l.dl_frontend_features(one, None, 1, 48000, 3, 257, 1, 0, None, 320, one, 299, None) == -1   # stft framing
     assert b'301' in l.dl_last_error()
-    assert l.dl_frontend_features(one, None, 1, 48000, 3, 24, 1, None, 64, one, 301, None) == -1
+    assert l.dl_frontend_features(one, None, 1, 48000, 3, 24, 1, 0, None, 64, one, 301, None) == -1
     assert b'257' in l.dl_last_error()
+    assert l.dl_frontend_features(one, None, 1, 48000, 0, 24, 1, 3, None, 128, one, 299, None) == -1      # delta order
+    assert b'delta' in l.dl_last_error()
 
 
 def test_fft512_phase_functions_on_cpu(tmp_path):
@@ -74,11 +76,14 @@ def test_no_cpu_fallback():
         audio.extract_embedding(torch.zeros(1, 24, 100))
 
 
-@pytest.mark.parametrize('feat_type,F,nsamp,lengths,pad', [
-    ('mfcc', 24, 16000, None, 'reflect'), ('logfbank', 60, 8000, None, 'reflect'), ('fbank', 24, 8000, None, 'reflect'),
-    ('mfcc', 24, 20000, [20000, 12345, 300], 'reflect'), ('stft', 257, 8000, None, 'reflect'),
-    ('stft', 257, 8000, None, 'constant'), ('stft', 257, 20000, [20000, 12345, 700], 'reflect')])
-def test_frontend_kernel_source_on_cpu_threads(tmp_path, feat_type, F, nsamp, lengths, pad):
+@pytest.mark.parametrize('feat_type,F,nsamp,lengths,pad,delta', [
+    ('mfcc', 24, 16000, None, 'reflect', 0), ('logfbank', 60, 8000, None, 'reflect', 0),
+    ('fbank', 24, 8000, None, 'reflect', 0), ('mfcc', 24, 20000, [20000, 12345, 300], 'reflect', 0),
+    ('stft', 257, 8000, None, 'reflect', 0), ('stft', 257, 8000, None, 'constant', 0),
+    ('stft', 257, 20000, [20000, 12345, 700], 'reflect', 0),
+    ('mfcc', 24, 20000, [20000, 12345, 300], 'reflect', 2), ('logfbank', 60, 8000, None, 'reflect', 2),
+    ('mfcc', 13, 6000, None, 'reflect', 1), ('stft', 257, 6000, [6000, 1000], 'reflect', 2)])
+def test_frontend_kernel_source_on_cpu_threads(tmp_path, feat_type, F, nsamp, lengths, pad, delta):
     """The generation-2 front-end kernels are compiled FROM THEIR CUDA SOURCE for the CPU (one OS thread per CUDA
     thread, tests/frontend_cpu_emul.cpp) and compared with the oracle: framing, FFT, mel/DCT tables, ragged lengths,
     stft padding, CMVN and the bf16 channels-last copy are all checked without a GPU."""
@@ -95,17 +100,18 @@ def test_frontend_kernel_source_on_cpu_threads(tmp_path, feat_type, F, nsamp, le
         lf = str(tmp_path / 'len.i32')
         np.asarray(lengths, np.int32).tofile(lf)
     kind = {'mfcc': 0, 'fbank': 1, 'logfbank': 2, 'stft': 3}[feat_type]
-    out = subprocess.run([exe, str(kind), str(F), str(nsamp), str(B), '0' if pad == 'reflect' else '1', '1',
-                          str(tmp_path / 'wav.f32'), lf, str(tmp_path / 'out.bin')], check=True, capture_output=True,
-                         text=True).stdout.split()
+    out = subprocess.run([exe, str(kind), str(F), str(nsamp), str(B), '0' if pad == 'reflect' else '1',
+                          str(1 + 10 * delta), str(tmp_path / 'wav.f32'), lf, str(tmp_path / 'out.bin')], check=True,
+                         capture_output=True, text=True).stdout.split()
     T, ld = int(out[1]), int(out[3])
     raw = np.fromfile(str(tmp_path / 'out.bin'), dtype=np.uint8)
+    Fb, F = F, F * (1 + delta)                           # F: rows of one utterance incl. the delta features
     f32 = raw[:B * F * T * 4].view(np.float32).reshape(B, F, T)
     bf = (raw[B * F * T * 4:].view(np.uint16).reshape(B, T, ld).astype(np.uint32) << 16).view(np.float32)
     for i in range(B):
         n = nsamp if lengths is None else lengths[i]
         ref = frontend_np.extract_feature(wav[i, :n].astype(np.float64), 16000, feat_type,
-                                          dict(num_cep=F, num_bin=F, pad_mode=pad)).T
+                                          dict(num_cep=Fb, num_bin=Fb, pad_mode=pad, delta=delta)).T
         assert np.abs(f32[i][:, :ref.shape[1]] - ref).max() < 2e-3
         assert np.all(f32[i][:, ref.shape[1]:] == 0)                     # padding frames of a ragged batch
         assert np.abs(bf[i, :ref.shape[1], :F].T - ref).max() < 5e-2
