@@ -1,8 +1,7 @@
 // Stem pre-pass, generation 2 (V1 fused: x/255, centre crop, (x-mean)/std; models/video_models/dataloaders.py:19-24):
 // uint8 crops or normalised f32 frames -> zero-bordered bf16 frames xp (frames, H+8, pitch), row iy+3, column ix+3.
 // One block per frame; a thread writes 8 consecutive columns (16 B) from three aligned 32-bit loads of the raw row
-// (funnel-shifted to the crop offset) -- no 64-bit index divisions, 2.7x fewer load instructions than generation 1;
-// the interior of a frame (10 of 12 column groups x 88 of 96 rows) runs in a loop of its own without bounds checks.
+// (funnel-shifted to the crop offset) -- no 64-bit index divisions, 2.7x fewer load instructions than generation 1.
 // `lengths` (may be NULL): valid frames per clip of T frames; later frames are written as zeros.
 // Free of CUDA-runtime dependencies so that tests/frontend_cpu_emul.cpp can run this source on CPU threads.
 // The includer provides: pack_bf16x2(float, float), __ldg, __funnelshift_r, uint4.
@@ -24,37 +23,9 @@ __global__ void __launch_bounds__(256) stem_prepass2_kernel(const void* __restri
   const int groups = pitch >> 3;
   const int n = rows * groups;
   uint16_t* of = xp + (size_t)f * rows * pitch;
-  // ---- interior of a live u8 frame: column groups whose 8 pixels and 3 source words all lie inside the crop / raw row.
-  // Every lane of this loop runs the same straight-line code (an "interior" branch inside the general loop below would
-  // diverge in every warp, consecutive lanes holding different groups: measured 36 -> 41 us).
-  const bool fast = is_u8 && aligned4 && !dead && W >= 13;
-  const int g_lo = 1;
-  int g_hi = g_lo;                                   // exclusive
-  if (fast) {
-    g_hi = (W - 5) / 8 + 1;                          // 8 g - 3 + 8 <= W
-    while (g_hi > g_lo && ((8 * (g_hi - 1) - 3 + dw) & ~3) + 12 > Wraw) --g_hi;
-    const int ni = g_hi - g_lo;
-    for (int i = threadIdx.x; i < H * ni; i += 256) {
-      const int iy = i / ni, g = g_lo + i - iy * ni;
-      const uint8_t* src = static_cast<const uint8_t*>(x) + ((size_t)f * Hraw + (iy + dh)) * Wraw;
-      const int c0 = g * 8 - 3 + dw, wb = c0 & ~3, sh = 8 * (c0 - wb);
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + wb);
-      const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-      const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf((float)(((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu), u8_scale, u8_bias);
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(of + (size_t)(iy + 3) * pitch + g * 8) = o;
-    }
-  }
-  // ---- everything else: border rows and groups, dead frames, f32 input, unaligned raw rows
   for (int i = threadIdx.x; i < n; i += 256) {
     const int row = i / groups, g = i - row * groups;
     const int iy = row - 3, ix0 = g * 8 - 3;
-    if (fast && iy >= 0 && iy < H && g >= g_lo && g < g_hi) continue;       // written above
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
