@@ -158,17 +158,51 @@ def oracle_av_extract_batched(raw, wav, sda, sdv, aopts):
         return models_ref.concat_fusion(xv, em)
 
 
+def pin_cpu_threads():
+    """NumPy's OpenBLAS pool (pthreads, spin-waiting) and torch's OpenMP pool oversubscribe the cores when both run
+    at full width: the MFCC's small matmuls wake `cores` BLAS threads between every torch conv (measured: 6.9 utt/s
+    -> 18 utt/s on 8 cores, 6.3 -> 28 on the bench box, just by pinning BLAS).  The CPU arm therefore runs NumPy's
+    BLAS on ONE thread whatever the launcher's environment says and sizes torch's pool explicitly."""
+    info = {'OMP_NUM_THREADS': os.environ.get('OMP_NUM_THREADS'), 'OPENBLAS_NUM_THREADS': os.environ.get('OPENBLAS_NUM_THREADS'),
+            'MKL_NUM_THREADS': os.environ.get('MKL_NUM_THREADS')}
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=1, user_api='blas')
+        info['numpy_blas_threads'] = 1
+    except Exception as e:          # threadpoolctl is in the image; say so if that ever changes
+        info['numpy_blas_threads'] = 'unpinned (%s)' % type(e).__name__
+    return info
+
+
+def best_torch_threads(fn, cores):
+    """Time `fn` at torch thread counts {1, cores/2, cores} (one call each after one untimed call) and keep the
+    fastest: the reference arm gets all the host threads it can actually use."""
+    cand = sorted({1, max(1, cores // 2), cores})
+    torch.set_num_threads(cores)
+    fn()
+    res = {}
+    for n in cand:
+        torch.set_num_threads(n)
+        t0 = time.perf_counter()
+        fn()
+        res[n] = time.perf_counter() - t0
+    best = min(res, key=res.get)
+    torch.set_num_threads(best)
+    return best, {str(k): round(v, 4) for k, v in res.items()}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     from deeplip_b200 import synth
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    env = pin_cpu_threads()
     aopts = synth.audio_opts('etdnn', 'statistic')
     sda = synth.make_audio_state_dict(aopts, seed=1)
     sdv = synth.make_video_state_dict(seed=1)
     per_step = args.ref_utts
     raw, wav = synth_batch(per_step, seed=1)
+    threads, sweep = best_torch_threads(lambda: oracle_av_extract(raw[:1], wav[:1], sda, sdv, aopts), cores)
     for _ in range(max(1, min(args.warmup, 2))):
         oracle_av_extract(raw[:1], wav[:1], sda, sdv, aopts)
     t0 = time.perf_counter()
@@ -180,9 +214,11 @@ def run_reference(args, rank):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args, per_gpu_batch=per_step),
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'host_cores': cores, 'kind': 'port',
+                             'thread_sweep_s_per_utt': sweep, 'env': env,
                              'sample': '%d utterances/step x %d steps, per-utterance B=1 loop like '
-                                       'train_fusion.py:386-410 (oracle/ port of the reference modules)' %
+                                       'train_fusion.py:386-410 (oracle/ port of the reference modules); torch threads = '
+                                       'best of {1, cores/2, cores}, NumPy BLAS pinned to 1 thread' %
                                        (per_step, args.steps)},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
@@ -425,11 +461,11 @@ def run_ours(args, rank, world, local):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
+        cpu_env = pin_cpu_threads()
         aopts = synth.audio_opts('etdnn', 'statistic')
         sda, sdv = synth.make_audio_state_dict(aopts, seed=1), synth.make_video_state_dict(seed=1)
         raw, wav = host[0][0].numpy(), host[0][1].numpy()
-        oracle_av_extract(raw[:1], wav[:1], sda, sdv, aopts)
+        threads, sweep = best_torch_threads(lambda: oracle_av_extract(raw[:1], wav[:1], sda, sdv, aopts), cores)
         n, t0 = 0, time.perf_counter()
         ref_rows = []
         while n < B and (time.perf_counter() - t0 < 12.0 or n < 4):
@@ -443,11 +479,13 @@ def run_ours(args, rank, world, local):
         tb0 = time.perf_counter()
         ref_b = oracle_av_extract_batched(raw[:nb], wav[:nb], sda, sdv, aopts)
         dtb = time.perf_counter() - tb0
-        cpu = {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        cpu = {'value': n / dt, 'unit': UNIT, 'cores': threads, 'host_cores': cores, 'kind': 'port',
+               'thread_sweep_s_per_utt': sweep, 'env': cpu_env,
                'batched_b8_value': nb / dtb,
                'batched_b8_max_abs_vs_loop': float((ref_b.double() - ref[:nb]).abs().max()) if n >= nb else None,
                'sample': '%d of the %d utterances of batch 0, per-utterance B=1 loop (train_fusion.py:386-410) '
-                         'through oracle/ (torch fp32 CPU + NumPy MFCC)' % (n, B),
+                         'through oracle/ (torch fp32 CPU + NumPy MFCC); torch threads = best of {1, cores/2, cores}, '
+                         'NumPy BLAS pinned to 1 thread' % (n, B),
                'parity_min_cosine_vs_gpu': cos}
 
     total_gflop = (GFLOP_TRUNK_PER_UTT + GFLOP_STEM_PER_UTT + GFLOP_AUDIO_PER_UTT) * n_total

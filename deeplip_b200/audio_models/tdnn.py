@@ -131,14 +131,27 @@ class SpeakerEmbNet(nn.Module):
                             one=torch.ones(E, device=dev), lrelu=torch.full((E,), LRELU, device=dev))
         return self._pk
 
+    @property
+    def min_frames(self):
+        """Fewest feature frames an utterance needs: two must survive the valid convs (unbiased std)."""
+        return self.context_loss + 2
+
     def embed_ntc(self, x_ntc, lengths=None):
         """x_ntc: (B,T,ld) bf16 channels-last features; lengths: valid *input* frames (int32, CUDA)."""
         if self.training:
             raise RuntimeError('deeplip_b200.SpeakerEmbNet is inference-only: call .eval()')
         pk = self._packed()
+        if x_ntc.shape[1] - self.context_loss < 2:
+            # the reference's Conv1d raises on an input shorter than its kernel, and one surviving frame has no
+            # unbiased std; fail here instead of returning NaN embeddings
+            raise ValueError('utterance of %d feature frames is shorter than the TDNN receptive field (%d frames '
+                             'needed)' % (x_ntc.shape[1], self.min_frames))
         for blk in self.tdnn:
             x_ntc = blk.forward_ntc(x_ntc)
         if lengths is not None:
+            # Rows of a ragged batch shorter than `min_frames` cannot be detected here without a device sync: their
+            # pooled std is NaN (one frame) and so is their embedding.  Callers that own host lengths check them
+            # first (HostPipeline.run does; `min_frames` is the bound).
             lengths = (lengths - self.context_loss).clamp_(min=1).to(torch.int32)
         _, pooled = self.pooling.pool_ntc(x_ntc, self.trunk_out, lengths)          # (B, 2C) bf16
         B = pooled.shape[0]

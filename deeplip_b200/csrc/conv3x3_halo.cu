@@ -251,11 +251,13 @@ extern "C" int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, con
   DL_CHECK_ARG((long long)N * img_rows < (1ll << 31) / 16, "conv3x3_halo: too many rows");
   int st = require_sm100();
   if (st != DL_OK) return st;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_dev;
+  bool* configured = configured_dev.slot();
+  if (!configured) return fail(DL_ERR_CUDA, "conv3x3_halo: no current device");
+  if (!*configured) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "conv3x3_halo smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    *configured = true;
   }
   HaloParams p;
   p.rows_total = N * img_rows; p.img_rows = img_rows; p.H = H; p.W = W;

@@ -26,25 +26,25 @@ int check_launch(const char* what) {
   return DL_OK;
 }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
+  static PerDevice<int> sms;
+  int* s = sms.slot();
+  if (!s) return 0;
+  if (*s == 0) cudaDeviceGetAttribute(s, cudaDevAttrMultiProcessorCount, current_device());
+  return *s;
 }
 
 int require_sm100() {
-  static int major = -1;
-  if (major < 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return fail(DL_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
-    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  }
-  if (major != 10) return fail(DL_ERR_UNSUPPORTED, "deeplip_b200 needs an sm_100 device (found sm_%d0)", major);
+  static PerDevice<int> major;          // 0 = not queried yet
+  int* m = major.slot();
+  if (!m) return fail(DL_ERR_CUDA, "no CUDA device (cudaGetDevice failed or device index >= %d)", kMaxDevices);
+  if (*m == 0) cudaDeviceGetAttribute(m, cudaDevAttrComputeCapabilityMajor, current_device());
+  if (*m != 10) return fail(DL_ERR_UNSUPPORTED, "deeplip_b200 needs an sm_100 device (found sm_%d0)", *m);
   return DL_OK;
 }
 

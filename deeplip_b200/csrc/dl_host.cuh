@@ -11,8 +11,18 @@ namespace dl {
 int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);          // cudaGetLastError -> DL_OK / DL_ERR_CUDA
-int device_sm_count();
-int require_sm100();
+int current_device();      // cudaGetDevice, or -1
+int device_sm_count();     // of the current device
+int require_sm100();       // of the current device
+
+// Once-per-device host state (function attributes, constant tables): a process may drive several GPUs
+// (the reference's nn.DataParallel usage, a manual cuda:1 call), and each device needs its own setup.
+constexpr int kMaxDevices = 64;
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices] = {};
+  T* slot() { const int d = current_device(); return (d >= 0 && d < kMaxDevices) ? &v[d] : nullptr; }
+};
 int opt_pair();            // tuning switches (dl_set_option): CTA-pair kernels on / off
 int opt_dbg();
 int opt_frontend();        // 2 = register-resident radix-8 FFT front end (default), 1 = first-generation kernels

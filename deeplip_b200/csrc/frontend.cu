@@ -198,8 +198,10 @@ __global__ void __launch_bounds__(256) frontend_cmvn_kernel(float* __restrict__ 
 
 
 static int upload_twiddles() {
-  static bool done = false;
-  if (done) return DL_OK;
+  static PerDevice<bool> done_dev;
+  bool* done = done_dev.slot();
+  if (!done) return fail(DL_ERR_CUDA, "frontend: no current device");
+  if (*done) return DL_OK;
   float2 tw[kNfft / 2];
   for (int k = 0; k < kNfft / 2; ++k) {
     const double a = -2.0 * M_PI * (double)k / (double)kNfft;
@@ -207,7 +209,7 @@ static int upload_twiddles() {
   }
   cudaError_t e = cudaMemcpyToSymbol(c_twiddle, tw, sizeof(tw));
   if (e != cudaSuccess) return fail(DL_ERR_CUDA, "frontend twiddles: %s", cudaGetErrorString(e));
-  done = true;
+  *done = true;
   return DL_OK;
 }
 

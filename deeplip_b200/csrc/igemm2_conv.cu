@@ -271,12 +271,14 @@ template <int BLOCK_N, bool kResB, int TAPS>
 static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, cudaStream_t stream) {
   using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_dev;
+  bool* configured = configured_dev.slot();
+  if (!configured) return fail(DL_ERR_CUDA, "igemm2: no current device");
+  if (!*configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N, kResB, TAPS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "igemm2 smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    *configured = true;
   }
   const int super_tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
   int pairs = device_sm_count() / 2;

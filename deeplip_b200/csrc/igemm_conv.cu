@@ -208,12 +208,14 @@ static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
                         cudaStream_t stream) {
   using Cfg = IgemmCfg<BLOCK_N, kResB>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_dev;
+  bool* configured = configured_dev.slot();
+  if (!configured) return fail(DL_ERR_CUDA, "igemm: no current device");
+  if (!*configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm_conv_kernel<BLOCK_N, kResB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "igemm smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
+    *configured = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   int grid = device_sm_count();

@@ -495,11 +495,13 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   int grid = device_sm_count();
   if (grid <= 0) grid = 148;
   if (p.units < grid) grid = p.units;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static PerDevice<size_t> configured_dev;
+  size_t* configured = configured_dev.slot();
+  if (!configured) return fail(DL_ERR_CUDA, "stem: no current device");
+  if (smem > *configured) {
     cudaError_t e = cudaFuncSetAttribute(stem_conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
+    *configured = smem;
   }
   stem_conv3d_kernel<<<grid, kStemThreads, smem, cs>>>(mapW, mapX, p);
   return check_launch("stem_conv3d_kernel");

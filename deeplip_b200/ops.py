@@ -24,18 +24,61 @@ def _need_cuda(*ts):
             raise RuntimeError('deeplip_b200 ops need CUDA tensors (there is no CPU fallback)')
 
 
-_WS = {}
+class BufferCache:
+    """Persistent device buffers keyed by shape (stem workspace, the trunk's zero-padded activation layouts).
+
+    A buffer is never resized in place: a new shape gets a new buffer and the old one stays cached (LRU, `cap`
+    shapes), so raw pointers that an earlier call baked into a CUDA graph stay valid while the buffer is cached;
+    GraphedExtractor additionally pins what it captured with `recording()`, which keeps those tensors alive after an
+    eviction.  One model instance drives ONE stream at a time: two streams through the same cached buffers race
+    (as they would through the reference's in-place BatchNorm buffers)."""
+
+    def __init__(self, cap=8):
+        from collections import OrderedDict
+        self._d = OrderedDict()
+        self._cap = cap
+        self._rec = None
+
+    def get(self, key, make):
+        buf = self._d.get(key)
+        if buf is None:
+            buf = make()
+            self._d[key] = buf
+            while len(self._d) > self._cap:
+                self._d.popitem(last=False)
+        else:
+            self._d.move_to_end(key)
+        if self._rec is not None:
+            self._rec.append(buf)
+        return buf
+
+    def recording(self):
+        """Context manager: collects every buffer handed out inside it (returned list keeps them alive)."""
+        cache = self
+
+        class _Rec:
+            def __enter__(self):
+                self.prev, cache._rec = cache._rec, []
+                return cache._rec
+
+            def __exit__(self, *exc):
+                got, cache._rec = cache._rec, self.prev
+                if self.prev is not None:
+                    self.prev.extend(got)
+                return False
+        return _Rec()
+
+    def clear(self):
+        self._d.clear()
+
+
+BUFFERS = BufferCache()
 
 
 def _workspace(device, nbytes):
-    """Per-device scratch the C ABI asks the caller to own (grown on demand, reused across calls on the
-    same stream)."""
-    key = str(device)
-    buf = _WS.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _WS[key] = buf
-    return buf
+    """Per-device scratch the C ABI asks the caller to own, one buffer per size (see BufferCache)."""
+    return BUFFERS.get(('ws', str(device), int(nbytes)),
+                       lambda: torch.empty(int(nbytes), dtype=torch.uint8, device=device))
 
 
 def ceil_to(x, m):

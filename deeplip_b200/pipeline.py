@@ -77,14 +77,19 @@ class GraphedExtractor:
         self.video.copy_(video_example)
         side = torch.cuda.Stream(device=self.wav.device)
         side.wait_stream(torch.cuda.current_stream(self.wav.device))
-        with torch.cuda.stream(side):          # first calls build packed weights, set attributes, size caches
-            for _ in range(warmup):
-                self.ex.extract(self.wav, self.video)
-        torch.cuda.current_stream(self.wav.device).wait_stream(side)
-        torch.cuda.synchronize(self.wav.device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self.ex.extract(self.wav, self.video)
+        # The kernels' persistent buffers (stem workspace, zero-padded trunk layouts) are allocated outside the graph
+        # pool and their addresses are baked into the graph: hold references for the graph's lifetime, so that eager
+        # calls at other shapes (a dataset's tail batch) can neither free nor resize them (ops.BufferCache).
+        with ops.BUFFERS.recording() as pinned:
+            with torch.cuda.stream(side):      # first calls build packed weights, set attributes, size caches
+                for _ in range(warmup):
+                    self.ex.extract(self.wav, self.video)
+            torch.cuda.current_stream(self.wav.device).wait_stream(side)
+            torch.cuda.synchronize(self.wav.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self.ex.extract(self.wav, self.video)
+        self._pinned_buffers = list(pinned)
 
     @torch.no_grad()
     def extract(self, wav, video):
@@ -107,6 +112,9 @@ class HostPipeline:
     makes; the reference does one blocking `.to(device)` per clip (train_fusion.py:388, 399)."""
 
     def __init__(self, extractor, device='cuda', slots=2):
+        if slots < 2:
+            # with one slot the upload of batch k+1 would overwrite the slot batch k's kernels have not read yet
+            raise ValueError('HostPipeline needs slots >= 2 (the upload of batch k+1 overlaps the kernels of batch k)')
         self.ex = extractor
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -148,6 +156,11 @@ class HostPipeline:
         for bt in batches:
             if len(bt) not in (2, 4):
                 raise ValueError('HostPipeline batches are (wav, video) or (wav, video, wav_lengths, video_lengths)')
+            if len(bt) == 4 and self.ex.fusion != 'video' and hasattr(self.ex.audio, 'min_frames'):
+                nmin = int(bt[2].min())
+                if ops.num_frames(nmin, feat_type=self.ex.feat_type) < self.ex.audio.min_frames:
+                    raise ValueError('ragged batch holds an utterance of %d samples: shorter than the audio model\'s '
+                                     'receptive field (%d feature frames needed)' % (nmin, self.ex.audio.min_frames))
         main = torch.cuda.current_stream(self.device)
         for ev in self._free:
             ev.record(main)

@@ -253,28 +253,21 @@ class ResNet(nn.Module):
                 self.layer3[0].downsample is not None)
 
     def pitched_buffers(self, N, P, Q, ld, device):
-        """Two persistent (N, P, Q, ld) activation buffers (only the first ld/2 channels carry block outputs)."""
-        key = (N, P, Q, ld, str(device))
-        if getattr(self, '_pit_key', None) != key:
-            self._pit = [torch.zeros((N, P, Q, ld), device=device, dtype=torch.bfloat16) for _ in range(2)]
-            self._pit_key = key
-        return self._pit
+        """Two persistent (N, P, Q, ld) activation buffers (only the first ld/2 channels carry block outputs).
+        Cached per shape (ops.BufferCache): a new batch shape never frees buffers an earlier shape -- or a CUDA
+        graph captured at it -- still uses."""
+        return ops.BUFFERS.get(('pitched', id(self), N, P, Q, ld, str(device)), lambda: [
+            torch.zeros((N, P, Q, ld), device=device, dtype=torch.bfloat16) for _ in range(2)])
 
     def guarded_buffers(self, N, P, Q, device):
         """Persistent zeroed (N, P+1, Q+1, 128) buffers; the kernels never write the guard row / column."""
-        key = (N, P, Q, str(device))
-        if getattr(self, '_grd_key', None) != key:
-            self._grd = [torch.zeros((N, P + 1, Q + 1, 128), device=device, dtype=torch.bfloat16) for _ in range(3)]
-            self._grd_key = key
-        return self._grd
+        return ops.BUFFERS.get(('guarded', id(self), N, P, Q, str(device)), lambda: [
+            torch.zeros((N, P + 1, Q + 1, 128), device=device, dtype=torch.bfloat16) for _ in range(3)])
 
     def stacked_buffers(self, N, H, W, device, count):
         """Persistent zero-initialised (N, H+1, W, 64) activation buffers (padding rows are never written)."""
-        key = (N, H, W, str(device), count)
-        if getattr(self, '_stk_key', None) != key:
-            self._stk = [torch.zeros((N, H + 1, W, 64), device=device, dtype=torch.bfloat16) for _ in range(count)]
-            self._stk_key = key
-        return self._stk
+        return ops.BUFFERS.get(('stacked', id(self), N, H, W, str(device), count), lambda: [
+            torch.zeros((N, H + 1, W, 64), device=device, dtype=torch.bfloat16) for _ in range(count)])
 
     def forward_nhwc(self, x, stacked_H=None):
         """(N,H,W,64) bf16 -- or stacked rows (N,H+1,W,64) with stacked_H=H -- -> (N,P,Q,512) bf16, before the

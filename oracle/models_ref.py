@@ -1,7 +1,7 @@
 """fp32 PyTorch (CPU) restatement of the reference's model forwards, driven by a
 reference-format ``state_dict``.  TEST INFRASTRUCTURE ONLY (oracle/__init__.py).
 
-PINNED: ``tests/test_oracle_pinned.py`` checks every function here against the
+PINNED: ``tests/test_oracle.py`` checks every function here against the
 reference's own modules imported from /root/reference (when present) and against
 golden vectors under tests/golden/ that ``oracle/gen_golden.py`` produced by
 running those modules.

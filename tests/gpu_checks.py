@@ -690,6 +690,20 @@ def graphed_extractor_case(B=4, T=8, nsamp=24000, seed=2):
         out['shape_check'] = False
     except RuntimeError:
         out['shape_check'] = True
+    # Eager calls at OTHER shapes after capture (a dataset's tail batch) must not free or resize the persistent
+    # buffers whose addresses the graph holds: run more shapes than ops.BUFFERS caches (forcing evictions), allocate
+    # and scribble over fresh memory, then replay and compare bits.
+    from deeplip_b200 import ops
+    for b in range(1, B):
+        for t in (T - 1, T + 1, T + 2):
+            r = torch.from_numpy(synth.lip_crops_u8(spk[:b], T=t, seed=seed + 7)).to(DEV)
+            ex.extract(wav[:b], r)
+    junk = [torch.full((64 << 20,), 0x7f, dtype=torch.uint8, device=DEV) for _ in range(8)]
+    torch.cuda.synchronize()
+    out['replay_after_other_shapes'] = bool(torch.equal(g.extract(wav, raw), ref))
+    out['replay_new_batch_after_other_shapes'] = bool(torch.equal(g.extract(wav2, raw2), ref2))
+    del junk
+    assert len(g._pinned_buffers) > 0
     assert all(out.values()), out
     return out
 

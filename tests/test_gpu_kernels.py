@@ -2,7 +2,8 @@
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not torch.cuda.is_available(), reason='needs a CUDA device (no CPU fallback)')]
 
 if torch.cuda.is_available():
     import gpu_checks as G

@@ -5,7 +5,8 @@ Tolerances are north_star's: embedding cosine >= 0.999, per-trial score within 1
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not torch.cuda.is_available(), reason='needs a CUDA device (no CPU fallback)')]
 
 if torch.cuda.is_available():
     import gpu_checks as G

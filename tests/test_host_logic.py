@@ -353,3 +353,38 @@ def test_two_rank_gloo_shard_gather_score(tmp_path):
     text = out.stdout.decode()
     assert out.returncode == 0, text[-2000:]
     assert 'rank 0 ok' in text and 'rank 1 ok' in text
+
+
+def test_host_pipeline_rejects_single_slot():
+    """one staging slot would be overwritten by the next upload before the kernels read it."""
+    from deeplip_b200.pipeline import HostPipeline
+    with pytest.raises(ValueError):
+        HostPipeline(object(), 'cuda', slots=1)
+
+
+def test_buffer_cache_keeps_old_shapes_and_pins_recorded():
+    """persistent buffers are cached per shape (a new shape must not free what a CUDA graph captured) and
+    `recording()` hands the graph owner references that survive eviction."""
+    from deeplip_b200.ops import BufferCache
+    c = BufferCache(cap=2)
+    a = c.get(('k', 1), lambda: torch.zeros(4))
+    assert c.get(('k', 1), lambda: torch.ones(4)) is a
+    with c.recording() as rec:
+        b = c.get(('k', 2), lambda: torch.zeros(8))
+        assert c.get(('k', 1), lambda: None) is a
+    assert rec[0] is b and rec[1] is a
+    c.get(('k', 3), lambda: torch.zeros(1))
+    c.get(('k', 4), lambda: torch.zeros(1))          # evicts shapes 2 and 1 from the cache ...
+    assert c.get(('k', 2), lambda: torch.ones(8)) is not b
+    assert rec[0] is b and float(b.sum()) == 0.0      # ... but the recorded references still own the old buffers
+
+
+def test_tdnn_rejects_utterance_shorter_than_receptive_field():
+    """the reference's Conv1d raises on too-short input; the drop-in must not return NaN embeddings."""
+    from deeplip_b200 import synth
+    from deeplip_b200.audio_models.tdnn import SpeakerEmbNet
+    net = SpeakerEmbNet(synth.audio_opts('etdnn', 'statistic')).eval()
+    assert net.min_frames == net.context_loss + 2 == 24
+    x = torch.zeros((1, net.context_loss + 1, 64), dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        net.embed_ntc(x)
