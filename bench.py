@@ -234,6 +234,93 @@ def workload_config(args, per_gpu_batch):
                   'batches (226 MB)'}
 
 
+# --------------------------------------------------------------------------------------------- whole-list jobs
+JOB_LISTS = {'grid': 'trial_grid_v1.txt', 'lomgrid': 'trial_lomgrid_v1.txt'}
+POOL_VARIANTS = 4
+
+
+def job_pool(tl, seed):
+    """Synthetic inputs for every utterance of a real trial list without 25 834 distinct clips in memory: a pool of
+    (speakers x POOL_VARIANTS) GRID-shaped utterances with speaker structure and strong within-speaker variation
+    (so the EER is not 0); utterance u uses pool entry (speaker(u), crc32(u) % POOL_VARIANTS)."""
+    import zlib
+    from deeplip_b200 import synth
+    spk_of = [synth.speaker_of_utt(u) for u in tl.utts]
+    spks = sorted(set(spk_of))
+    pos = {s: i for i, s in enumerate(spks)}
+    pool_spk = [s for s in spks for _ in range(POOL_VARIANTS)]
+    raw = synth.lip_crops_u8(pool_spk, T=4, H=RAW_HW, W=RAW_HW, seed=seed, utt_sigma=1.6, frame_sigma=10.0)
+    raw = np.tile(raw, (1, (T_FRAMES + 3) // 4, 1, 1))[:, :T_FRAMES]
+    rng = np.random.default_rng(seed + 5)
+    raw = np.clip(raw.astype(np.int16) + rng.integers(-6, 7, raw.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+    wav = synth.speech_like_audio(pool_spk, nsamp=NSAMP, seed=seed, noise=0.35)
+    umap = np.array([pos[s] * POOL_VARIANTS + zlib.crc32(u.encode()) % POOL_VARIANTS for s, u in zip(spk_of, tl.utts)],
+                    dtype=np.int64)
+    return raw, wav, umap, len(spks)
+
+
+def run_job(name, args, rank, world, dev, ex, peaks, full_check):
+    """configs[2] (name='grid') / configs[3] ('lomgrid') as ONE job on the real trial list (deeplip_b200.jobs):
+    all utterances sharded over the ranks at a FIXED global batch (strong scaling), fused rows written straight into
+    the all-gather table, ONE NCCL all_gather, sharded gather-dot scoring, gathered scores, EER on rank 0."""
+    from deeplip_b200 import dist as dl_dist, ops
+    from deeplip_b200.fusion_models import utils as U
+    from deeplip_b200.jobs import TrialListJob
+    from deeplip_b200.trials import TrialList
+    tl = TrialList.from_file(os.path.join(ROOT, 'tests', 'golden', JOB_LISTS[name]))
+    raw_h, wav_h, umap_h, n_spk = job_pool(tl, seed=11)
+    raw_p, wav_p, umap = torch.from_numpy(raw_h).to(dev), torch.from_numpy(wav_h).to(dev), torch.from_numpy(umap_h).to(dev)
+    job = TrialListJob(tl, ex.dim, rank, world, device=dev, global_batch=args.job_batch)
+
+    def extract(lo, hi, out):                       # the "loader": gather the batch's clips from the resident pool
+        idx = umap[lo:hi]
+        ex.extract(wav_p.index_select(0, idx), raw_p.index_select(0, idx), out=out)
+
+    def score(table, en, te):
+        return ops.cosine_score_trials(table, en, te)
+
+    job.run(extract, score)                         # untimed pass: buffers for the batch and tail shapes, NCCL warm
+    torch.cuda.synchronize()
+    res = job.run(extract, score, eer_fn=U.eer_from_scores)
+    gather_ok = job.verify_gather()
+    ms = {k: dl_dist.max_over_ranks(v, dev) for k, v in sorted(res['ms'].items())}
+    total_ms = dl_dist.max_over_ranks(sum(res['ms'].values()), dev)
+    if rank != 0:
+        return None
+    out = {'list': JOB_LISTS[name], 'n_utts': res['n_utts'], 'n_trials': res['n_trials'], 'dim': ex.dim,
+           'global_batch': args.job_batch, 'per_gpu_batch': job.batch, 'rows_per_rank': job.per, 'scaling': 'strong',
+           'phase_ms_max_over_ranks': ms, 'device_ms': total_ms, 'eer_ms_cpu': res.get('eer_ms_cpu'),
+           'wall_s': (total_ms + res.get('eer_ms_cpu', 0.0)) / 1e3,
+           'utt_per_s': res['n_utts'] / (total_ms / 1e3), 'trials_per_s_scoring': res['n_trials'] / (ms['score'] / 1e3),
+           'allgather_bytes': res['allgather_bytes'],
+           'allgather_gbs': (res['allgather_bytes'] / (ms['all_gather'] / 1e3) / 1e9) if world > 1 else None,
+           'gathered_table_equals_shards': gather_ok, 'eer': float(res['eer']), 'threshold': float(res['threshold']),
+           'inputs': 'pool of %d speakers x %d synthetic GRID-shaped utterances resident in HBM; each batch is gathered '
+                     'from it on the device inside the timed region' % (n_spk, POOL_VARIANTS)}
+    # ---- parity against the oracle on the real list: a 64-utterance sample always; every score + the EER at N=1
+    from deeplip_b200 import synth
+    aopts = synth.audio_opts('etdnn', 'statistic')
+    sda, sdv = synth.make_audio_state_dict(aopts, seed=1), synth.make_video_state_dict(seed=1)
+    pin_cpu_threads()
+    torch.set_num_threads(os.cpu_count() or 1)
+    trial_ids = np.arange(len(tl)) if full_check else np.r_[0:16, 4000:4016]
+    need = sorted(set(umap_h[tl.enrol_idx[trial_ids]]) | set(umap_h[tl.test_idx[trial_ids]]))
+    t0 = time.perf_counter()
+    ref_rows = {int(p): oracle_av_extract(raw_h[p:p + 1], wav_h[p:p + 1], sda, sdv, aopts)[0].double().numpy() for p in need}
+    a = np.stack([ref_rows[int(umap_h[i])] for i in tl.enrol_idx[trial_ids]])
+    b = np.stack([ref_rows[int(umap_h[i])] for i in tl.test_idx[trial_ids]])
+    ref_scores = (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+    got = res['scores'].cpu().numpy()[trial_ids]
+    chk = {'trials_checked': int(len(trial_ids)), 'utterances': int(len(set(tl.enrol_idx[trial_ids]) | set(tl.test_idx[trial_ids]))),
+           'distinct_inputs': len(need), 'max_abs_score_err': float(np.abs(got - ref_scores).max()), 'tolerance': 1e-3,
+           'oracle_s': time.perf_counter() - t0}
+    if full_check:
+        ref_eer, _ = U.eer_from_scores(tl.labels, ref_scores.astype(np.float32))
+        chk.update(oracle_eer=float(ref_eer), eer_abs_diff=float(abs(ref_eer - res['eer'])), eer_tolerance=5e-4)
+    out['oracle_check'] = chk
+    return out
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local):
     from deeplip_b200 import _lib, dist as dl_dist, synth
@@ -455,6 +542,17 @@ def run_ours(args, rank, world, local):
     except Exception as e:      # scoring is reported next to the headline, it must not sink it
         scoring = {'error': repr(e)[:200]}
 
+    # ---- configs[2] / configs[3] as whole-list jobs on the real trial lists (strong scaling at a fixed global batch)
+    jobs = {}
+    for name in ([] if args.job == 'none' else ['lomgrid', 'grid'] if args.job == 'both' else [args.job]):
+        try:
+            jobs[name] = run_job(name, args, rank, world, dev, ex, peaks, full_check=(world == 1 and not args.no_cpu_baseline))
+        except Exception as e:          # reported next to the headline, must not sink it
+            import traceback
+            traceback.print_exc()
+            jobs[name] = {'error': repr(e)[:300]}
+            if world > 1:
+                raise                    # a rank that leaves a collective early would hang the others
     if rank != 0:
         return
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
@@ -500,7 +598,7 @@ def run_ours(args, rank, world, local):
             'step_tflops': total_gflop / (ms / args.steps),
             'breakdown_ms': {'stem': stem_ms, 'trunk': trunk_ms, 'audio_frontend_tdnn': audio_ms},
             'hbm_kernels': hbm_kernels,
-            'stem_tflops': GFLOP_STEM_PER_UTT * B / stem_ms}
+            'stem_tflops': GFLOP_STEM_PER_UTT * B / stem_ms, 'jobs': jobs}
     emit(line)
 
 
@@ -513,6 +611,9 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='utterances per GPU per step')
     ap.add_argument('--ref-utts', type=int, default=4, help='utterances per step of the CPU reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--job', default='both', choices=['both', 'grid', 'lomgrid', 'none'],
+                    help='whole-list jobs on the real trial lists (configs[2] = grid, configs[3] = lomgrid)')
+    ap.add_argument('--job-batch', type=int, default=256, help='GLOBAL batch of the jobs (256 / N per GPU)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

@@ -303,13 +303,18 @@ def attn_logits(h_f32, v, k):
 
 
 # ------------------------------------------------------------------ K8
-def znorm_concat(a, v, biased=False, video_first=False, l2norm=False, want_bf16=False):
-    _need_cuda(a, v)
+def znorm_concat(a, v, biased=False, video_first=False, l2norm=False, want_bf16=False, out=None):
+    """out: optional caller-owned contiguous (B, Da+Dv) f32 rows -- e.g. this batch's slice of the all-gather
+    table (K8 writes straight into the collective's buffer, no copy before the all_gather)."""
+    _need_cuda(a, v, out)
     a = a.contiguous().float()
     v = v.contiguous().float()
     B, Da = a.shape
     Dv = v.shape[1]
-    out = torch.empty((B, Da + Dv), device=a.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((B, Da + Dv), device=a.device, dtype=torch.float32)
+    else:
+        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, Da + Dv)
     ob = torch.empty((B, Da + Dv), device=a.device, dtype=torch.bfloat16) if want_bf16 else None
     st = _lib.lib().dl_znorm_concat(_ptr(a), Da, _ptr(v), Dv, B, int(biased), int(video_first), int(l2norm),
                                     _ptr(out), _ptr(ob), _stream())

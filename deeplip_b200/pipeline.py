@@ -47,22 +47,42 @@ class AVExtractor:
             return em.view(B, G, -1).mean(dim=1)      # mean over clips (train_fusion.py:401)
         return self.video.utterance_embedding(video, video_lengths)
 
-    def fuse(self, xv_audio, em_video):
+    def fuse(self, xv_audio, em_video, out=None):
+        """out: optional caller-owned (B, D) f32 rows the fused embeddings are written to (the job's all-gather
+        table); the default concat fusions write there directly, the others are copied in."""
         if self.fusion == 'concat':          # F0, the default executed at test time
-            return ops.znorm_concat(xv_audio, em_video, l2norm=self.l2norm)
+            return ops.znorm_concat(xv_audio, em_video, l2norm=self.l2norm, out=out)
         if self.fusion == 'concat_np':       # F3, models/fusion_models/utils.py:465-471
-            return ops.znorm_concat(xv_audio, em_video, biased=True, video_first=True, l2norm=self.l2norm)
+            return ops.znorm_concat(xv_audio, em_video, biased=True, video_first=True, l2norm=self.l2norm, out=out)
         if self.fusion == 'linear':          # F1 on cat([audio, video])
-            return self.fusion_model(torch.cat([xv_audio, em_video], dim=1))
-        if self.fusion == 'lowfer':          # F2
-            return ops.lowfer(xv_audio, em_video)
-        return xv_audio if self.fusion == 'audio' else em_video
+            y = self.fusion_model(torch.cat([xv_audio, em_video], dim=1))
+        elif self.fusion == 'lowfer':        # F2
+            y = ops.lowfer(xv_audio, em_video)
+        else:
+            y = xv_audio if self.fusion == 'audio' else em_video
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
+    @property
+    def dim(self):
+        """Width of one fused embedding row."""
+        ea = getattr(self.audio, 'embedding_dim', 512)
+        if self.fusion in ('concat', 'concat_np'):
+            return ea + 512
+        if self.fusion == 'lowfer':
+            return 3 * ea
+        if self.fusion == 'linear':
+            return self.fusion_model.fc1.out_features if getattr(self.fusion_model, 'extract_feats', True) else \
+                self.fusion_model.fc2.out_features
+        return ea if self.fusion == 'audio' else 512
 
     @torch.no_grad()
-    def extract(self, wav, video, wav_lengths=None, video_lengths=None):
+    def extract(self, wav, video, wav_lengths=None, video_lengths=None, out=None):
         xv = self.audio_embedding(wav, wav_lengths) if self.fusion != 'video' else None
         em = self.video_embedding(video, video_lengths) if self.fusion != 'audio' else None
-        return self.fuse(xv, em)
+        return self.fuse(xv, em, out=out)
 
 
 class GraphedExtractor:

@@ -1,6 +1,8 @@
 """Kernel-level parity checks: CUDA path (through the C ABI) vs the CPU oracle on seeded inputs.
 Each check returns a dict of error metrics and raises AssertionError when out of tolerance.
 Used by tests/test_gpu_*.py and tools/gpu_diag.py."""
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -547,8 +549,13 @@ def scoring_full_case(tmpdir, kind='grid'):
     import os
     from deeplip_b200.trials import TrialList
     from deeplip_b200.fusion_models import utils as U
-    path = make_trial_file(os.path.join(tmpdir, 'trial_%s.txt' % kind), kind)
+    if kind.endswith('_real'):      # the reference's own shipped lists (database/trial_*_v1.txt), reproduced under tests/golden
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'trial_%s_v1.txt' % kind[:-5])
+    else:
+        path = make_trial_file(os.path.join(tmpdir, 'trial_%s.txt' % kind), kind)
     tl = TrialList.from_file(path)
+    if kind.endswith('_real'):
+        assert len(tl) == 20000 and len(tl.utts) == {'grid_real': 25834, 'lomgrid_real': 3541}[kind]
     labels, pairs = scoring_ref.parse_trials(path)
     table, enrol, test = scoring_ref.utterance_table(pairs)
     assert table == tl.utts and np.array_equal(enrol, tl.enrol_idx) and np.array_equal(test, tl.test_idx)
@@ -832,3 +839,41 @@ def audio_resnet_case(B=3, Fd=24, T=120, pooling='average', seed=1):
     out = {'cos_min': float(cosine_rows(got, ref).min()), 'rel': rel_err(got, ref)}
     assert out['cos_min'] > 0.999, out
     return out
+
+
+def trial_list_job_case(tmpdir, B=5, T=6, nsamp=16000, seed=3):
+    """deeplip_b200.jobs.TrialListJob on one GPU with the real extractor: the table assembled batch by batch through
+    `extract(out=table rows)` (K8 writing straight into the gather buffer) is bit-identical to the embeddings of ONE
+    batched call, the scores equal the oracle's on that table, and the job's EER equals the oracle's EER."""
+    from deeplip_b200.fusion_models import utils as U
+    from deeplip_b200.jobs import TrialListJob
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    from deeplip_b200.trials import TrialList
+    audio, video = build_models(DEV, seed=1)
+    ex = AVExtractor(audio, video)
+    assert ex.dim == 1024
+    tl = TrialList.from_file(make_trial_file(os.path.join(str(tmpdir), 'job.txt'), 'grid', n_target=30, n_non=60))
+    n = len(tl.utts)
+    spk = [synth.speaker_of_utt(u) for u in tl.utts]
+    pool_spk = sorted(set(spk))
+    wav_p = torch.from_numpy(synth.speech_like_audio(pool_spk, nsamp=nsamp, seed=seed, noise=0.3)).to(DEV)
+    raw_p = torch.from_numpy(synth.lip_crops_u8(pool_spk, T=T, seed=seed, utt_sigma=1.0)).to(DEV)
+    umap = torch.tensor([pool_spk.index(s) for s in spk], device=DEV)
+    job = TrialListJob(tl, ex.dim, 0, 1, device=DEV, global_batch=B)
+
+    def extract(lo, hi, out):
+        idx = umap[lo:hi]
+        got = ex.extract(wav_p.index_select(0, idx), raw_p.index_select(0, idx), out=out)
+        assert got.data_ptr() == out.data_ptr()
+
+    res = job.run(extract, lambda tab, en, te: ops.cosine_score_trials(tab, en, te), eer_fn=U.eer_from_scores)
+    whole = ex.extract(wav_p.index_select(0, umap), raw_p.index_select(0, umap))
+    torch.cuda.synchronize()
+    assert job.table.shape == (n, 1024) and torch.equal(job.table, whole), 'in-table extraction differs from one batched call'
+    ref = scoring_ref.cosine_scores_vec(whole.cpu().numpy(), tl.enrol_idx, tl.test_idx)
+    err = float(np.abs(res['scores'].cpu().numpy() - ref).max())
+    assert err < 1e-5, err
+    ref_eer, _ = scoring_ref.eer_from_scores(tl.labels, list(ref.astype(np.float32).reshape(-1, 1)))
+    assert abs(res['eer'] - ref_eer) < 5e-4
+    assert job.verify_gather() and set(res['ms']) == {'extract', 'checksum', 'all_gather', 'score', 'gather_scores'}
+    return {'n_utts': n, 'score_abs': err, 'eer': float(res['eer'])}

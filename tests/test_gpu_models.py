@@ -53,9 +53,13 @@ def test_fusion_vs_reference_golden():
     G.fusion_golden_case()
 
 
-@pytest.mark.parametrize('kind', ['grid', 'lomgrid'])
+@pytest.mark.parametrize('kind', ['grid', 'lomgrid', 'grid_real', 'lomgrid_real'])
 def test_scoring_full_trial_list(tmp_path, kind):
     G.scoring_full_case(str(tmp_path), kind)
+
+
+def test_trial_list_job_extracts_into_the_gather_table(tmp_path):
+    G.trial_list_job_case(tmp_path)
 
 
 def test_av_pipeline_and_ragged_batch():

@@ -388,3 +388,85 @@ def test_tdnn_rejects_utterance_shorter_than_receptive_field():
     x = torch.zeros((1, net.context_loss + 1, 64), dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         net.embed_ntc(x)
+
+
+REAL_LISTS = {'grid': ('trial_grid_v1.txt', '58d2936203e004a82fdef9ee5c6076f6c3812655803d2ad1d84583111577ccab',
+                       25834, 20000, 14900),
+              'lomgrid': ('trial_lomgrid_v1.txt', '968e12cabba8067ae8662211fe8cea5bad901a66b83625737d32b7181ba61632',
+                          3541, 3526, 3447)}
+
+
+@pytest.mark.parametrize('name', ['grid', 'lomgrid'])
+def test_real_trial_lists_index_bit_exact(name):
+    """The reference's two shipped trial lists (database/trial_{grid,lomgrid}_v1.txt, reproduced under tests/golden/):
+    file sha256, and the WHOLE (enrol_idx, test_idx) vectors of the product parser against the position-weighted
+    xor checksums gen_golden.py stored from the oracle's parse of the reference files (bit-exact trial indexing)."""
+    import hashlib
+    from deeplip_b200.trials import TrialList
+    fname, sha, n_utts, n_left, n_right = REAL_LISTS[name]
+    path = os.path.join(ROOT, 'tests', 'golden', fname)
+    assert hashlib.sha256(open(path, 'rb').read()).hexdigest() == sha
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'scoring.npz'))
+    assert str(g[name + '_sha256']) == sha
+    tl = TrialList.from_file(path)
+    assert len(tl) == 20000 and len(tl.utts) == n_utts == int(g[name + '_n_utts'])
+    assert int(tl.labels.sum()) == 4000 == int(g[name + '_labels_sum']) and tl.labels[:4000].all() and not tl.labels[4000:].any()
+    assert len(np.unique(tl.enrol_idx)) == n_left and len(np.unique(tl.test_idx)) == n_right
+    w = np.arange(len(tl)) + 1
+    assert int(np.bitwise_xor.reduce(tl.enrol_idx.astype(np.int64) * w)) == int(g[name + '_enrol_crc'])
+    assert int(np.bitwise_xor.reduce(tl.test_idx.astype(np.int64) * w)) == int(g[name + '_test_crc'])
+    assert np.array_equal(tl.enrol_idx[:64], g[name + '_enrol_head']) and np.array_equal(tl.test_idx[:64], g[name + '_test_head'])
+    # label == (speaker1 == speaker2) on every line (SURVEY 8(d))
+    from deeplip_b200 import synth
+    spk = np.array([synth.speaker_of_utt(u) for u in tl.utts])
+    assert np.array_equal((spk[tl.enrol_idx] == spk[tl.test_idx]).astype(np.int64), tl.labels)
+
+
+_JOB_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from deeplip_b200 import dist as D, synth
+from deeplip_b200.jobs import TrialListJob
+from deeplip_b200.trials import TrialList
+from deeplip_b200.fusion_models.utils import eer_from_scores
+from oracle import scoring_ref
+rank, world, _ = D.init_from_env('gloo')
+tl = TrialList.from_file(%(trial)r)
+full = torch.from_numpy(synth.structured_embeddings([synth.speaker_of_utt(u) for u in tl.utts], dim=32, seed=4, within=3.0))
+job = TrialListJob(tl, 32, rank, world, device='cpu', global_batch=256)
+assert job.batch == 128 and job.per == 1771 and job.table.shape == (3542, 32)
+calls = []
+def extract(lo, hi, out):                 # this rank "extracts" only rows it owns, straight into its table slice
+    assert job.lo <= lo < hi <= job.hi and hi - lo <= job.batch and out.shape == (hi - lo, 32)
+    assert out.data_ptr() == job.table[rank * job.per + lo - job.lo].data_ptr()
+    calls.append((lo, hi)); out.copy_(full[lo:hi])
+def score(table, en, te):
+    return torch.from_numpy(scoring_ref.cosine_scores_vec(table.numpy(), en.numpy(), te.numpy())).float()
+res = job.run(extract, score, eer_fn=eer_from_scores)
+assert calls[0][0] == job.lo and calls[-1][1] == job.hi and len(calls) == -(-(job.hi - job.lo) // 128)
+assert job.verify_gather()
+assert torch.equal(job.table[:len(tl.utts)], full) and float(job.table[len(tl.utts):].abs().sum()) == 0
+ref = scoring_ref.cosine_scores_vec(full.numpy(), tl.enrol_idx, tl.test_idx).astype(np.float32)
+assert np.array_equal(res['scores'].numpy(), ref)
+if rank == 0:
+    eer, _ = scoring_ref.eer_from_scores(tl.labels, list(ref.reshape(-1, 1)))
+    assert abs(res['eer'] - eer) < 1e-12 and 0.0 < eer < 0.5
+    assert set(res['ms']) == {'extract', 'checksum', 'all_gather', 'score', 'gather_scores'}
+job.table[0, 0] += 1.0                    # a corrupted gather must be caught on every rank
+assert not job.verify_gather()
+D.barrier(); dist.destroy_process_group()
+sys.stdout.write('rank %%d ok\n' %% rank); sys.stdout.flush()
+'''
+
+
+def test_two_rank_gloo_trial_list_job_on_real_lomgrid(tmp_path):
+    """configs[3] as a job (deeplip_b200.jobs.TrialListJob) on the real trial_lomgrid_v1 list, world_size 2 on gloo:
+    shards, in-table extraction, ONE all-gather, sharded scoring, gathered scores == the single-process oracle, EER."""
+    script = tmp_path / 'job_worker.py'
+    script.write_text(_JOB_WORKER % {'root': ROOT, 'trial': os.path.join(ROOT, 'tests', 'golden', 'trial_lomgrid_v1.txt')})
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr',
+           '127.0.0.1', '--master-port', '29613', str(script)]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=240)
+    text = out.stdout.decode()
+    assert out.returncode == 0, text[-3000:]
+    assert 'rank 0 ok' in text and 'rank 1 ok' in text
