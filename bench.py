@@ -283,6 +283,40 @@ def run_job(name, args, rank, world, dev, ex, peaks, full_check):
     torch.cuda.synchronize()
     res = job.run(extract, score, eer_fn=U.eer_from_scores)
     gather_ok = job.verify_gather()
+    # ---- the dense formulation (report both): one tensor-core GEMM over the unique left x right
+    # utterances + a gather of the 20 000 wanted entries, on the job's real table; rank 0's GPU only (not sharded)
+    dense = None
+    if rank == 0:
+        try:
+            ds = U.DenseScorer(tl, dev)
+            table = job.table[:job.n_utts]
+            sd = ds.score(table)
+            _, A, Bm = ds.score(table, return_parts=True)
+            torch.cuda.synchronize()
+
+            def timed_ms(fn, reps=5):
+                ev = []
+                for _ in range(reps):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(); b.record()
+                    ev.append((a, b))
+                torch.cuda.synchronize()
+                return statistics.median(a.elapsed_time(b) for a, b in ev)
+            all_ms = timed_ms(lambda: ds.score(table))
+            gemm_ms = timed_ms(lambda: ops.conv_igemm(A.view(ds.n_left, 1, 1, ex.dim), Bm, ex.dim, ds.n_right_pad,
+                                                      want_bf16=False, want_f32=True))
+            gd_ms = timed_ms(lambda: ops.cosine_score_trials(table, job.enrol, job.test)) if world == 1 else None
+            tf = ds.flop(ex.dim) / (gemm_ms / 1e3) / 1e12
+            dense = {'n_left': ds.n_left, 'n_right': ds.n_right, 'gflop': ds.flop(ex.dim) / 1e9, 'gemm_ms': gemm_ms,
+                     'gemm_tflops': tf, 'peak': peaks['bf16_tflops'], 'frac_of_burst_peak': tf / peaks['bf16_tflops'],
+                     'score_matrix_bytes_f32': ds.n_left * ds.n_right_pad * 4,
+                     'whole_list_ms': all_ms, 'gather_dot_whole_list_ms': gd_ms,
+                     'max_abs_vs_gather_dot': float((sd - ops.cosine_score_trials(table, torch.from_numpy(tl.enrol_idx).to(dev),
+                                                                                  torch.from_numpy(tl.test_idx).to(dev))).abs().max()),
+                     'note': 'normalise + row gathers + GEMM (bf16 operands, f32 scores) + gather; L2 not flushed'}
+            del A, Bm, sd
+        except Exception as e:
+            dense = {'error': repr(e)[:300]}
     ms = {k: dl_dist.max_over_ranks(v, dev) for k, v in sorted(res['ms'].items())}
     total_ms = dl_dist.max_over_ranks(sum(res['ms'].values()), dev)
     if rank != 0:
@@ -294,7 +328,7 @@ def run_job(name, args, rank, world, dev, ex, peaks, full_check):
            'utt_per_s': res['n_utts'] / (total_ms / 1e3), 'trials_per_s_scoring': res['n_trials'] / (ms['score'] / 1e3),
            'allgather_bytes': res['allgather_bytes'],
            'allgather_gbs': (res['allgather_bytes'] / (ms['all_gather'] / 1e3) / 1e9) if world > 1 else None,
-           'gathered_table_equals_shards': gather_ok, 'eer': float(res['eer']), 'threshold': float(res['threshold']),
+           'gathered_table_equals_shards': gather_ok, 'dense_scoring': dense, 'eer': float(res['eer']), 'threshold': float(res['threshold']),
            'inputs': 'pool of %d speakers x %d synthetic GRID-shaped utterances resident in HBM; each batch is gathered '
                      'from it on the device inside the timed region' % (n_spk, POOL_VARIANTS)}
     # ---- parity against the oracle on the real list: a 64-utterance sample always; every score + the EER at N=1

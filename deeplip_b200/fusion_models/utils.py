@@ -58,26 +58,45 @@ def score_trials_featurefusion(emb_audio, emb_video, trials, device='cuda'):
     return ops.cosine_score_trials(fused, _dev(trials.enrol_idx, device), _dev(trials.test_idx, device))
 
 
-def score_trials_dense(emb, trials, device='cuda'):
+class DenseScorer:
     """The dense formulation north_star names: L2-normalise every embedding once, one tensor-core GEMM
     S = enrol x test^T over the UNIQUE left / right utterances of the list (dl_conv_igemm_bf16, bf16 operands,
     fp32 accumulate), then gather scores[i] = S[row(i), col(i)] (dl_gather_scores).  It does
     n_left * n_right * D MACs for n_trials useful dot products (about 15 000x more arithmetic than the list needs
     on GRID), so `score_trials` (gather-dot, HBM-bound) is the default; this variant exists for lists that are
-    dense in enrol x test."""
-    e = _dev(emb, device).float()
-    _, eb = ops.l2_normalize(e, want_bf16=True)
-    left, rows = np.unique(trials.enrol_idx, return_inverse=True)
-    right, cols = np.unique(trials.test_idx, return_inverse=True)
-    A = eb[_dev(left.astype(np.int64), device)].contiguous()          # (n_left, D) bf16
-    Bm = eb[_dev(right.astype(np.int64), device)].contiguous()        # (n_right, D) bf16  == "weights"
-    D = e.shape[1]
-    n_right_pad = (len(right) + 7) // 8 * 8
-    if n_right_pad != len(right):
-        Bm = torch.cat([Bm, torch.zeros((n_right_pad - len(right), D), device=Bm.device, dtype=Bm.dtype)])
-    assert D % 64 == 0, 'dense scoring needs the embedding dim to be a multiple of 64'
-    _, S = ops.conv_igemm(A.view(len(left), 1, 1, D), Bm, D, n_right_pad, want_bf16=False, want_f32=True)
-    return ops.gather_scores(S, _dev(rows.astype(np.int32), device), _dev(cols.astype(np.int32), device))
+    dense in enrol x test.  The list-dependent index work (unique utterances, row / column of every trial) is done
+    once here on the host; `score(emb)` is device work only."""
+
+    def __init__(self, trials, device='cuda'):
+        left, rows = np.unique(trials.enrol_idx, return_inverse=True)
+        right, cols = np.unique(trials.test_idx, return_inverse=True)
+        self.n_left, self.n_right = len(left), len(right)
+        self.n_right_pad = (self.n_right + 7) // 8 * 8
+        self.left = _dev(left.astype(np.int64), device)
+        right_pad = np.concatenate([right, np.full(self.n_right_pad - self.n_right, right[-1])]).astype(np.int64)
+        self.right = _dev(right_pad, device)          # pad columns repeat the last row; never gathered
+        self.rows = _dev(rows.astype(np.int32), device)
+        self.cols = _dev(cols.astype(np.int32), device)
+        self.device = device
+
+    def flop(self, D):
+        return 2.0 * self.n_left * self.n_right * D
+
+    def score(self, emb, return_parts=False):
+        e = _dev(emb, self.device).float()
+        D = e.shape[1]
+        assert D % 64 == 0, 'dense scoring needs the embedding dim to be a multiple of 64'
+        _, eb = ops.l2_normalize(e, want_bf16=True)
+        A = eb.index_select(0, self.left)             # (n_left, D) bf16
+        Bm = eb.index_select(0, self.right)           # (n_right_pad, D) bf16  == "weights"
+        _, S = ops.conv_igemm(A.view(self.n_left, 1, 1, D), Bm, D, self.n_right_pad, want_bf16=False, want_f32=True)
+        out = ops.gather_scores(S, self.rows, self.cols)
+        return (out, A, Bm) if return_parts else out
+
+
+def score_trials_dense(emb, trials, device='cuda'):
+    """One-shot form of DenseScorer."""
+    return DenseScorer(trials, device).score(emb)
 
 
 def eer_cos(trials, emb, device='cuda'):
