@@ -283,8 +283,9 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   // ---- a handful of rows through a 1x1 filter (the fc heads: one row per utterance) is latency, not throughput:
   // linear_small_kernel spreads it over Cout/4 blocks instead of one or two tensor-core CTAs
   // (only where one "pixel" is one batch item, P Q == 1, and whatever the batch size up to 4096, so that an utterance
-  // gets the same summation order alone and inside a batch)
-  if (opt_small_linear() && split == 0 && M <= 4096 && P * Q == 1 && d->R == 1 && d->S == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
+  // gets the same summation order alone and inside a batch; Cout <= 2048 keeps wide "layers" -- the dense trial-scoring
+  // GEMM of a small list, 3 526 x 3 447 on LomGRID -- on the tensor-core path: 2.9 ms here vs. tens of microseconds)
+  if (opt_small_linear() && split == 0 && M <= 4096 && d->Cout <= 2048 && P * Q == 1 && d->R == 1 && d->S == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
       d->pad_w == 0 && !lin && !residual && d->C % 8 == 0 && d->out_img_rows == 0 &&
       (d->img_rows == 0 || d->img_rows == d->H) && (d->img_cols == 0 || d->img_cols == d->W) &&
       (((uintptr_t)x | (uintptr_t)w_packed) & 15) == 0) {
