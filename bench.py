@@ -259,6 +259,37 @@ def job_pool(tl, seed):
     return raw, wav, umap, len(spks)
 
 
+def oracle_rows_in_subprocess(raw, wav):
+    """Oracle embeddings of a few utterances, computed by a FRESH CPU-only process (`bench.py --oracle-worker`): inside
+    a torchrun rank (OMP_NUM_THREADS=1 in the environment, a CUDA context, NCCL's threads, the peer rank spinning in a
+    barrier) the same 43 utterances took 50 s instead of 2; a clean process is also the cleaner checker."""
+    tmp = tempfile.mkdtemp(prefix='oracle_')
+    fin, fout = os.path.join(tmp, 'in.npz'), os.path.join(tmp, 'out.npy')
+    np.savez(fin, raw=raw, wav=wav)
+    env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS',
+                                                            'RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'CUDA_VISIBLE_DEVICES')}
+    env['CUDA_VISIBLE_DEVICES'] = ''
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), '--oracle-worker', fin, fout], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    if r.returncode != 0:
+        raise RuntimeError('oracle worker failed: ' + r.stdout.decode()[-500:])
+    out = np.load(fout)
+    for f in (fin, fout):
+        os.unlink(f)
+    os.rmdir(tmp)
+    return out
+
+
+def oracle_worker(fin, fout):
+    from deeplip_b200 import synth
+    pin_cpu_threads()
+    torch.set_num_threads(os.cpu_count() or 1)
+    d = np.load(fin)
+    aopts = synth.audio_opts('etdnn', 'statistic')
+    sda, sdv = synth.make_audio_state_dict(aopts, seed=1), synth.make_video_state_dict(seed=1)
+    np.save(fout, oracle_av_extract(d['raw'], d['wav'], sda, sdv, aopts).double().numpy())
+
+
 def run_job(name, args, rank, world, dev, ex, peaks, full_check):
     """configs[2] (name='grid') / configs[3] ('lomgrid') as ONE job on the real trial list (deeplip_b200.jobs):
     all utterances sharded over the ranks at a FIXED global batch (strong scaling), fused rows written straight into
@@ -332,15 +363,11 @@ def run_job(name, args, rank, world, dev, ex, peaks, full_check):
            'inputs': 'pool of %d speakers x %d synthetic GRID-shaped utterances resident in HBM; each batch is gathered '
                      'from it on the device inside the timed region' % (n_spk, POOL_VARIANTS)}
     # ---- parity against the oracle on the real list: a 64-utterance sample always; every score + the EER at N=1
-    from deeplip_b200 import synth
-    aopts = synth.audio_opts('etdnn', 'statistic')
-    sda, sdv = synth.make_audio_state_dict(aopts, seed=1), synth.make_video_state_dict(seed=1)
-    pin_cpu_threads()
-    torch.set_num_threads(os.cpu_count() or 1)
     trial_ids = np.arange(len(tl)) if full_check else np.r_[0:16, 4000:4016]
     need = sorted(set(umap_h[tl.enrol_idx[trial_ids]]) | set(umap_h[tl.test_idx[trial_ids]]))
     t0 = time.perf_counter()
-    ref_rows = {int(p): oracle_av_extract(raw_h[p:p + 1], wav_h[p:p + 1], sda, sdv, aopts)[0].double().numpy() for p in need}
+    rows = oracle_rows_in_subprocess(raw_h[need], wav_h[need])
+    ref_rows = {int(p): rows[k] for k, p in enumerate(need)}
     a = np.stack([ref_rows[int(umap_h[i])] for i in tl.enrol_idx[trial_ids]])
     b = np.stack([ref_rows[int(umap_h[i])] for i in tl.test_idx[trial_ids]])
     ref_scores = (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
@@ -680,12 +707,16 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--job', default='both', choices=['both', 'grid', 'lomgrid', 'none'],
                     help='whole-list jobs on the real trial lists (configs[2] = grid, configs[3] = lomgrid)')
+    ap.add_argument('--oracle-worker', nargs=2, metavar=('IN', 'OUT'), help=argparse.SUPPRESS)
     ap.add_argument('--job-batch', type=int, default=256, help='GLOBAL batch of the jobs (256 / N per GPU)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     claim_stdout()
+    if args.oracle_worker:
+        oracle_worker(*args.oracle_worker)
+        return
     if args.impl == 'reference':
         run_reference(args, rank)
         return

@@ -18,7 +18,7 @@ class ConvDesc(C.Structure):
                 ('N', 'H', 'W', 'C', 'ldx', 'Cout', 'R', 'S', 'stride_h', 'stride_w', 'pad_h', 'pad_w',
                  'dil_h', 'dil_w', 'ldy', 'ldf')] + [('f32_slope', C.c_float)] + [(n, C.c_int) for n in
                 ('img_rows', 'img_cols', 'lin', 'valid_h', 'valid_w', 'out_img_rows', 'out_img_cols',
-                 'split_channel', 'split_center_only')] + [('y_split', C.c_void_p)]
+                 'split_channel', 'split_center_only')] + [('y_split', C.c_void_p), ('center_only_from', C.c_int)]
 
 
 _p, _i, _f = C.c_void_p, C.c_int, C.c_float

@@ -122,8 +122,16 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const uint32_t bb = mapa_shared(smem_u32(bfull), 0);
         if (rank == 0) mbar_expect_tx_cluster(bb, 2u * (uint32_t)num_kb * Cfg::B_BYTES);
         else mbar_arrive_cluster(bb);
-        for (int kb = 0; kb < num_kb; ++kb)
-          tma2_load_2d(bres + kb * Cfg::B_BYTES, &mapB, bb, kb * 64, (int)rank * (BLOCK_N / 2));
+        if (BLOCK_N == 256 && p.half_skip) {
+          // this CTA's B block = [conv1 rows 64 rank .. +63 | skip rows 128 + 64 rank .. +63] (two 64-row boxes)
+          for (int kb = 0; kb < num_kb; ++kb) {
+            tma2_load_2d(bres + kb * Cfg::B_BYTES, &mapB, bb, kb * 64, (int)rank * 64);
+            tma2_load_2d(bres + kb * Cfg::B_BYTES + Cfg::B_BYTES / 2, &mapB, bb, kb * 64, 128 + (int)rank * 64);
+          }
+        } else {
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma2_load_2d(bres + kb * Cfg::B_BYTES, &mapB, bb, kb * 64, (int)rank * (BLOCK_N / 2));
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -210,6 +218,29 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
+        if (kResB && BLOCK_N == 256 && p.half_skip) {
+          // Two N = 128 streams into one 256-column accumulator: columns [0,128) = conv1 over every K block (B rows
+          // 0..63 of each CTA's block), columns [128,256) = the skip conv over the centre tap's K blocks only (B rows
+          // 64..127).  36 + 4 half-width MMAs per tile instead of 36 full-width ones; bit-identical (the products
+          // left out are exact zeros).
+          constexpr uint32_t idesc_h = umma_idesc_bf16(256, 128);
+          const int ckb0 = ((p.R >> 1) * p.S + (p.S >> 1)) * p.cchunks;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + stage * Cfg::STAGE_BYTES));
+            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(bres) + kb * Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc_h, (kb | k) != 0 ? 1u : 0u);
+            if (kb >= ckb0 && kb < ckb0 + p.cchunks) {
+              const uint64_t sdesc = bdesc + (uint64_t)((Cfg::B_BYTES / 2) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma2_bf16(d + 128, adesc + 2 * k, sdesc + 2 * k, idesc_h, (kb != ckb0 || k != 0) ? 1u : 0u);
+            }
+            umma2_commit_both(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else {
         int mp_, n_blk_;
         tile_of(t, mp_, n_blk_);
         const int nkb = (ctr_mode && n_blk_ >= p.skip_n0) ? p.cchunks : num_kb;
@@ -223,6 +254,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           for (int k = 0; k < ((p.dbg & 8) ? 1 : 4); ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma2_commit_both(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
         }
         }
         umma2_commit_both(&tfull[acc]);
@@ -298,15 +330,19 @@ int igemm_pair_taps(const IgemmParams& p, int block_n) {
   return 1;
 }
 
+bool igemm_pair_resident(const IgemmParams& p, int block_n) {
+  const long long num_kb = (long long)p.R * p.S * p.cchunks;
+  return opt_pair_resident() && p.taps == 1 && p.num_n_blocks == 1 && num_kb * (block_n / 2) * 128 <= kPairResidentBBytes &&
+         p.Cout <= kPairResidentMaxCout;
+}
+
 // Called by dl_conv_igemm_bf16 (igemm_conv.cu) for wide, large-M problems.
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
                       cudaStream_t stream) {
   if (p.taps == 3)
     return block_n == 128 ? launch_igemm2<128, false, 3>(mapA, mapB, p, stream) : launch_igemm2<256, false, 3>(mapA, mapB, p, stream);
   if (p.taps == 5) return launch_igemm2<256, false, 5>(mapA, mapB, p, stream);
-  const long long num_kb = (long long)p.R * p.S * p.cchunks;
-  const bool res = opt_pair_resident() && p.num_n_blocks == 1 && num_kb * (block_n / 2) * 128 <= kPairResidentBBytes &&
-                   p.Cout <= kPairResidentMaxCout;
+  const bool res = igemm_pair_resident(p, block_n);
   if (block_n == 128) return res ? launch_igemm2<128, true, 1>(mapA, mapB, p, stream) : launch_igemm2<128, false, 1>(mapA, mapB, p, stream);
   return res ? launch_igemm2<256, true, 1>(mapA, mapB, p, stream) : launch_igemm2<256, false, 1>(mapA, mapB, p, stream);
 }

@@ -32,6 +32,7 @@ struct IgemmParams {
   uint16_t* y2;        // split output: channels >= split_c go to y2[row * ldy + c - split_c] (split_c = 0: off)
   int split_c;
   int skip_n0;         // pair kernel: n blocks >= skip_n0 see the filter's centre tap only (-1: none)
+  int half_skip;       // pair kernel, one resident 256-wide n block: channels >= 128 see the centre tap only -> two N=128 MMA streams
 };
 
 // GEMM row -> row of y / residual, and whether it is stored at all.

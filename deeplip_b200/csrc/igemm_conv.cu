@@ -228,6 +228,7 @@ static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
                       cudaStream_t stream);   // igemm2_conv.cu
 int igemm_pair_taps(const IgemmParams& p, int block_n);
+bool igemm_pair_resident(const IgemmParams& p, int block_n);   // the pair kernel would keep this CTA's weight half in smem
 
 }  // namespace dl
 
@@ -321,6 +322,7 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   p.y2 = static_cast<uint16_t*>(d->y_split);
   p.split_c = split > 0 ? split : 0;
   p.skip_n0 = -1;
+  p.half_skip = 0;
   p.num_m_blocks = (int)((M + 127) / 128);
 
   const int block_n = d->Cout <= 64 ? 64 : (d->Cout <= 128 ? 128 : 256);
@@ -337,6 +339,13 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   if (split > 0 && d->split_center_only && pair && p.taps == 1 && (d->R & 1) && (d->S & 1) && split % block_n == 0)
     p.skip_n0 = split / block_n;
   p.a_rows = 128 + (p.taps - 1) * d->dil_w;
+  // declared centre-tap-only upper half of ONE 256-wide tile (layer2's fused entry block): the resident pair kernel
+  // runs the two halves as separate N = 128 MMA streams, the upper one on the centre tap's K blocks only
+  DL_CHECK_ARG(d->center_only_from == 0 || (d->center_only_from > 0 && d->center_only_from < d->Cout && split == 0),
+               "conv_igemm: center_only_from must lie inside (0, Cout) and excludes split_channel");
+  if (d->center_only_from == 128 && d->Cout == 256 && pair && p.taps == 1 && (d->R & 1) && (d->S & 1) && !lin &&
+      igemm_pair_resident(p, block_n))
+    p.half_skip = 1;
 
   CUtensorMap mapA, mapB;
   if (lin) {
@@ -349,8 +358,10 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
                                d->stride_w, d->pad_h, d->pad_w, d->dil_h, d->dil_w, 64, 128);
   }
   if (st != DL_OK) return st;
+  // weight boxes: a CTA of a pair loads its half of the n block; in half_skip mode as two quarter boxes (64 conv1 rows
+  // + 64 skip rows), so that an N = 128 pair MMA finds "its" 64 rows at the same offset in both CTAs
   st = make_tiled_2d_bf16(&mapB, w_packed, (uint64_t)d->Cout, (uint64_t)Ktot, (uint64_t)Ktot,
-                          (uint32_t)(pair ? block_n / 2 : block_n), 64);
+                          (uint32_t)(p.half_skip ? block_n / 4 : (pair ? block_n / 2 : block_n)), 64);
   if (st != DL_OK) return st;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);

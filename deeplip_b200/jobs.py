@@ -75,6 +75,7 @@ class TrialListJob:
         self.table = torch.zeros((self.per * world, dim), dtype=torch.float32, device=self.device)
         self.local = self.table[rank * self.per:(rank + 1) * self.per]
         sl = trials.shard(rank, world)
+        self._sync_token = torch.zeros((1,), dtype=torch.float32, device=self.device)
         self.enrol = torch.from_numpy(np.ascontiguousarray(trials.enrol_idx[sl])).to(self.device)
         self.test = torch.from_numpy(np.ascontiguousarray(trials.test_idx[sl])).to(self.device)
 
@@ -113,6 +114,9 @@ class TrialListJob:
         tm.mark('extract')
         self._pre_checksum = _bits_checksum(self.local) if self.world > 1 else None
         tm.mark('checksum')
+        if self.world > 1:        # a one-element all_reduce on the stream: the ranks' skew (unequal clocks, a slower
+            dist.all_reduce(self._sync_token)      # shard) lands in its own span, not in the all_gather's
+        tm.mark('rank_skew')
         self.gather_table()
         tm.mark('all_gather')
         local_scores = score(self.table[:self.n_utts], self.enrol, self.test)

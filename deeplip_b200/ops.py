@@ -165,7 +165,8 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
 # ------------------------------------------------------------------ K3 / K5 / K7
 def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=(1, 1), scale=None, shift=None,
                slope=None, residual=None, want_bf16=True, want_f32=False, scale2=None, shift2=None,
-               f32_slope=1.0, H=None, W=None, out=None, out_channel_offset=0, residual_channel_offset=0, split=None):
+               f32_slope=1.0, H=None, W=None, out=None, out_channel_offset=0, residual_channel_offset=0, split=None,
+               center_only_from=0):
     """x: (N,H,W,ldx) bf16 channels-last -- or (N,img_rows,img_cols,ldx) stacked / guarded with the true extents
     passed as H, W.  `out` may be a wider (channel slice) and / or guarded (N, >=P, >=Q, ld) caller-owned buffer;
     with `out`, `residual` is a buffer of out's shape read at `residual_channel_offset` (the kernel indexes the residual
@@ -173,6 +174,7 @@ def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=
     split=(c, center_only): sibling convs in one launch -- output channels >= c go to a second dense tensor and, with
     center_only, are declared to have zero weights off the centre tap (dl_conv_desc.split_channel); the first return
     value is then the pair (y[..., :c], y[..., c:]) as two dense tensors.
+    center_only_from=c: declares channels >= c centre-tap-only without splitting the output (dl_conv_desc.center_only_from).
     Returns (y_bf16 (N,P,Q,Cout) | out | None, y_f32 (N*P*Q,Cout) | None)."""
     _need_cuda(x, w_packed, scale, shift, slope, residual, scale2, shift2)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
@@ -218,7 +220,7 @@ def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=
         assert residual_channel_offset == 0 or out is not None
         r_ptr = C.c_void_p(residual.data_ptr() + 2 * residual_channel_offset)
     d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ldy, Cout,
-                 float(f32_slope), img_rows, img_cols, 0, 0, 0, out_rows, out_cols)
+                 float(f32_slope), img_rows, img_cols, 0, 0, 0, out_rows, out_cols, 0, 0, None, int(center_only_from))
     st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
                                        r_ptr, y_ptr if y_ptr is not None else _ptr(y), _ptr(yf),
                                        _ptr(scale2), _ptr(shift2), C.byref(d), _stream())

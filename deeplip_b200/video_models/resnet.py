@@ -144,7 +144,8 @@ class BasicBlock(nn.Module):
         out: caller-owned (N, P, Q, 2 planes) buffer; returns it with the block output in channels [0, planes)."""
         pk = self._packed()
         both, _ = ops.conv_igemm(x, pk['wf'], self.inplanes, 2 * self.planes, 3, 3, (2, 2), (1, 1), (1, 1),
-                                 pk['sf'], pk['hf'], pk['af'], H=H, W=W)             # [conv1 | skip], pitch 2 planes
+                                 pk['sf'], pk['hf'], pk['af'], H=H, W=W,             # [conv1 | skip], pitch 2 planes
+                                 center_only_from=self.planes)
         ops.conv_igemm(both, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1), pk['s2'], pk['h2'],
                        pk['a2'], residual=both, residual_channel_offset=self.planes, out=out)
         return out

@@ -143,6 +143,12 @@ typedef struct dl_conv_desc {
    * skips their other K blocks.  Needs split_channel % 256 == 0, no residual, no f32 output, lin = 0. */
   int split_channel, split_center_only;
   void* y_split;
+  /* 0 = off.  Declares that output channels c >= center_only_from have zero weights off the filter's centre tap,
+   * WITHOUT a split output (layer2's entry block: conv1 and the 1x1 skip as one 64 -> 256 conv whose halves share one
+   * pitch-256 buffer).  With Cout = 256 and center_only_from = 128 the CTA-pair kernel multiplies the conv1 half with
+   * N = 128 MMAs over all taps and the skip half with N = 128 MMAs on the centre tap only (5/9 of the tensor work of
+   * the N = 256 form); every other kernel ignores the hint and multiplies the zeros: same bits. */
+  int center_only_from;
 } dl_conv_desc;
 
 int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,

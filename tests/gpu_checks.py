@@ -875,5 +875,5 @@ def trial_list_job_case(tmpdir, B=5, T=6, nsamp=16000, seed=3):
     assert err < 1e-5, err
     ref_eer, _ = scoring_ref.eer_from_scores(tl.labels, list(ref.astype(np.float32).reshape(-1, 1)))
     assert abs(res['eer'] - ref_eer) < 5e-4
-    assert job.verify_gather() and set(res['ms']) == {'extract', 'checksum', 'all_gather', 'score', 'gather_scores'}
+    assert job.verify_gather() and set(res['ms']) == {'extract', 'checksum', 'rank_skew', 'all_gather', 'score', 'gather_scores'}
     return {'n_utts': n, 'score_abs': err, 'eer': float(res['eer'])}

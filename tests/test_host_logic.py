@@ -451,7 +451,7 @@ assert np.array_equal(res['scores'].numpy(), ref)
 if rank == 0:
     eer, _ = scoring_ref.eer_from_scores(tl.labels, list(ref.reshape(-1, 1)))
     assert abs(res['eer'] - eer) < 1e-12 and 0.0 < eer < 0.5
-    assert set(res['ms']) == {'extract', 'checksum', 'all_gather', 'score', 'gather_scores'}
+    assert set(res['ms']) == {'extract', 'checksum', 'rank_skew', 'all_gather', 'score', 'gather_scores'}
 job.table[0, 0] += 1.0                    # a corrupted gather must be caught on every rank
 assert not job.verify_gather()
 D.barrier(); dist.destroy_process_group()
