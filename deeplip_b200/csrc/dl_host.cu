@@ -170,9 +170,10 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 
 namespace dl {
 static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1}, g_opt_dbg{0}, g_opt_tap_share{1}, g_opt_frontend{2},
-    g_opt_stft_pad{0}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{256};
+    g_opt_stft_pad{0}, g_opt_staged{1}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{256};
 int opt_pair() { return g_opt_pair.load(std::memory_order_relaxed); }
 int opt_pair_resident() { return g_opt_pair_resident.load(std::memory_order_relaxed); }
+int opt_staged_epilogue() { return g_opt_staged.load(std::memory_order_relaxed); }
 int opt_tap_share() { return g_opt_tap_share.load(std::memory_order_relaxed); }
 int opt_dbg() { return g_opt_dbg.load(std::memory_order_relaxed); }
 int opt_frontend() { return g_opt_frontend.load(std::memory_order_relaxed); }
@@ -196,6 +197,7 @@ int dl_set_option(const char* name, int value) {
   if (!strcmp(name, "statpool_slab")) { dl::g_opt_statpool_slab.store(value); return DL_OK; }
   if (!strcmp(name, "stft_pad")) { dl::g_opt_stft_pad.store(value); return DL_OK; }
   if (!strcmp(name, "pair_resident")) { dl::g_opt_pair_resident.store(value); return DL_OK; }
+  if (!strcmp(name, "staged_epilogue")) { dl::g_opt_staged.store(value); return DL_OK; }
   return dl::fail(DL_ERR_INVALID, "unknown option '%s'", name);
 }
 int dl_version(void) { return 100; }

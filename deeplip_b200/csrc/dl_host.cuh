@@ -32,6 +32,7 @@ int opt_statpool_mlp();    // stat pool: 16-byte loads in flight per lane, 4 (de
 int opt_statpool_slab();   // stat pool: channels per block, 256 (default) or 128 (half a warp per time step; measured slower)
 int opt_stft_pad();        // stft centre padding: 0 reflect (librosa < 0.10), 1 zeros (librosa >= 0.10)
 int opt_tap_share();     // pair kernel shares one operand-A box across horizontal taps (guarded-linear mode)
+int opt_staged_epilogue();   // 1 = resident pair kernels store their tiles through shared memory + TMA (default), 0 = per-lane stores
 int opt_pair_resident();   // resident weight-half variant of the pair kernel on / off                          // DL_OK or DL_ERR_UNSUPPORTED
 
 // 2-D tiled map over a row-major (rows, cols) 16-bit matrix with row pitch `ld` elements;

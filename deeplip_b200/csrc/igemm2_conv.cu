@@ -28,35 +28,50 @@ constexpr int kPairResidentMaxCout = 512;
 // is a valid operand).  A's share of the per-SM ingest (measured ceiling ~50 B/cycle) drops TAPS-fold.
 constexpr int kTapBoxRows = 144;                  // A box capacity: 128 + (TAPS-1)*dil_w <= 144
 
-template <int BLOCK_N, bool kResB, int TAPS>
+// kStg: output tiles leave through kStg 16 KB shared-memory staging buffers (128 rows x 64 channels, 128B swizzle)
+// and one TMA store per 64-channel slab -- full 128-byte lines, asynchronous -- instead of per-lane 16-byte stores at a
+// row-pitch stride (measured on the layer2 convs: the direct stores cost 26 of 180 us, on the fused entry 44 of 152).
+// Only the resident single-n-block variants use it (dense row-major y, no f32 side output).
+// kHalf (BLOCK_N = 256, resident): the n block's upper half is centre-tap-only (IgemmParams::half_skip): the weights
+// are kept compact (64 conv1 rows per K block + 64 skip rows for the centre tap's K blocks only: 80 KB instead of
+// 144 KB), which pays for six A stages (the kernel is load-latency bound with four) and two staging buffers.
+constexpr int kStgBytes = 128 * 128;
+constexpr int kHalfMaxBlocks = 10;                // conv1 K blocks + skip K blocks of the compact layout
+
+template <int BLOCK_N, bool kResB, int TAPS, int kStg = 0, bool kHalf = false>
 struct Igemm2Cfg {
   static_assert(TAPS == 1 || !kResB, "tap sharing streams its weights");
+  static_assert(kStg == 0 || (kResB && TAPS == 1), "the staged epilogue is built for the resident variants");
+  static_assert(!kHalf || (kResB && BLOCK_N == 256 && kStg > 0), "half-skip mode: resident 256-wide tile");
   static constexpr int A_BYTES = (TAPS > 1 ? kTapBoxRows : 128) * 64 * 2;
   static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of one weight K block
   static constexpr int STAGE_BYTES = kResB ? A_BYTES : A_BYTES + TAPS * B_BYTES;
-  static constexpr int BRES_BYTES = kResB ? kPairResidentBBytes : 0;
-  static constexpr int PSTRIDE = (kResB || TAPS > 1) ? kPairResidentMaxCout : kMaxCout;   // staged epilogue parameters
+  static constexpr int BRES_BYTES = kResB ? (kHalf ? kHalfMaxBlocks * (B_BYTES / 2) : kPairResidentBBytes) : 0;
+  // per-channel epilogue parameters staged in shared memory: one n block (<= BLOCK_N channels) in the kStg variants
+  static constexpr int PSTRIDE = kStg > 0 ? BLOCK_N : ((kResB || TAPS > 1) ? kPairResidentMaxCout : kMaxCout);
   static constexpr int STAGES =
-      kResB ? 4 : (TAPS == 1 ? (BLOCK_N == 256 ? 6 : 8) : (225 * 1024 - 3 * PSTRIDE * 4) / STAGE_BYTES);
+      kResB ? (kHalf ? 6 : 4) : (TAPS == 1 ? (BLOCK_N == 256 ? 6 : 8) : (225 * 1024 - 3 * PSTRIDE * 4) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
   static constexpr int PARAM_BYTES = 3 * PSTRIDE * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+  static constexpr int STG_BYTES = kStg * kStgBytes;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + STG_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
   static constexpr int THREADS = 320;
   static_assert(STAGES >= 2, "pipeline depth");
 };
 
-template <int BLOCK_N, bool kResB, int TAPS>
+template <int BLOCK_N, bool kResB, int TAPS, int kStg, bool kHalf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const IgemmParams p) {
-  using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS>;
+                   const __grid_constant__ CUtensorMap mapY, const IgemmParams p) {
+  using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS, kStg, kHalf>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* bres = smem + STAGES * Cfg::STAGE_BYTES;            // resident weight half (kResB only)
-  float* prm = reinterpret_cast<float*>(bres + Cfg::BRES_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bres + Cfg::BRES_BYTES + Cfg::PARAM_BYTES);
+  uint8_t* stg = bres + Cfg::BRES_BYTES;                       // kStg output staging buffers (1024-byte aligned)
+  float* prm = reinterpret_cast<float*>(stg + Cfg::STG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + Cfg::STG_BYTES + Cfg::PARAM_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -73,6 +88,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    if (kStg > 0) tma_prefetch_desc(&mapY);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -120,15 +136,20 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (elect_one_sync()) {
       if (kResB) {                       // whole weight half of this CTA, credited to the leader's barrier
         const uint32_t bb = mapa_shared(smem_u32(bfull), 0);
-        if (rank == 0) mbar_expect_tx_cluster(bb, 2u * (uint32_t)num_kb * Cfg::B_BYTES);
-        else mbar_arrive_cluster(bb);
-        if (BLOCK_N == 256 && p.half_skip) {
-          // this CTA's B block = [conv1 rows 64 rank .. +63 | skip rows 128 + 64 rank .. +63] (two 64-row boxes)
-          for (int kb = 0; kb < num_kb; ++kb) {
-            tma2_load_2d(bres + kb * Cfg::B_BYTES, &mapB, bb, kb * 64, (int)rank * 64);
-            tma2_load_2d(bres + kb * Cfg::B_BYTES + Cfg::B_BYTES / 2, &mapB, bb, kb * 64, 128 + (int)rank * 64);
-          }
+        if (kHalf) {
+          // compact layout, 64-row boxes: block kb = conv1 rows 64 rank .. +63 of K block kb; blocks num_kb .. =
+          // skip rows 128 + 64 rank .. +63 of the centre tap's K blocks.  An N = 128 pair MMA takes "its" 64 rows
+          // from the same offset in both CTAs.
+          constexpr uint32_t HB = Cfg::B_BYTES / 2;
+          const int ckb0 = ((p.R >> 1) * p.S + (p.S >> 1)) * p.cchunks;
+          if (rank == 0) mbar_expect_tx_cluster(bb, 2u * (uint32_t)(num_kb + p.cchunks) * HB);
+          else mbar_arrive_cluster(bb);
+          for (int kb = 0; kb < num_kb; ++kb) tma2_load_2d(bres + kb * HB, &mapB, bb, kb * 64, (int)rank * 64);
+          for (int c = 0; c < p.cchunks; ++c)
+            tma2_load_2d(bres + (num_kb + c) * HB, &mapB, bb, (ckb0 + c) * 64, 128 + (int)rank * 64);
         } else {
+          if (rank == 0) mbar_expect_tx_cluster(bb, 2u * (uint32_t)num_kb * Cfg::B_BYTES);
+          else mbar_arrive_cluster(bb);
           for (int kb = 0; kb < num_kb; ++kb)
             tma2_load_2d(bres + kb * Cfg::B_BYTES, &mapB, bb, kb * 64, (int)rank * (BLOCK_N / 2));
         }
@@ -218,22 +239,21 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
-        if (kResB && BLOCK_N == 256 && p.half_skip) {
-          // Two N = 128 streams into one 256-column accumulator: columns [0,128) = conv1 over every K block (B rows
-          // 0..63 of each CTA's block), columns [128,256) = the skip conv over the centre tap's K blocks only (B rows
-          // 64..127).  36 + 4 half-width MMAs per tile instead of 36 full-width ones; bit-identical (the products
-          // left out are exact zeros).
+        if (kHalf) {
+          // Two N = 128 streams into one 256-column accumulator: columns [0,128) = conv1 over every K block,
+          // columns [128,256) = the skip conv over the centre tap's K blocks only.  36 + 4 half-width MMAs per tile
+          // instead of 36 full-width ones; bit-identical (the products left out are exact zeros).
           constexpr uint32_t idesc_h = umma_idesc_bf16(256, 128);
           const int ckb0 = ((p.R >> 1) * p.S + (p.S >> 1)) * p.cchunks;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + stage * Cfg::STAGE_BYTES));
-            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(bres) + kb * Cfg::B_BYTES);
+            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(bres) + kb * (Cfg::B_BYTES / 2));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc_h, (kb | k) != 0 ? 1u : 0u);
             if (kb >= ckb0 && kb < ckb0 + p.cchunks) {
-              const uint64_t sdesc = bdesc + (uint64_t)((Cfg::B_BYTES / 2) >> 4);
+              const uint64_t sdesc = umma_desc_sw128_kmajor(smem_u32(bres) + (num_kb + kb - ckb0) * (Cfg::B_BYTES / 2));
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma2_bf16(d + 128, adesc + 2 * k, sdesc + 2 * k, idesc_h, (kb != ckb0 || k != 0) ? 1u : 0u);
             }
@@ -269,19 +289,27 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const bool fast = p.y != nullptr && p.yf == nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int sbuf = 0;                                  // kStg: staging buffer of the next slab
+    const bool issuer = warp == 2 && lane == 0;    // kStg: the thread that owns this CTA's TMA stores
     for (int t = pair; t < total; t += num_pairs) {
       int mp, n_blk;
       tile_of(t, mp, n_blk);
-      long long row = (long long)(2 * mp + (int)rank) * 128 + quarter * 32 + lane;
+      const int tile_row0 = (2 * mp + (int)rank) * 128;
+      long long row = (long long)tile_row0 + quarter * 32 + lane;
       const bool row_ok = igemm_map_row(p, row) && !(p.dbg & 2);
       const int cbase = n_blk * BLOCK_N;
       uint4 res[4];
       igemm_prefetch_residual(p, row, row_ok, cbase, chunk0, has_res, res);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      if (!(p.dbg & 4))
-      igemm_epilogue_tile<BLOCK_N>(p, prm, Cfg::PSTRIDE, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0, has_res, fast,
-                                   res);
+      if (!(p.dbg & 4)) {
+        if constexpr (kStg > 0)
+          igemm_epilogue_tile_staged<BLOCK_N, kStg>(p, prm, Cfg::PSTRIDE, tmem_base + acc * BLOCK_N, row, row_ok, tile_row0, cbase,
+                                                    quarter, chunk0, has_res, res, stg, sbuf, &mapY, issuer);
+        else
+          igemm_epilogue_tile<BLOCK_N>(p, prm, Cfg::PSTRIDE, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0,
+                                       has_res, fast, res);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // the leader's MMA thread waits
@@ -290,6 +318,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
   }
 
+  if (kStg > 0 && warp == 2 && lane == 0) bulk_wait_group0();     // this CTA's outstanding output stores
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                 // nobody leaves (or frees TMEM) while the peer may still touch this CTA
@@ -299,15 +328,16 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
 }
 
-template <int BLOCK_N, bool kResB, int TAPS>
-static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, cudaStream_t stream) {
-  using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS>;
+template <int BLOCK_N, bool kResB, int TAPS, int kStg = 0, bool kHalf = false>
+static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, cudaStream_t stream,
+                         const CUtensorMap* mapY = nullptr) {
+  using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS, kStg, kHalf>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
   static PerDevice<bool> configured_dev;
   bool* configured = configured_dev.slot();
   if (!configured) return fail(DL_ERR_CUDA, "igemm2: no current device");
   if (!*configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N, kResB, TAPS>,
+    cudaError_t e = cudaFuncSetAttribute(igemm2_conv_kernel<BLOCK_N, kResB, TAPS, kStg, kHalf>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(DL_ERR_CUDA, "igemm2 smem attribute: %s", cudaGetErrorString(e));
     *configured = true;
@@ -317,7 +347,8 @@ static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const
   if (pairs <= 0) pairs = 74;
   if (super_tiles < pairs) pairs = super_tiles;
   if ((p.dbg & 64) && pairs > 1) pairs /= 2;          // measurement aid: half the SMs (per-SM vs chip-wide ingest)
-  igemm2_conv_kernel<BLOCK_N, kResB, TAPS><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+  igemm2_conv_kernel<BLOCK_N, kResB, TAPS, kStg, kHalf><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
+      mapA, mapB, mapY ? *mapY : mapA, p);
   return check_launch("igemm2_conv_kernel");
 }
 
@@ -330,6 +361,19 @@ int igemm_pair_taps(const IgemmParams& p, int block_n) {
   return 1;
 }
 
+bool igemm_pair_resident(const IgemmParams& p, int block_n);
+
+// Which staged variant (if any) launch_igemm_pair would pick: 0 none, 1 = 128-wide resident tile, 2 = half-skip entry tile
+// (compact weights: at most kHalfMaxBlocks 64-row blocks).
+int igemm_pair_staged(const IgemmParams& p, int block_n, bool want_half) {
+  if (!opt_staged_epilogue() || !igemm_pair_resident(p, block_n) || p.y == nullptr || p.yf != nullptr || p.lin || p.out_wp > 0 ||
+      p.split_c > 0 || p.Cout % 64 != 0 || (reinterpret_cast<uintptr_t>(p.y) & 15) != 0)
+    return 0;
+  if (block_n == 256 && want_half && p.R * p.S * p.cchunks + p.cchunks <= kHalfMaxBlocks) return 2;
+  if (block_n == 128) return 1;
+  return 0;
+}
+
 bool igemm_pair_resident(const IgemmParams& p, int block_n) {
   const long long num_kb = (long long)p.R * p.S * p.cchunks;
   return opt_pair_resident() && p.taps == 1 && p.num_n_blocks == 1 && num_kb * (block_n / 2) * 128 <= kPairResidentBBytes &&
@@ -338,11 +382,18 @@ bool igemm_pair_resident(const IgemmParams& p, int block_n) {
 
 // Called by dl_conv_igemm_bf16 (igemm_conv.cu) for wide, large-M problems.
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const CUtensorMap* mapY) {
   if (p.taps == 3)
     return block_n == 128 ? launch_igemm2<128, false, 3>(mapA, mapB, p, stream) : launch_igemm2<256, false, 3>(mapA, mapB, p, stream);
   if (p.taps == 5) return launch_igemm2<256, false, 5>(mapA, mapB, p, stream);
   const bool res = igemm_pair_resident(p, block_n);
+  // mapY != nullptr: the caller found the output eligible for the staged (TMA store) epilogue, see igemm_pair_staged
+  if (res && mapY != nullptr) {
+    if (block_n == 256 && p.half_skip) return launch_igemm2<256, true, 1, 2, true>(mapA, mapB, p, stream, mapY);
+    // 128-wide resident tile: four A stages + ONE staging buffer is all that fits next to the 144 KB of weights (three
+    // stages + two buffers measured 218 vs 171 us on the layer2 convs: the im2col pipeline needs its depth)
+    if (block_n == 128) return launch_igemm2<128, true, 1, 1, false>(mapA, mapB, p, stream, mapY);
+  }
   if (block_n == 128) return res ? launch_igemm2<128, true, 1>(mapA, mapB, p, stream) : launch_igemm2<128, false, 1>(mapA, mapB, p, stream);
   return res ? launch_igemm2<256, true, 1>(mapA, mapB, p, stream) : launch_igemm2<256, false, 1>(mapA, mapB, p, stream);
 }

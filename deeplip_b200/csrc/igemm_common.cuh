@@ -173,4 +173,86 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const 
   }
 }
 
+// Staged form of the fast path above for the resident CTA-pair kernels (one n block, dense row-major y, Cout % 64 == 0):
+// the 8 epilogue warps of a CTA assemble one [128 rows x 64 channels] bf16 slab at a time in a 16 KB shared-memory
+// buffer (128-byte rows, 128B swizzle -- the layout the TMA store expects) and one thread sends it with ONE
+// cp.async.bulk.tensor store: full 128-byte lines, asynchronous, rows past M clipped by the tensor map.  NBUF = 2:
+// slab k+1 is assembled while slab k drains (one named barrier per slab); NBUF = 1: the buffer is reclaimed first
+// (two barriers per slab).  Warps with chunk0 = 0 / 1 fill the lower / upper 32 channels of every row.
+// Arithmetic and rounding are those of igemm_epilogue_tile: same bits.
+template <int BLOCK_N, int NBUF>
+__device__ __forceinline__ void igemm_epilogue_tile_staged(const IgemmParams& p, const float* prm, int pstride,
+                                                           uint32_t tmem_acc, long long row, bool row_ok, int tile_row0,
+                                                           int cbase, int quarter, int chunk0, bool has_res,
+                                                           uint4 (&res)[4], uint8_t* stg, int& sbuf, const void* mapY,
+                                                           bool issuer) {
+  const int m = quarter * 32 + (int)lane_id();
+#pragma unroll 1
+  for (int i = 0; i < BLOCK_N / 64; ++i) {
+    if (cbase + 64 * i >= p.Cout) break;                 // the same for all eight warps
+    const int j = 2 * i + chunk0;
+    const int c0 = cbase + j * 32;
+    uint32_t acc_r[32];
+    tmem_ld_32x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + j * 32, acc_r);
+    uint4 res_cur[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) res_cur[g] = res[g];
+    if (has_res && row_ok && i + 1 < BLOCK_N / 64 && c0 + 96 <= p.Cout) {      // prefetch the next slab's residual
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.ldy + c0 + 64);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) res[g] = __ldg(rp + g);
+    }
+    tmem_ld_wait();
+    const float4* sc = reinterpret_cast<const float4*>(prm + c0);
+    const float4* sh = reinterpret_cast<const float4*>(prm + pstride + c0);
+    const float4* sl = reinterpret_cast<const float4*>(prm + 2 * pstride + c0);
+    uint4 o[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 s4 = sc[2 * g + h], h4 = sh[2 * g + h];
+        v[4 * h + 0] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 0]), s4.x, h4.x);
+        v[4 * h + 1] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 1]), s4.y, h4.y);
+        v[4 * h + 2] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 2]), s4.z, h4.z);
+        v[4 * h + 3] = fmaf(__uint_as_float(acc_r[8 * g + 4 * h + 3]), s4.w, h4.w);
+      }
+      if (has_res && row_ok) {
+        const uint4 rr = res_cur[g];
+        v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+        v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 l4 = sl[2 * g + h];
+        v[4 * h + 0] = v[4 * h + 0] > 0.f ? v[4 * h + 0] : v[4 * h + 0] * l4.x;
+        v[4 * h + 1] = v[4 * h + 1] > 0.f ? v[4 * h + 1] : v[4 * h + 1] * l4.y;
+        v[4 * h + 2] = v[4 * h + 2] > 0.f ? v[4 * h + 2] : v[4 * h + 2] * l4.z;
+        v[4 * h + 3] = v[4 * h + 3] > 0.f ? v[4 * h + 3] : v[4 * h + 3] * l4.w;
+      }
+      o[g].x = pack_bf16x2(v[0], v[1]); o[g].y = pack_bf16x2(v[2], v[3]);
+      o[g].z = pack_bf16x2(v[4], v[5]); o[g].w = pack_bf16x2(v[6], v[7]);
+    }
+    uint8_t* sb = stg + sbuf * (128 * 128);
+    if (NBUF == 1) {                                     // reclaim the only buffer: its last store has read it
+      if (issuer) bulk_wait_group_read0();
+      named_bar_sync(1, 256);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(sb + m * 128 + (((chunk0 * 4 + g) ^ (m & 7)) << 4)) = o[g];
+    fence_proxy_async_smem();                            // generic-proxy writes -> visible to the TMA unit
+    // NBUF == 2: the previous slab's store (other buffer) must have read its buffer before anyone passes this barrier
+    // and starts on the slab after this one
+    if (NBUF == 2 && issuer) bulk_wait_group_read0();
+    named_bar_sync(1, 256);
+    if (issuer && !(p.dbg & 2)) {
+      tma_store_2d(mapY, sb, cbase + 64 * i, tile_row0);
+      bulk_commit_group();
+    }
+    if (NBUF == 2) sbuf ^= 1;
+  }
+}
+
 }  // namespace dl

@@ -226,7 +226,8 @@ static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
 }
 
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
-                      cudaStream_t stream);   // igemm2_conv.cu
+                      cudaStream_t stream, const CUtensorMap* mapY);   // igemm2_conv.cu
+int igemm_pair_staged(const IgemmParams& p, int block_n, bool want_half);   // 0 none, 1 = 128-wide, 2 = half-skip entry tile
 int igemm_pair_taps(const IgemmParams& p, int block_n);
 bool igemm_pair_resident(const IgemmParams& p, int block_n);   // the pair kernel would keep this CTA's weight half in smem
 
@@ -343,9 +344,9 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   // runs the two halves as separate N = 128 MMA streams, the upper one on the centre tap's K blocks only
   DL_CHECK_ARG(d->center_only_from == 0 || (d->center_only_from > 0 && d->center_only_from < d->Cout && split == 0),
                "conv_igemm: center_only_from must lie inside (0, Cout) and excludes split_channel");
-  if (d->center_only_from == 128 && d->Cout == 256 && pair && p.taps == 1 && (d->R & 1) && (d->S & 1) && !lin &&
-      igemm_pair_resident(p, block_n))
-    p.half_skip = 1;
+  const bool want_half = d->center_only_from == 128 && d->Cout == 256 && p.taps == 1 && (d->R & 1) && (d->S & 1);
+  const int staged = pair ? igemm_pair_staged(p, block_n, want_half) : 0;
+  p.half_skip = staged == 2 ? 1 : 0;
 
   CUtensorMap mapA, mapB;
   if (lin) {
@@ -365,7 +366,14 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   if (st != DL_OK) return st;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (pair) return launch_igemm_pair(mapA, mapB, p, block_n, s);
+  if (pair) {
+    CUtensorMap mapY;
+    if (staged) {       // 64-channel x 128-row boxes of the dense (M, ldy) output; rows past M are clipped by the TMA unit
+      st = make_tiled_2d_bf16(&mapY, y, (uint64_t)M, (uint64_t)d->Cout, (uint64_t)d->ldy, 128, 64);
+      if (st != DL_OK) return st;
+    }
+    return launch_igemm_pair(mapA, mapB, p, block_n, s, staged ? &mapY : nullptr);
+  }
   switch (block_n) {
     case 64: return resident ? launch_igemm<64, true>(mapA, mapB, p, s) : launch_igemm<64, false>(mapA, mapB, p, s);
     case 128: return resident ? launch_igemm<128, true>(mapA, mapB, p, s) : launch_igemm<128, false>(mapA, mapB, p, s);
