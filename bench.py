@@ -512,17 +512,21 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     trunk_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
     trunk_tflops = GFLOP_TRUNK_PER_UTT * B / trunk_ms          # GFLOP / ms == TFLOP/s
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r1v_trunk_traffic.json')
-    if os.path.exists(tpath) and B == 64:          # dram bytes per launch from the committed ncu capture
+    # DRAM bytes per launch: ncu cannot run inside the bench (a number taken under a profiler is not a bench value), so
+    # this cites the committed capture of the same step, and says which commit's kernels it saw
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'r2c_trunk_traffic.json')
+    if os.path.exists(tpath) and B == 64:
         tj = json.load(open(tpath))
         traffic = tj['trunk_dram_bytes_per_step'] / max(1, n_trunk)
+        traffic_src = 'avg DRAM bytes per trunk launch: ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d trunk ' \
+                      'launches of one step, %s, captured at commit %s' % (tj['trunk_conv_launches'], tj['source'], tj.get('commit'))
     roofline = {'kernel': 'igemm_conv / igemm2_conv / conv3x3_halo kernels (the %d ResNet-18 trunk conv launches of one step; '
                           'entry blocks run conv1 + skip as one launch)' % n_trunk,
                 'bound': 'tensor',
                 'achieved': trunk_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': trunk_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
-                'traffic_note': 'avg DRAM bytes per trunk launch (ncu dram__bytes_read+write, profiles/r1v_step_traffic.txt)',
+                'traffic_note': traffic_src,
                 'peak_src': peaks['src'] + ' (sustained bf16 cuBLAS)', 'launches': n_trunk,
                 'avg_launch_ms': trunk_ms / max(1, n_trunk),
                 'flop_per_launch': GFLOP_TRUNK_PER_UTT * B * 1e9 / max(1, n_trunk)}

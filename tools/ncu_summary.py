@@ -1,9 +1,10 @@
-"""Key metrics + hottest SASS lines of one ncu report.  python tools/ncu_summary.py rep.ncu-rep [out.md]"""
+"""Key metrics + hottest SASS lines of one ncu report.  python tools/ncu_summary.py rep.ncu-rep [out.md] [launch index in the report]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+hdr, units, vals = rows[0], rows[1], rows[2 + which]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active',
@@ -18,7 +19,7 @@ out = ['## %s' % vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else '##
 for h, u, v in zip(hdr, units, vals):
     if h in want:
         out.append('- `%s` = %s %s' % (h, v, u))
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--launch-skip', str(which), '--launch-count', '1'], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
 sh = srows[1]; data = srows[2:]
 ix = {h: i for i, h in enumerate(sh)}
