@@ -31,7 +31,9 @@ constexpr int kTapBoxRows = 144;                  // A box capacity: 128 + (TAPS
 // kStg: output tiles leave through kStg 16 KB shared-memory staging buffers (128 rows x 64 channels, 128B swizzle)
 // and one TMA store per 64-channel slab -- full 128-byte lines, asynchronous -- instead of per-lane 16-byte stores at a
 // row-pitch stride (measured on the layer2 convs: the direct stores cost 26 of 180 us, on the fused entry 44 of 152).
-// Only the resident single-n-block variants use it (dense row-major y, no f32 side output).
+// Needs a dense row-major y (no guarded layouts) and no f32 side output; a split output brings a second tensor map.
+// Short-K layers gain most: on the E-TDNN k=1 layers (K = 512) the per-lane stores were 3.7 of 15.9 us at B = 64 and
+// 19 of 48 us at B = 256 (tools/tdnn_fixed.py).
 // kHalf (BLOCK_N = 256, resident): the n block's upper half is centre-tap-only (IgemmParams::half_skip): the weights
 // are kept compact (64 conv1 rows per K block + 64 skip rows for the centre tap's K blocks only: 80 KB instead of
 // 144 KB), which pays for six A stages (the kernel is load-latency bound with four) and two staging buffers.
@@ -41,16 +43,19 @@ constexpr int kHalfMaxBlocks = 10;                // conv1 K blocks + skip K blo
 template <int BLOCK_N, bool kResB, int TAPS, int kStg = 0, bool kHalf = false>
 struct Igemm2Cfg {
   static_assert(TAPS == 1 || !kResB, "tap sharing streams its weights");
-  static_assert(kStg == 0 || (kResB && TAPS == 1), "the staged epilogue is built for the resident variants");
+  static_assert(kStg == 0 || TAPS == 1, "the staged epilogue is not built for the tap-sharing variants");
+  static_assert(kStg == 0 || kResB || (BLOCK_N == 256 && kStg == 2), "streaming-weights staged variant: 256-wide, two buffers");
   static_assert(!kHalf || (kResB && BLOCK_N == 256 && kStg > 0), "half-skip mode: resident 256-wide tile");
   static constexpr int A_BYTES = (TAPS > 1 ? kTapBoxRows : 128) * 64 * 2;
   static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of one weight K block
   static constexpr int STAGE_BYTES = kResB ? A_BYTES : A_BYTES + TAPS * B_BYTES;
   static constexpr int BRES_BYTES = kResB ? (kHalf ? kHalfMaxBlocks * (B_BYTES / 2) : kPairResidentBBytes) : 0;
   // per-channel epilogue parameters staged in shared memory: one n block (<= BLOCK_N channels) in the kStg variants
-  static constexpr int PSTRIDE = kStg > 0 ? BLOCK_N : ((kResB || TAPS > 1) ? kPairResidentMaxCout : kMaxCout);
+  static constexpr int PSTRIDE = (kStg > 0 && kResB) ? BLOCK_N : ((kResB || TAPS > 1) ? kPairResidentMaxCout : kMaxCout);
+  // streaming weights + staging: five 32 KB stages instead of six make room for the two 16 KB staging buffers
   static constexpr int STAGES =
-      kResB ? (kHalf ? 6 : 4) : (TAPS == 1 ? (BLOCK_N == 256 ? 6 : 8) : (225 * 1024 - 3 * PSTRIDE * 4) / STAGE_BYTES);
+      kResB ? (kHalf ? 6 : 4)
+            : (TAPS == 1 ? (BLOCK_N == 256 ? (kStg > 0 ? 5 : 6) : 8) : (225 * 1024 - 3 * PSTRIDE * 4) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
   static constexpr int PARAM_BYTES = 3 * PSTRIDE * 4;
@@ -63,7 +68,8 @@ struct Igemm2Cfg {
 template <int BLOCK_N, bool kResB, int TAPS, int kStg, bool kHalf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const __grid_constant__ CUtensorMap mapY, const IgemmParams p) {
+                   const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapY2,
+                   const IgemmParams p) {
   using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS, kStg, kHalf>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -88,7 +94,10 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
-    if (kStg > 0) tma_prefetch_desc(&mapY);
+    if (kStg > 0) {
+      tma_prefetch_desc(&mapY);
+      if (p.split_c > 0) tma_prefetch_desc(&mapY2);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -305,7 +314,9 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       if (!(p.dbg & 4)) {
         if constexpr (kStg > 0)
           igemm_epilogue_tile_staged<BLOCK_N, kStg>(p, prm, Cfg::PSTRIDE, tmem_base + acc * BLOCK_N, row, row_ok, tile_row0, cbase,
-                                                    quarter, chunk0, has_res, res, stg, sbuf, &mapY, issuer);
+                                                    quarter, chunk0, has_res, res, stg, sbuf,
+                                                    (p.split_c > 0 && cbase >= p.split_c) ? &mapY2 : &mapY,
+                                                    (p.split_c > 0 && cbase >= p.split_c) ? cbase - p.split_c : cbase, issuer);
         else
           igemm_epilogue_tile<BLOCK_N>(p, prm, Cfg::PSTRIDE, tmem_base + acc * BLOCK_N, row, row_ok, cbase, quarter, chunk0,
                                        has_res, fast, res);
@@ -330,7 +341,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
 template <int BLOCK_N, bool kResB, int TAPS, int kStg = 0, bool kHalf = false>
 static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, cudaStream_t stream,
-                         const CUtensorMap* mapY = nullptr) {
+                         const CUtensorMap* mapY = nullptr, const CUtensorMap* mapY2 = nullptr) {
   using Cfg = Igemm2Cfg<BLOCK_N, kResB, TAPS, kStg, kHalf>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared-memory budget");
   static PerDevice<bool> configured_dev;
@@ -348,7 +359,7 @@ static int launch_igemm2(const CUtensorMap& mapA, const CUtensorMap& mapB, const
   if (super_tiles < pairs) pairs = super_tiles;
   if ((p.dbg & 64) && pairs > 1) pairs /= 2;          // measurement aid: half the SMs (per-SM vs chip-wide ingest)
   igemm2_conv_kernel<BLOCK_N, kResB, TAPS, kStg, kHalf><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(
-      mapA, mapB, mapY ? *mapY : mapA, p);
+      mapA, mapB, mapY ? *mapY : mapA, mapY2 ? *mapY2 : mapA, p);
   return check_launch("igemm2_conv_kernel");
 }
 
@@ -364,11 +375,13 @@ int igemm_pair_taps(const IgemmParams& p, int block_n) {
 bool igemm_pair_resident(const IgemmParams& p, int block_n);
 
 // Which staged variant (if any) launch_igemm_pair would pick: 0 none, 1 = 128-wide resident tile, 2 = half-skip entry tile
-// (compact weights: at most kHalfMaxBlocks 64-row blocks).
+// (compact weights: at most kHalfMaxBlocks 64-row blocks), 3 = 256-wide tiles with streaming weights.
 int igemm_pair_staged(const IgemmParams& p, int block_n, bool want_half) {
-  if (!opt_staged_epilogue() || !igemm_pair_resident(p, block_n) || p.y == nullptr || p.yf != nullptr || p.lin || p.out_wp > 0 ||
-      p.split_c > 0 || p.Cout % 64 != 0 || (reinterpret_cast<uintptr_t>(p.y) & 15) != 0)
+  if (!opt_staged_epilogue() || p.taps != 1 || p.y == nullptr || p.yf != nullptr || p.lin || p.out_wp > 0 ||
+      (reinterpret_cast<uintptr_t>(p.y) & 15) != 0 || (p.split_c > 0 && (reinterpret_cast<uintptr_t>(p.y2) & 15) != 0))
     return 0;
+  if (!igemm_pair_resident(p, block_n)) return block_n == 256 ? 3 : 0;      // streaming weights, 256-wide tiles
+  if (p.split_c > 0) return 0;
   if (block_n == 256 && want_half && p.R * p.S * p.cchunks + p.cchunks <= kHalfMaxBlocks) return 2;
   if (block_n == 128) return 1;
   return 0;
@@ -382,7 +395,7 @@ bool igemm_pair_resident(const IgemmParams& p, int block_n) {
 
 // Called by dl_conv_igemm_bf16 (igemm_conv.cu) for wide, large-M problems.
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
-                      cudaStream_t stream, const CUtensorMap* mapY) {
+                      cudaStream_t stream, const CUtensorMap* mapY, const CUtensorMap* mapY2) {
   if (p.taps == 3)
     return block_n == 128 ? launch_igemm2<128, false, 3>(mapA, mapB, p, stream) : launch_igemm2<256, false, 3>(mapA, mapB, p, stream);
   if (p.taps == 5) return launch_igemm2<256, false, 5>(mapA, mapB, p, stream);
@@ -394,6 +407,7 @@ int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const Ig
     // stages + two buffers measured 218 vs 171 us on the layer2 convs: the im2col pipeline needs its depth)
     if (block_n == 128) return launch_igemm2<128, true, 1, 1, false>(mapA, mapB, p, stream, mapY);
   }
+  if (!res && mapY != nullptr && block_n == 256) return launch_igemm2<256, false, 1, 2, false>(mapA, mapB, p, stream, mapY, mapY2);
   if (block_n == 128) return res ? launch_igemm2<128, true, 1>(mapA, mapB, p, stream) : launch_igemm2<128, false, 1>(mapA, mapB, p, stream);
   return res ? launch_igemm2<256, true, 1>(mapA, mapB, p, stream) : launch_igemm2<256, false, 1>(mapA, mapB, p, stream);
 }

@@ -173,7 +173,8 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& p, const 
   }
 }
 
-// Staged form of the fast path above for the resident CTA-pair kernels (one n block, dense row-major y, Cout % 64 == 0):
+// Staged form of the fast path above for the CTA-pair kernels (dense row-major y; channels past Cout in the last slab
+// are computed on garbage and clipped by the tensor map):
 // the 8 epilogue warps of a CTA assemble one [128 rows x 64 channels] bf16 slab at a time in a 16 KB shared-memory
 // buffer (128-byte rows, 128B swizzle -- the layout the TMA store expects) and one thread sends it with ONE
 // cp.async.bulk.tensor store: full 128-byte lines, asynchronous, rows past M clipped by the tensor map.  NBUF = 2:
@@ -185,7 +186,7 @@ __device__ __forceinline__ void igemm_epilogue_tile_staged(const IgemmParams& p,
                                                            uint32_t tmem_acc, long long row, bool row_ok, int tile_row0,
                                                            int cbase, int quarter, int chunk0, bool has_res,
                                                            uint4 (&res)[4], uint8_t* stg, int& sbuf, const void* mapY,
-                                                           bool issuer) {
+                                                           int col0, bool issuer) {
   const int m = quarter * 32 + (int)lane_id();
 #pragma unroll 1
   for (int i = 0; i < BLOCK_N / 64; ++i) {
@@ -248,7 +249,7 @@ __device__ __forceinline__ void igemm_epilogue_tile_staged(const IgemmParams& p,
     if (NBUF == 2 && issuer) bulk_wait_group_read0();
     named_bar_sync(1, 256);
     if (issuer && !(p.dbg & 2)) {
-      tma_store_2d(mapY, sb, cbase + 64 * i, tile_row0);
+      tma_store_2d(mapY, sb, col0 + 64 * i, tile_row0);      // col0: this n block's first channel in mapY's tensor
       bulk_commit_group();
     }
     if (NBUF == 2) sbuf ^= 1;

@@ -226,8 +226,8 @@ static int launch_igemm(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
 }
 
 int launch_igemm_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const IgemmParams& p, int block_n,
-                      cudaStream_t stream, const CUtensorMap* mapY);   // igemm2_conv.cu
-int igemm_pair_staged(const IgemmParams& p, int block_n, bool want_half);   // 0 none, 1 = 128-wide, 2 = half-skip entry tile
+                      cudaStream_t stream, const CUtensorMap* mapY, const CUtensorMap* mapY2);   // igemm2_conv.cu
+int igemm_pair_staged(const IgemmParams& p, int block_n, bool want_half);   // 0 none, 1 = 128-wide, 2 = half-skip entry tile, 3 = streaming 256-wide
 int igemm_pair_taps(const IgemmParams& p, int block_n);
 bool igemm_pair_resident(const IgemmParams& p, int block_n);   // the pair kernel would keep this CTA's weight half in smem
 
@@ -367,12 +367,14 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (pair) {
-    CUtensorMap mapY;
-    if (staged) {       // 64-channel x 128-row boxes of the dense (M, ldy) output; rows past M are clipped by the TMA unit
-      st = make_tiled_2d_bf16(&mapY, y, (uint64_t)M, (uint64_t)d->Cout, (uint64_t)d->ldy, 128, 64);
+    CUtensorMap mapY, mapY2;
+    if (staged) {       // 64-channel x 128-row boxes of the dense (M, ldy) output; rows past M / channels past Cout are clipped by the TMA unit
+      st = make_tiled_2d_bf16(&mapY, y, (uint64_t)M, (uint64_t)(split > 0 ? split : d->Cout), (uint64_t)d->ldy, 128, 64);
+      if (st == DL_OK && split > 0)
+        st = make_tiled_2d_bf16(&mapY2, d->y_split, (uint64_t)M, (uint64_t)(d->Cout - split), (uint64_t)d->ldy, 128, 64);
       if (st != DL_OK) return st;
     }
-    return launch_igemm_pair(mapA, mapB, p, block_n, s, staged ? &mapY : nullptr);
+    return launch_igemm_pair(mapA, mapB, p, block_n, s, staged ? &mapY : nullptr, (staged && split > 0) ? &mapY2 : nullptr);
   }
   switch (block_n) {
     case 64: return resident ? launch_igemm<64, true>(mapA, mapB, p, s) : launch_igemm<64, false>(mapA, mapB, p, s);
