@@ -74,3 +74,22 @@ def max_over_ranks(value, device):
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+_HOST_GROUP = None
+
+
+def host_barrier():
+    """Barrier that BLOCKS on sockets (a gloo group created on first use) instead of spinning: ranks that wait for
+    rank 0's CPU work (the EER, the oracle check) in an NCCL barrier each burn a core in cudaStreamSynchronize, and an
+    OpenMP team sized to all cores then collapses (measured: the 43-utterance oracle sample 2 s alone, 65 s next to
+    three spinning ranks).  Collective: every rank must call it the same number of times."""
+    global _HOST_GROUP
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    if dist.get_backend() == 'gloo':
+        dist.barrier()
+        return
+    if _HOST_GROUP is None:
+        _HOST_GROUP = dist.new_group(backend='gloo')
+    dist.barrier(group=_HOST_GROUP)
