@@ -200,7 +200,94 @@ CONV_CASES = {
     'pair_128': dict(N=300, H=11, W=11, C=128, Cout=128, R=3, S=3, stride=1, pad=1, residual=True),
     'pair_256_s2': dict(N=1101, H=11, W=11, C=128, Cout=256, R=3, S=3, stride=2, pad=1),
     'pair_512_odd': dict(N=3700, H=3, W=3, C=256, Cout=512, R=3, S=3, stride=1, pad=1, residual=True),
+    # staged (TMA store) epilogue of the streaming pair kernel with a last slab that is half outside Cout (1504 = 23.5 x 64)
+    'pair_tdnn_k1_1504': dict(N=70, H=1, W=280, C=512, Cout=1500, R=1, S=1),
+    'pair_tdnn_k3_res_odd_rows': dict(N=67, H=1, W=293, C=512, Cout=512, R=1, S=3, dil=(1, 2), residual=True),
 }
+
+
+def conv_center_only_case(N=150, H=22, W=22, seed=5):
+    """dl_conv_desc.center_only_from: a 64 -> 256 3x3 stride-2 conv whose channels >= 128 carry a 1x1 conv on the centre
+    tap (layer2's fused entry block) at a size that runs on the CTA-pair kernel: with the hint (two N = 128 MMA streams,
+    compact weights, staged epilogue) == without it (N = 256 MMAs over the zero weights, per-lane stores with
+    staged_epilogue = 0) bit for bit, and both == the fp32 reference within tolerance."""
+    from deeplip_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(N, H, W, 64, generator=g))
+    w1 = bf16r(torch.randn(128, 64, 3, 3, generator=g) / 24.0)
+    wd = bf16r(torch.randn(128, 64, 1, 1, generator=g) / 8.0)
+    scale, shift, slope = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.2, torch.rand(256, generator=g) * 0.5
+    ref = torch.cat([F.conv2d(x.permute(0, 3, 1, 2), w1, None, stride=2, padding=1),
+                     F.conv2d(x.permute(0, 3, 1, 2), wd, None, stride=2, padding=0)], dim=1)
+    ref = ref * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = torch.where(ref > 0, ref, ref * slope[None, :, None, None])
+    wf = torch.zeros((256, 9 * 64), device=DEV, dtype=torch.bfloat16)
+    wf[:128] = packing.pack_conv_weight(w1.to(DEV))
+    wf[128:, 4 * 64:5 * 64] = packing.pack_conv_weight(wd.to(DEV))
+    xd = x.to(DEV).to(torch.bfloat16)
+    args = (xd, wf, 64, 256, 3, 3, (2, 2), (1, 1), (1, 1), scale.to(DEV), shift.to(DEV), slope.to(DEV))
+    hinted, _ = ops.conv_igemm(*args, center_only_from=128)
+    _lib.set_option('staged_epilogue', 0)
+    try:
+        plain, _ = ops.conv_igemm(*args)
+    finally:
+        _lib.set_option('staged_epilogue', 1)
+    torch.cuda.synchronize()
+    out = {'equal': bool(torch.equal(hinted, plain)), 'rel': rel_err(hinted.float().cpu().permute(0, 3, 1, 2), ref)}
+    assert out['equal'] and out['rel'] < 1.5e-2, out
+    return out
+
+
+def staged_epilogue_bitwise_case(seed=9):
+    """The staged (shared memory + TMA store) epilogue against the per-lane stores, bit for bit, on the three kernel
+    variants that have it: resident 128-wide (+ residual, output in a wider-pitch buffer), streaming 256-wide with two n
+    blocks (+ residual), streaming with a split output."""
+    from deeplip_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+
+    def both(fn):
+        a = fn()
+        _lib.set_option('staged_epilogue', 0)
+        try:
+            b = fn()
+        finally:
+            _lib.set_option('staged_epilogue', 1)
+        torch.cuda.synchronize()
+        return a, b
+
+    def prm(c):
+        return (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.randn(c, generator=g) * 0.2).to(DEV), (torch.rand(c, generator=g) * 0.5).to(DEV)
+    # resident 128-wide tile writing channels [0,128) of a pitch-256 buffer, residual read from channels [128,256)
+    N = 310
+    x = torch.randn(N, 11, 11, 256, generator=g).to(DEV).to(torch.bfloat16)
+    w = packing.pack_conv_weight((torch.randn(128, 128, 3, 3, generator=g) / 34.0).to(DEV))
+    sc, sh, sl = prm(128)
+
+    def l2():
+        o = torch.zeros(N, 11, 11, 256, device=DEV, dtype=torch.bfloat16)
+        ops.conv_igemm(x, w, 128, 128, 3, 3, (1, 1), (1, 1), (1, 1), sc, sh, sl, residual=x, residual_channel_offset=128, out=o)
+        return o
+    a, b = both(l2)
+    out['resident_128_pitched'] = bool(torch.equal(a, b)) and float(a[..., 128:].abs().max()) == 0.0
+    # streaming 256-wide, two n blocks, residual, M not a multiple of 256
+    x2 = torch.randn(3701, 3, 3, 256, generator=g).to(DEV).to(torch.bfloat16)
+    w2 = packing.pack_conv_weight((torch.randn(512, 256, 3, 3, generator=g) / 48.0).to(DEV))
+    r2 = torch.randn(3701, 3, 3, 512, generator=g).to(DEV).to(torch.bfloat16)
+    sc2, sh2, sl2 = prm(512)
+    a, b = both(lambda: ops.conv_igemm(x2, w2, 256, 512, 3, 3, (1, 1), (1, 1), (1, 1), sc2, sh2, sl2, residual=r2)[0])
+    out['streaming_256_res'] = bool(torch.equal(a, b))
+    # split output (two dense tensors, second tensor map), centre-tap-only upper half
+    x3 = torch.randn(1200, 11, 11, 128, generator=g).to(DEV).to(torch.bfloat16)
+    w3 = torch.zeros((512, 9 * 128), device=DEV, dtype=torch.bfloat16)
+    w3[:256] = packing.pack_conv_weight((torch.randn(256, 128, 3, 3, generator=g) / 34.0).to(DEV))
+    w3[256:, 4 * 128:5 * 128] = packing.pack_conv_weight((torch.randn(256, 128, 1, 1, generator=g) / 11.0).to(DEV))
+    sc3, sh3, sl3 = prm(512)
+    a, b = both(lambda: ops.conv_igemm(x3, w3, 128, 512, 3, 3, (2, 2), (1, 1), (1, 1), sc3, sh3, sl3, split=(256, True))[0])
+    out['split_output'] = bool(torch.equal(a[0], b[0])) and bool(torch.equal(a[1], b[1]))
+    assert all(out.values()), out
+    return out
+
 
 
 def stem_case(B=2, T=6, H=88, W=88, u8=False, seed=0):

@@ -14,9 +14,18 @@ else:
 @pytest.mark.parametrize('name', ['l1_3x3_64', 'l2_3x3s2_64_128', 'l2_1x1s2_64_128', 'l2_3x3_128', 'l3_3x3s2_128_256',
                                   'l3_3x3_256', 'l4_3x3s2_256_512', 'l4_3x3_512', 'tdnn_k5_24_512', 'tdnn_k3d3_512',
                                   'tdnn_k1_512_1500', 'fc_3000_512', 'fc_3000_512_igemm', 'fc_3000_512_b64',
-                                  'fc_512_512_b100', 'fc_512_512_b300', 'fc_1024_512_b33_ld', 'conv1x1_small_map', 'many_tiles', 'pair_128', 'pair_256_s2', 'pair_512_odd'])
+                                  'fc_512_512_b100', 'fc_512_512_b300', 'fc_1024_512_b33_ld', 'conv1x1_small_map', 'many_tiles', 'pair_128', 'pair_256_s2', 'pair_512_odd',
+                                  'pair_tdnn_k1_1504', 'pair_tdnn_k3_res_odd_rows'])
 def test_conv_igemm(name):
     G.conv_case(**G.CONV_CASES[name])
+
+
+def test_conv_center_only_hint_is_bit_identical_on_the_pair_kernel():
+    G.conv_center_only_case()
+
+
+def test_staged_epilogue_equals_per_lane_stores_bit_for_bit():
+    G.staged_epilogue_bitwise_case()
 
 
 @pytest.mark.parametrize('kw', [dict(), dict(N=3, H=8, W=40, residual=False), dict(N=1, H=3, W=8), dict(N=300)])
