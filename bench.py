@@ -128,7 +128,18 @@ def synth_batch(B, seed):
     noise = rng.integers(-6, 7, raw.shape, dtype=np.int16)
     raw = np.clip(raw.astype(np.int16) + noise, 0, 255).astype(np.uint8)
     wav = synth.speech_like_audio(spk, nsamp=NSAMP, seed=seed)
-    return raw, wav
+    return raw, pcm16(wav)
+
+
+def pcm16(wav):
+    """float [-1, 1] -> int16 PCM, the sample format of the corpus' wav files and what crosses PCIe here (96 KB instead of
+    192 KB per utterance); `soundfile.read` hands the reference value / 32768 (datasets.py:70-76), which is what both the
+    front-end kernel and the CPU arm (`pcm_to_float`) compute -- exactly, so the two arms see identical samples."""
+    return np.clip(np.rint(wav * 32767.0), -32768, 32767).astype(np.int16)
+
+
+def pcm_to_float(wav):
+    return wav.astype(np.float64) / 32768.0 if wav.dtype == np.int16 else wav.astype(np.float64)
 
 
 # --------------------------------------------------------------------------------------------- reference arm
@@ -138,7 +149,7 @@ def oracle_av_extract(raw, wav, sda, sdv, aopts):
     outs = []
     with torch.no_grad():
         for i in range(raw.shape[0]):
-            feat = torch.from_numpy(frontend_np.extract_feature(wav[i].astype(np.float64)).T)[None]
+            feat = torch.from_numpy(frontend_np.extract_feature(pcm_to_float(wav[i])).T)[None]
             xv, _ = models_ref.speaker_extract_embedding(sda, feat, aopts)
             x = models_ref.video_preprocess(torch.from_numpy(raw[i]))[None, None]
             em = models_ref.lipreading_features(sdv, x).squeeze(0).mean(dim=0, keepdim=True)
@@ -151,7 +162,7 @@ def oracle_av_extract_batched(raw, wav, sda, sdv, aopts):
     batch, its extraction loop just never passes one."""
     from oracle import frontend_np, models_ref
     with torch.no_grad():
-        feat = torch.from_numpy(np.stack([frontend_np.extract_feature(w.astype(np.float64)).T for w in wav]))
+        feat = torch.from_numpy(np.stack([frontend_np.extract_feature(pcm_to_float(w)).T for w in wav]))
         xv, _ = models_ref.speaker_extract_embedding(sda, feat, aopts)
         x = torch.stack([models_ref.video_preprocess(torch.from_numpy(r)) for r in raw])[:, None]
         em = models_ref.lipreading_features(sdv, x).mean(dim=1)
@@ -229,9 +240,11 @@ def workload_config(args, per_gpu_batch):
                         'concat fusion, GRID utterances (75x96x96 u8 crops -> 88x88, 3 s 16 kHz audio); '
                         'video-only configs[1] is its dominant part',
             'per_gpu_batch': per_gpu_batch, 'global_batch': per_gpu_batch * args.gpus,
-            'frames': T_FRAMES, 'crop': CROP_HW, 'audio_samples': NSAMP, 'parallelism': 'dp%d' % args.gpus,
+            'frames': T_FRAMES, 'crop': CROP_HW, 'audio_samples': NSAMP, 'audio_format': 'int16 PCM (value / 32768 in the '
+            'front-end load, as soundfile.read decodes the corpus files; the CPU arm gets the same samples as floats)',
+            'parallelism': 'dp%d' % args.gpus,
             'l2': '160 MiB memset (1.33x the 126 MB L2) between steps, inside the timed region, + 4 rotating input '
-                  'batches (226 MB)'}
+                  'batches (201 MB)'}
 
 
 # --------------------------------------------------------------------------------------------- whole-list jobs
@@ -253,7 +266,7 @@ def job_pool(tl, seed):
     raw = np.tile(raw, (1, (T_FRAMES + 3) // 4, 1, 1))[:, :T_FRAMES]
     rng = np.random.default_rng(seed + 5)
     raw = np.clip(raw.astype(np.int16) + rng.integers(-6, 7, raw.shape, dtype=np.int16), 0, 255).astype(np.uint8)
-    wav = synth.speech_like_audio(pool_spk, nsamp=NSAMP, seed=seed, noise=0.25)
+    wav = pcm16(synth.speech_like_audio(pool_spk, nsamp=NSAMP, seed=seed, noise=0.25))
     umap = np.array([pos[s] * POOL_VARIANTS + zlib.crc32(u.encode()) % POOL_VARIANTS for s, u in zip(spk_of, tl.utts)],
                     dtype=np.int64)
     return raw, wav, umap, len(spks)
@@ -488,7 +501,7 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     e2e = args.steps * n_total / (ms_e2e / 1e3)
-    h2d = B * (T_FRAMES * RAW_HW * RAW_HW + NSAMP * 4)
+    h2d = B * (T_FRAMES * RAW_HW * RAW_HW + NSAMP * 2)          # u8 crops + int16 PCM
     d2h = n_total * 1024 * 4
 
     # ---- roofline of the dominant kernels: the trunk's conv launches of one step (16 with the fused entry blocks)
@@ -583,8 +596,8 @@ def run_ours(args, rank, world, local):
 
     hbm_kernels = {}
     try:
-        FE_BYTES = NSAMP * 4 + 299 * 24 * 4                      # 220 704 B / utterance (mfcc-24)
-        wav64 = devb[0][1]
+        FE_BYTES = NSAMP * 4 + 299 * 24 * 4                      # 220 704 B / utterance (mfcc-24), SURVEY 8(d): f32 samples
+        wav64 = devb[0][1].float() / 32768.0                      # the survey's input format for this figure
         wav_big = wav64.repeat(16, 1)                            # 1024 utterances, 197 MB
         for name, w in (('frontend_B%d' % B, wav64), ('frontend_B%d' % wav_big.shape[0], wav_big)):
             ops.frontend_features(w, 'mfcc', 24, True)

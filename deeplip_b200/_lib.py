@@ -26,6 +26,7 @@ _p, _i, _f = C.c_void_p, C.c_int, C.c_float
 # name -> argtypes ; every compute entry point returns int
 SIGNATURES = {
     'dl_frontend_features': [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p],
+    'dl_frontend_features_pcm16': [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p],
     'dl_nct_to_ntc_bf16': [_p, _i, _i, _i, _p, _i, _p],
     'dl_stem_conv3d_bn_prelu_pool': [_p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _i, _p, _p, _p],
     'dl_conv3x3_c64_halo_bf16': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],

@@ -237,9 +237,26 @@ static int upload_tables() {
 
 }  // namespace dl
 
+static int frontend_features_impl(const float* wav, int pcm16, const int32_t* lengths, int B, int nsamp, int kind, int F,
+                                  int cmvn, int delta, void* feat_bf16, int ld_bf16, float* feat_f32, int T,
+                                  void* stream);
+
 extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
                                     int cmvn, int delta, void* feat_bf16, int ld_bf16, float* feat_f32, int T,
                                     void* stream) {
+  return frontend_features_impl(wav, 0, lengths, B, nsamp, kind, F, cmvn, delta, feat_bf16, ld_bf16, feat_f32, T, stream);
+}
+
+extern "C" int dl_frontend_features_pcm16(const int16_t* wav, const int32_t* lengths, int B, int nsamp, int kind, int F,
+                                          int cmvn, int delta, void* feat_bf16, int ld_bf16, float* feat_f32, int T,
+                                          void* stream) {
+  return frontend_features_impl(reinterpret_cast<const float*>(wav), 1, lengths, B, nsamp, kind, F, cmvn, delta, feat_bf16,
+                                ld_bf16, feat_f32, T, stream);
+}
+
+static int frontend_features_impl(const float* wav, int pcm16, const int32_t* lengths, int B, int nsamp, int kind, int F,
+                                  int cmvn, int delta, void* feat_bf16, int ld_bf16, float* feat_f32, int T,
+                                  void* stream) {
   using namespace dl;
   DL_CHECK_ARG(wav && feat_f32, "frontend: wav and feat_f32 are required");
   DL_CHECK_ARG(B > 0 && nsamp > 0, "frontend: empty batch");
@@ -260,9 +277,11 @@ extern "C" int dl_frontend_features(const float* wav, const int32_t* lengths, in
   const int gen = opt_frontend();
   DL_CHECK_ARG(delta == 0 || gen >= 2, "frontend: delta features need the generation-2 kernels");
   DL_CHECK_ARG(!stft || gen >= 2, "frontend: stft needs the generation-2 kernels (dl_set_option(\"frontend\", 2))");
+  DL_CHECK_ARG(!pcm16 || gen >= 2, "frontend: int16 PCM input needs the generation-2 kernels");
 
   FrontendTables tb;
   fill_frontend_tables(&tb, kind, F, opt_stft_pad());
+  tb.pcm16 = pcm16;
   cudaStream_t s = (cudaStream_t)stream;
   int st;
   if (gen >= 2) {

@@ -20,6 +20,7 @@ struct FrontendTables {
   int ncep;                  // number of coefficients written (F)
   int kind;                  // 0 mfcc, 1 fbank, 2 logfbank, 3 stft
   int pad_mode;              // stft: 0 reflect (librosa < 0.10 default), 1 zeros (librosa >= 0.10 default)
+  int pcm16;                 // 1: wav is int16 PCM, sample = value / 32768 (what soundfile.read returns for a 16-bit file)
   int bins[kMaxFilt + 2];    // FFT-bin edges of the triangular filters
   float inv_width[kMaxFilt + 1];   // 1 / (bins[j+1] - bins[j])
 };
@@ -99,7 +100,11 @@ __global__ void __launch_bounds__(256, 2) frontend_frames2_kernel(const float* _
         if (s < 0) s = -s;
         if (s >= len) s = 2 * (len - 1) - s;
       }
-      v[j] = (i <= kChunk && s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+      // int16 PCM: value / 32768 is exact in f32, so the two input formats give the same bits
+      v[j] = (i <= kChunk && s >= 0 && s < len)
+                 ? (tb.pcm16 ? (float)__ldg(reinterpret_cast<const int16_t*>(wav) + (size_t)b * nsamp + s) * (1.0f / 32768.0f)
+                             : __ldg(x + s))
+                 : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < kPer; ++j) {
@@ -348,7 +353,7 @@ inline double mel2hz(double mel) { return 700.0 * (pow(10.0, mel / 2595.0) - 1.0
 inline void fill_frontend_tables(FrontendTables* tb, int kind, int F, int pad_mode) {
   const int nfilt = kind == 3 ? 0 : (kind == 0 ? 26 : F);
   *tb = FrontendTables{};
-  tb->nfilt = nfilt; tb->ncep = F; tb->kind = kind; tb->pad_mode = pad_mode;
+  tb->nfilt = nfilt; tb->ncep = F; tb->kind = kind; tb->pad_mode = pad_mode; tb->pcm16 = 0;
   if (nfilt == 0) return;
   const double lo = hz2mel(0.0), hi = hz2mel(8000.0);
   for (int i = 0; i < nfilt + 2; ++i) {

@@ -98,13 +98,15 @@ FEAT_KINDS = {'mfcc': 0, 'fbank': 1, 'logfbank': 2, 'stft': 3}
 
 
 def frontend_features(wav, feat_type='mfcc', n_feat=24, cmvn=True, lengths=None, ld=None, delta=False):
-    """wav (B, nsamp) f32 -> (feat_f32 (B,F,T), feat_bf16 (B,T,ld)).  feat_type 'stft' (n_fft 512, hop 160,
+    """wav (B, nsamp) f32, or int16 PCM (sample = value / 32768, as soundfile.read decodes a 16-bit file; same bits
+    out) -> (feat_f32 (B,F,T), feat_bf16 (B,T,ld)).  feat_type 'stft' (n_fft 512, hop 160,
     Hann 400; models/fusion_models/datasets.py:237-241) has n_feat = 257.  delta (True = the reference's order 2, or
     0 / 1 / 2): `_delta` (:217-225) appends delta(feat, 1) and delta(feat, 2): F becomes n_feat * (1 + order)."""
     _need_cuda(wav, lengths)
     if feat_type not in FEAT_KINDS:
         raise NotImplementedError('Other features are not implemented!')      # datasets.py:243
-    wav = wav.contiguous().float()
+    pcm16 = wav.dtype == torch.int16
+    wav = wav.contiguous() if pcm16 else wav.contiguous().float()
     B, nsamp = wav.shape
     if feat_type == 'stft':
         n_feat = 257
@@ -114,8 +116,9 @@ def frontend_features(wav, feat_type='mfcc', n_feat=24, cmvn=True, lengths=None,
     ld = ld or ceil_to(n_out, 64)
     f32 = torch.empty((B, n_out, T), device=wav.device, dtype=torch.float32)
     b16 = torch.empty((B, T, ld), device=wav.device, dtype=torch.bfloat16)
-    st = _lib.lib().dl_frontend_features(_ptr(wav), _ptr(lengths), B, nsamp, FEAT_KINDS[feat_type], n_feat,
-                                         int(bool(cmvn)), order, _ptr(b16), ld, _ptr(f32), T, _stream())
+    fn = _lib.lib().dl_frontend_features_pcm16 if pcm16 else _lib.lib().dl_frontend_features
+    st = fn(_ptr(wav), _ptr(lengths), B, nsamp, FEAT_KINDS[feat_type], n_feat,
+            int(bool(cmvn)), order, _ptr(b16), ld, _ptr(f32), T, _stream())
     _lib.check(st, 'dl_frontend_features')
     return f32, b16
 

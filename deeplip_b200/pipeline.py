@@ -26,7 +26,8 @@ class AVExtractor:
         self.feat_type, self.n_feat, self.cmvn, self.l2norm, self.delta = feat_type, n_feat, cmvn, l2norm, delta
 
     def audio_embedding(self, wav, wav_lengths=None):
-        """wav (B,nsamp) f32 CUDA -> xv (B,E) f32 (LMCL convention: 2nd fc output, train_fusion.py:390)."""
+        """wav (B,nsamp) f32 -- or int16 PCM, value / 32768 -- CUDA -> xv (B,E) f32 (LMCL convention: 2nd fc output,
+        train_fusion.py:390)."""
         _, feat = ops.frontend_features(wav, self.feat_type, self.n_feat, self.cmvn, lengths=wav_lengths, delta=self.delta)
         frames = None
         if wav_lengths is not None:
@@ -150,7 +151,8 @@ class HostPipeline:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._free[slot])          # kernels that read this slot are done
             st = self._stage[slot]
-            if st is None or st[0].shape != wav_h.shape or st[1].shape != vid_h.shape or st[1].dtype != vid_h.dtype:
+            if st is None or st[0].shape != wav_h.shape or st[0].dtype != wav_h.dtype or st[1].shape != vid_h.shape or \
+                    st[1].dtype != vid_h.dtype:
                 st = [torch.empty(wav_h.shape, dtype=wav_h.dtype, device=self.device),
                       torch.empty(vid_h.shape, dtype=vid_h.dtype, device=self.device),
                       torch.empty((wav_h.shape[0],), dtype=torch.int32, device=self.device),

@@ -964,3 +964,21 @@ def trial_list_job_case(tmpdir, B=5, T=6, nsamp=16000, seed=3):
     assert abs(res['eer'] - ref_eer) < 5e-4
     assert job.verify_gather() and set(res['ms']) == {'extract', 'checksum', 'rank_skew', 'all_gather', 'score', 'gather_scores'}
     return {'n_utts': n, 'score_abs': err, 'eer': float(res['eer'])}
+
+
+def frontend_pcm16_case(B=3, nsamp=24000, seed=4):
+    """int16 PCM input (dl_frontend_features_pcm16) == the f32 entry point fed value / 32768, bit for bit, for every
+    feature kind; and AVExtractor takes either."""
+    rng = np.random.default_rng(seed)
+    pcm = torch.from_numpy(np.clip(np.rint(synth.speech_like_audio(list(range(B)), nsamp=nsamp, seed=seed) * 32767), -32768,
+                                   32767).astype(np.int16)).to(DEV)
+    lengths = torch.tensor([nsamp, nsamp - 3001, nsamp - 77][:B], dtype=torch.int32, device=DEV)
+    out = {}
+    for kind, nf in (('mfcc', 24), ('fbank', 24), ('logfbank', 60), ('stft', 257)):
+        for ln in (None, lengths):
+            a32, ab = ops.frontend_features(pcm, kind, nf, True, lengths=ln)
+            b32, bb = ops.frontend_features(pcm.float() / 32768.0, kind, nf, True, lengths=ln)
+            torch.cuda.synchronize()
+            out['%s%s' % (kind, '' if ln is None else '_ragged')] = bool(torch.equal(a32, b32) and torch.equal(ab, bb))
+    assert all(out.values()), out
+    return out

@@ -24,6 +24,10 @@ def test_conv_center_only_hint_is_bit_identical_on_the_pair_kernel():
     G.conv_center_only_case()
 
 
+def test_frontend_int16_pcm_input_equals_float_input_bit_for_bit():
+    G.frontend_pcm16_case()
+
+
 def test_staged_epilogue_equals_per_lane_stores_bit_for_bit():
     G.staged_epilogue_bitwise_case()
 
