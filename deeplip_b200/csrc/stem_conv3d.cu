@@ -202,8 +202,12 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
       for (; cur.unit < p.units; cur.advance()) {
         if (cur.unit != last_unit) { last_unit = cur.unit; fb = cur.unit / p.pairs_per_clip; t0 = 2 * (cur.unit - fb * p.pairs_per_clip); }
         mbar_wait(&sempty[slot], ph ^ 1);
-        mbar_expect_tx(&sfull[slot], strip_bytes);
-        tma_load_4d(strip + slot * strip_buf, &mapX, &sfull[slot], 0, tile_iy0[cur.tile] + 3, t0 + stem_stage_dt(cur.st), fb);
+        if (p.dbg & 16384) {             // timing emulation: no strip load at all (is the TMA unit's row rate the pace?)
+          mbar_arrive(&sfull[slot]);
+        } else {
+          mbar_expect_tx(&sfull[slot], strip_bytes);
+          tma_load_4d(strip + slot * strip_buf, &mapX, &sfull[slot], 0, tile_iy0[cur.tile] + 3, t0 + stem_stage_dt(cur.st), fb);
+        }
         if (++slot == (uint32_t)p.strip_slots) { slot = 0; ph ^= 1; }
       }
     }
@@ -237,7 +241,9 @@ stem_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
             const uint32_t dd = st == 1 ? d + 64 : d;
             const uint32_t wblk = st == 0 ? 4u : (st == 1 ? 0u : (uint32_t)(5 - st));
             const uint64_t bdesc = bd0 + (uint64_t)(wblk * 8192u >> 4);
-            const uint32_t idesc = st < 2 ? idesc64 : idesc128;
+            // dbg 4096 / 8192 (timing emulation only, results are garbage): issue the shared stages at N = 192 / 256 to
+            // measure what an MMA with A in tensor memory costs as N grows
+            const uint32_t idesc = st < 2 ? idesc64 : ((p.dbg & 4096) ? umma_idesc_bf16(128, 192) : ((p.dbg & 8192) ? umma_idesc_bf16(128, 256) : idesc128));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if ((p.dbg & 8) && k) break;
@@ -458,6 +464,10 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   p.out_img_rows = out_img_rows > 0 ? out_img_rows : p.Hp;
   p.dbg = opt_dbg();
   p.strip_slots = 6;
+  {   // measurement aid: dbg bits 16..19 = strip ring slots / 2 (even counts 2..16)
+    const int s2 = (p.dbg >> 16) & 15;
+    if (s2 >= 1 && 2 * s2 <= kStripSlotsMax) p.strip_slots = 2 * s2;
+  }
   DL_CHECK_ARG(p.out_img_rows >= p.Hp, "stem: out_img_rows < H/4");
   DL_CHECK_ARG(p.tiles_per_frame <= 64, "stem: frame too large (more than 64 tiles)");
 

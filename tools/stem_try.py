@@ -8,9 +8,8 @@ _, video = build_models()
 pk = video._packed()
 B, T = 64, 75
 x = torch.from_numpy(synth.lip_crops_u8([1] * B, T=T, H=96, W=96, seed=3)).cuda()
-cases = []
-for slots in (6,):
-    cases += [(1024, 'no pooling (BN+ring only)'), (2048, 'no BN/ring (pooling only)'), (0 | 48 | 8, 'MMA only 1/4'), (slots << 8, '%d slots full' % slots), (0 | 48, '%d slots, MMA only' % slots), (0 | 32, '%d slots, epilogue idle' % slots), (0 | 16, '%d slots, builders idle' % slots)]
+cases = [(0, 'full'), (48, 'MMA only'), (48 | 8, 'MMA only 1/4'), (48 | 16384, 'MMA only, no strip loads'), (48 | 8 | 16384, 'MMA 1/4, no strip loads'),
+         (32 | 16384, 'epilogue idle, no strip loads'), (16384, 'full, no strip loads (garbage)')]
 for dbg, what in cases:
     _lib.set_option('dbg', dbg)
     t = timeit(lambda: ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a']), n=(1 if dbg & 512 else 10)); torch.cuda.synchronize()
