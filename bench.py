@@ -570,6 +570,60 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     audio_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
 
+    # ---- every conv launch of the video branch on its own pair of CUDA events (one instrumented step per repetition,
+    # L2 flushed in between): GFLOP of the layer (the 1x1 skip counted with the entry conv it rides
+    # in) / time, against the sustained tensor peak.  The trunk runs back to back, so an event pair costs the launch a
+    # few microseconds it does not pay in the step: read these as upper bounds of the per-kernel times.
+    per_launch = None
+    try:
+        V3 = {(64, 64, 1): 2.6763, (64, 256, 2): 1.3382 + 0.1487, (128, 128, 1): 2.6763, (128, 512, 2): 1.5925 + 0.1769,
+              (256, 256, 1): 3.1850, (256, 1024, 2): 1.5925 + 0.1769, (512, 512, 1): 3.1850}
+        log = []
+        orig = {n: getattr(ops, n) for n in ('stem_conv3d', 'conv_igemm', 'conv3x3_halo')}
+
+        def wrap(name):
+            fn = orig[name]
+
+            def w(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*a, **k)
+                e1.record()
+                if name == 'stem_conv3d':
+                    key, gf = 'stem Conv3d 1->64 k(5,7,7) + BN + PReLU + maxpool', GFLOP_STEM_PER_UTT
+                elif name == 'conv3x3_halo':
+                    key, gf = 'layer1 3x3 64->64' + (' +res' if k.get('residual') is not None else ''), V3[(64, 64, 1)]
+                else:
+                    cin, cout, st = a[2], a[3], (a[6] if len(a) > 6 else k.get('stride', (1, 1)))[0]
+                    key = '%s 3x3 s%d %d->%d%s' % ('entry conv + skip' if st == 2 else 'conv', st, cin, cout,
+                                                   ' +res' if k.get('residual') is not None else '')
+                    gf = V3.get((cin, cout, st))
+                log.append((key, gf, e0, e1))
+                return out
+            return w
+        runs = []
+        try:
+            for n in orig:
+                setattr(ops, n, wrap(n))
+            for i in range(5):
+                flush.zero_()
+                log.clear()
+                video.utterance_embedding(devb[i % nrot][0])
+                torch.cuda.synchronize()
+                runs.append([(k, gf, a.elapsed_time(b)) for k, gf, a, b in log])
+        finally:
+            for n, fn in orig.items():
+                setattr(ops, n, fn)
+        per_launch = []
+        for j, (k, gf, _) in enumerate(runs[0]):
+            ms_j = statistics.median(r[j][2] for r in runs)
+            row = {'launch': k, 'us': round(ms_j * 1e3, 1)}
+            if gf:
+                row.update(gflop=round(gf * B, 1), tflops=round(gf * B / ms_j, 1), frac_of_sustained=round(gf * B / ms_j / peaks['bf16_tflops_sustained'], 3))
+            per_launch.append(row)
+    except Exception as e:      # reported next to the headline, must not sink it
+        per_launch = {'error': repr(e)[:200]}
+
     # ---- HBM-bound kernels timed alone (CUDA events, L2 flushed): front end K1 at the step's batch and at a batch
     # large enough to leave the launch-latency regime; algorithmic bytes per utterance from SURVEY 8(d)
     flush_rd = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
@@ -715,7 +769,7 @@ def run_ours(args, rank, world, local):
             'step_tflops': total_gflop / (ms / args.steps),
             'breakdown_ms': {'stem': stem_ms, 'trunk': trunk_ms, 'audio_frontend_tdnn': audio_ms},
             'hbm_kernels': hbm_kernels,
-            'stem_tflops': GFLOP_STEM_PER_UTT * B / stem_ms, 'jobs': jobs}
+            'stem_tflops': GFLOP_STEM_PER_UTT * B / stem_ms, 'video_launches': per_launch, 'jobs': jobs}
     emit(line)
 
 
