@@ -35,11 +35,13 @@ const char* dl_last_error(void);
  * (smem-resident weight half in the pair kernel, default 1), "tap_share" (one operand-A box per filter row in
  * the guarded-linear pair kernel, default 1), "frontend" (2 = register-resident FFT front end, 1 = first generation),
  * "prepass" (2 | 1, stem pre-pass generation), "small_linear" (1 = fc layers on linear_small_kernel, 0 = igemm),
- * "statpool_mlp" (4 | 8 loads in flight), "stft_pad" (0 reflect | 1 zeros: a convention, not a tuning switch).
- * Results agree to fp32 summation order either way.
+ * "statpool_mlp" (4 | 8 loads in flight), "staged_epilogue" (1 = the CTA-pair kernels send their output tiles through
+ * shared-memory slabs and TMA stores, 0 = per-lane 16-byte stores; bit-identical), "stft_pad" (0 reflect | 1 zeros: a
+ * convention, not a tuning switch).  Results agree to fp32 summation order either way.
  * "dbg" (default 0) is a measurement aid only: bits 1/2/4 drop the residual / stores / whole epilogue of the
- * pair kernel, 8 issues one MMA in four, 16/32 idle the stem's builders / epilogue (tools/epi_try.py,
- * tools/stem_try.py) -- any non-zero value produces WRONG results by design. */
+ * pair kernel, 8 issues one MMA in four, 16/32 idle the stem's builders / epilogue, 4096/8192 widen the stem's MMAs,
+ * 16384 drops its strip loads, bits 16..19 set its strip ring depth (tools/entry_ablate.py, tools/stem_try.py) -- any
+ * non-zero value produces WRONG results by design. */
 int dl_set_option(const char* name, int value);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long dl_launch_count(void);
