@@ -863,6 +863,31 @@ def plda_case(dim=512, n_spk=40, per=25, n_trials=20000, seed=0):
     return out
 
 
+def determinism_pair_size_case(B=26, T=72, reps=30, seed=2):
+    """The same at a size where every wide layer runs on the CTA-pair kernels with the staged (shared memory + TMA
+    store) epilogue (1 872 frames): back-to-back launches, bitwise equal, and equal to the per-lane-store epilogue."""
+    from deeplip_b200 import _lib
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    audio, video = build_models(DEV, seed=seed)
+    ex = AVExtractor(audio, video)
+    spk = [1 + i % 7 for i in range(B)]
+    raw = torch.from_numpy(synth.lip_crops_u8(spk, T=T, seed=seed)).to(DEV)
+    wav = torch.from_numpy(synth.speech_like_audio(spk, nsamp=48000, seed=seed)).to(DEV)
+    embs = [ex.extract(wav, raw).clone() for _ in range(reps)]
+    maps = [video.trunk_maps(raw).clone() for _ in range(4)]
+    _lib.set_option('staged_epilogue', 0)
+    try:
+        plain = ex.extract(wav, raw).clone()
+    finally:
+        _lib.set_option('staged_epilogue', 1)
+    torch.cuda.synchronize()
+    out = {'emb_mismatch': sum(int(not torch.equal(embs[0], e)) for e in embs[1:]),
+           'maps_mismatch': sum(int(not torch.equal(maps[0], m)) for m in maps[1:]),
+           'staged_equals_plain': bool(torch.equal(plain, embs[0]))}
+    assert out['emb_mismatch'] == 0 and out['maps_mismatch'] == 0 and out['staged_equals_plain'], out
+    return out
+
+
 def determinism_case(B=8, T=10, reps=25, seed=1):
     """Bitwise run-to-run determinism of the video path under back-to-back launches (no host sync in
     between).  Guards the smem hand-offs between generic-proxy readers and TMA refills: a missing proxy

@@ -86,6 +86,10 @@ def test_bitwise_determinism_back_to_back():
     G.determinism_case()
 
 
+def test_bitwise_determinism_at_pair_kernel_size():
+    G.determinism_pair_size_case()
+
+
 def test_modules_are_inference_only_and_fail_loudly_on_cpu():
     from deeplip_b200 import ops
     with pytest.raises(RuntimeError, match='no CPU fallback'):
