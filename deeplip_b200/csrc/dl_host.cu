@@ -120,12 +120,12 @@ int make_tiled_3d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64
 }
 
 int make_tiled_4d_bf16_noswizzle(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t d2,
-                                 uint64_t d3, uint32_t box_cols, uint32_t box_rows) {
+                                 uint64_t d3, uint32_t box_cols, uint32_t box_rows, uint32_t box_d2) {
   int st = load_driver();
   if (st != DL_OK) return st;
   cuuint64_t dims[4] = {cols, rows, d2, d3};
   cuuint64_t strides[3] = {cols * 2, rows * cols * 2, d2 * rows * cols * 2};
-  cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
+  cuuint32_t box[4] = {box_cols, box_rows, box_d2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -170,7 +170,7 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 
 namespace dl {
 static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1}, g_opt_dbg{0}, g_opt_tap_share{1}, g_opt_frontend{2},
-    g_opt_stft_pad{0}, g_opt_staged{1}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{256};
+    g_opt_stft_pad{0}, g_opt_staged{1}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{256}, g_opt_stem{2};
 int opt_pair() { return g_opt_pair.load(std::memory_order_relaxed); }
 int opt_pair_resident() { return g_opt_pair_resident.load(std::memory_order_relaxed); }
 int opt_staged_epilogue() { return g_opt_staged.load(std::memory_order_relaxed); }
@@ -182,6 +182,7 @@ int opt_small_linear() { return g_opt_small_linear.load(std::memory_order_relaxe
 int opt_statpool_mlp() { return g_opt_statpool_mlp.load(std::memory_order_relaxed); }
 int opt_statpool_slab() { return g_opt_statpool_slab.load(std::memory_order_relaxed); }
 int opt_stft_pad() { return g_opt_stft_pad.load(std::memory_order_relaxed); }
+int opt_stem() { return g_opt_stem.load(std::memory_order_relaxed); }
 }  // namespace dl
 
 extern "C" {
@@ -195,6 +196,7 @@ int dl_set_option(const char* name, int value) {
   if (!strcmp(name, "small_linear")) { dl::g_opt_small_linear.store(value); return DL_OK; }
   if (!strcmp(name, "statpool_mlp")) { dl::g_opt_statpool_mlp.store(value); return DL_OK; }
   if (!strcmp(name, "statpool_slab")) { dl::g_opt_statpool_slab.store(value); return DL_OK; }
+  if (!strcmp(name, "stem")) { dl::g_opt_stem.store(value); return DL_OK; }
   if (!strcmp(name, "stft_pad")) { dl::g_opt_stft_pad.store(value); return DL_OK; }
   if (!strcmp(name, "pair_resident")) { dl::g_opt_pair_resident.store(value); return DL_OK; }
   if (!strcmp(name, "staged_epilogue")) { dl::g_opt_staged.store(value); return DL_OK; }

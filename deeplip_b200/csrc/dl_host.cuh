@@ -30,6 +30,7 @@ int opt_prepass();         // 2 = one block per frame, aligned word loads (defau
 int opt_small_linear();    // 1 = fc layers (P Q == 1, <= 4096 rows) run on linear_small_kernel (default), 0 = igemm
 int opt_statpool_mlp();    // stat pool: 16-byte loads in flight per lane, 4 (default; measured faster) or 8
 int opt_statpool_slab();   // stat pool: channels per block, 256 (default) or 128 (half a warp per time step; measured slower)
+int opt_stem();            // 2 = channels-on-lanes stem kernel for W = 88 (default), 1 = first-generation kernel for every shape
 int opt_stft_pad();        // stft centre padding: 0 reflect (librosa < 0.10), 1 zeros (librosa >= 0.10)
 int opt_tap_share();     // pair kernel shares one operand-A box across horizontal taps (guarded-linear mode)
 int opt_staged_epilogue();   // 1 = resident pair kernels store their tiles through shared memory + TMA (default), 0 = per-lane stores
@@ -44,9 +45,9 @@ int make_tiled_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64
 int make_tiled_3d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t C,
                        uint32_t box_rows, uint32_t box_cols, uint32_t box_c);
 
-// 4-D tiled map, no swizzle, over a dense (d3, d2, rows, cols) 16-bit tensor; box = (box_cols, box_rows, 1, 1).
+// 4-D tiled map, no swizzle, over a dense (d3, d2, rows, cols) 16-bit tensor; box = (box_cols, box_rows, box_d2, 1).
 int make_tiled_4d_bf16_noswizzle(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t d2,
-                                 uint64_t d3, uint32_t box_cols, uint32_t box_rows);
+                                 uint64_t d3, uint32_t box_cols, uint32_t box_rows, uint32_t box_d2 = 1);
 
 // im2col map over an NHWC 16-bit activation tensor (pitch ldx elements per pixel): loads
 // `pixels` output positions x `channels` channels per request, 128-byte swizzle, zero OOB fill.

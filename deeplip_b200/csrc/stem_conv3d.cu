@@ -18,6 +18,7 @@
 #include "dl_host.cuh"
 #include "dl_ptx.cuh"
 #include "stem_prepass.cuh"
+#include "stem2_conv3d.cuh"
 
 namespace dl {
 
@@ -490,6 +491,39 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
         rows, pitch, static_cast<uint16_t*>(workspace));
     st = check_launch("stem_prepass_kernel");
     if (st != DL_OK) return st;
+  }
+
+  if (opt_stem() >= 2 && W == 2 * kS2Wo && H % 8 == 0) {
+    // ---- second generation (stem2_conv3d.cuh): channels on lanes, four conv rows per tile
+    Stem2Params q;
+    q.B = B; q.T = T;
+    q.tiles = H / 8;
+    q.pairs_per_clip = (T + 1) / 2;
+    q.units = B * q.pairs_per_clip;
+    q.out_img_rows = p.out_img_rows;
+    q.scale = scale; q.shift = shift; q.slope = slope;
+    q.y = static_cast<uint16_t*>(y);
+    q.w = static_cast<const uint16_t*>(w_packed);
+    q.dbg = p.dbg;
+    CUtensorMap mapW2, mapX2;
+    st = make_tiled_2d_bf16(&mapW2, w_packed, 64, 320, 320, 64, 64);
+    if (st != DL_OK) return st;
+    st = make_tiled_4d_bf16_noswizzle(&mapX2, workspace, (uint64_t)pitch, (uint64_t)rows, (uint64_t)T, (uint64_t)B,
+                                      (uint32_t)pitch, (uint32_t)kS2StripRows, 6);
+    if (st != DL_OK) return st;
+    int grid2 = device_sm_count();
+    if (grid2 <= 0) grid2 = 148;
+    if (q.units < grid2) grid2 = q.units;
+    static PerDevice<int> configured2_dev;
+    int* configured2 = configured2_dev.slot();
+    if (!configured2) return fail(DL_ERR_CUDA, "stem: no current device");
+    if (!*configured2) {
+      cudaError_t e = cudaFuncSetAttribute(stem2_conv3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2Smem);
+      if (e != cudaSuccess) return fail(DL_ERR_CUDA, "stem2 smem attribute: %s", cudaGetErrorString(e));
+      *configured2 = 1;
+    }
+    stem2_conv3d_kernel<<<grid2, kS2Threads, kS2Smem, cs>>>(mapW2, mapX2, q);
+    return check_launch("stem2_conv3d_kernel");
   }
 
   const int strip_elems = p.strip_rows * p.strip_pitch;
