@@ -34,14 +34,18 @@ const char* dl_last_error(void);
 /* Tuning switches for A/B measurements: "pair" (CTA-pair igemm kernels, default 1), "pair_resident"
  * (smem-resident weight half in the pair kernel, default 1), "tap_share" (one operand-A box per filter row in
  * the guarded-linear pair kernel, default 1), "frontend" (2 = register-resident FFT front end, 1 = first generation),
- * "prepass" (2 | 1, stem pre-pass generation), "small_linear" (1 = fc layers on linear_small_kernel, 0 = igemm),
+ * "prepass" (2 | 1, stem pre-pass generation), "stem" (2 = channels-on-lanes stem kernel where the shape allows it:
+ * W = 88 and H % 8 == 0, 1 = first-generation kernel for every shape; the two agree to fp32 summation order),
+ * "small_linear" (1 = fc layers on linear_small_kernel, 0 = igemm),
  * "statpool_mlp" (4 | 8 loads in flight), "staged_epilogue" (1 = the CTA-pair kernels send their output tiles through
  * shared-memory slabs and TMA stores, 0 = per-lane 16-byte stores; bit-identical), "stft_pad" (0 reflect | 1 zeros: a
  * convention, not a tuning switch).  Results agree to fp32 summation order either way.
  * "dbg" (default 0) is a measurement aid only: bits 1/2/4 drop the residual / stores / whole epilogue of the
  * pair kernel, 8 issues one MMA in four, 16/32 idle the stem's builders / epilogue, 4096/8192 widen the stem's MMAs,
- * 16384 drops its strip loads, bits 16..19 set its strip ring depth (tools/entry_ablate.py, tools/stem_try.py) -- any
- * non-zero value produces WRONG results by design. */
+ * 16384 drops its strip loads, bits 16..19 set its strip ring depth (tools/entry_ablate.py, tools/stem_try.py); in the
+ * second-generation stem 2/32 drop the bulk stores / staging writes, 8 issues one MMA per stage, 16 skips the builders'
+ * strip reads, 64 the epilogue arithmetic, 128 the strip loads, 256/512 substitute the operand data, 1024 multiplies
+ * the padded 8th window row too (tools/stem2_abl.py) -- any non-zero value produces WRONG results by design. */
 int dl_set_option(const char* name, int value);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long dl_launch_count(void);
@@ -97,6 +101,9 @@ int dl_nct_to_ntc_bf16(const float* x, int B, int C, int T, void* y, int ldc, vo
  *     workspace: caller-owned scratch of dl_stem_workspace_bytes(B, T, H, W) bytes (the normalised,
  *     zero-bordered bf16 frames the TMA unit streams from; this library never allocates).
  *     dl_set_option("prepass", 1) selects the first-generation pre-pass kernel (A/B measurements; no lengths).
+ *     Two kernels: W == 88 (the corpus crop) with H % 8 == 0 runs on stem2_conv3d_kernel (channels on the
+ *     accumulator lanes), every other shape -- and every shape after dl_set_option("stem", 1) --
+ *     on stem_conv3d_kernel.  Same contract, results equal to fp32 summation order.
  */
 long long dl_stem_workspace_bytes(int B, int T, int H, int W);
 int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,

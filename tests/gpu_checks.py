@@ -322,6 +322,61 @@ def stem_case(B=2, T=6, H=88, W=88, u8=False, seed=0):
     d = (y.float().cpu() - ref).abs()
     out['worst'] = [int(v) for v in np.unravel_index(int(d.argmax()), d.shape)]
     assert out['rel'] < 1.5e-2, out
+    # Both kernel generations (dl_set_option("stem"): 2 = channels-on-lanes kernel where the shape allows it (W = 88,
+    # H % 8 == 0), 1 = first generation for every shape) against the oracle, and against each other: they sum the same
+    # products in a different order, so they agree to fp32 accumulation error, i.e. a bf16 ulp on a few values.
+    _lib.set_option('stem', 1)
+    try:
+        yg1 = ops.stem_conv3d(xin, w, s.to(DEV), h.to(DEV), sd['frontend3D.2.weight'].to(DEV), crop=(H, W))
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option('stem', 2)
+    out['rel_gen1'] = rel_err(yg1, ref)
+    assert out['rel_gen1'] < 1.5e-2, out
+    dd = (y.float() - yg1.float()).abs()
+    out['gen1_vs_gen2_max_abs'] = float(dd.max())
+    out['gen1_vs_gen2_differing'] = int((y.view(torch.int16) != yg1.view(torch.int16)).sum())
+    tol = 2.0 ** -7 * max(1.0, float(y.float().abs().max()))          # one bf16 ulp at the largest magnitude
+    assert out['gen1_vs_gen2_max_abs'] <= tol and out['gen1_vs_gen2_differing'] <= max(8, y.numel() // 2000), out
+    if not (W == 88 and H % 8 == 0):
+        assert out['gen1_vs_gen2_differing'] == 0, out      # same kernel either way
+    return out
+
+
+def stem_ragged_stacked_case(B=3, T=9, seed=5):
+    """Second-generation stem with ragged clip lengths into the stacked-rows layout (one zero row between frames):
+    frames past a clip's length equal the result for zero normalised frames, the pad row stays zero, and the kernel
+    agrees with the first generation.  Odd T: the last frame pair of a clip is a half pair."""
+    sd = synth.make_video_state_dict(seed=seed, randomize=True)
+    w = packing.pack_stem_weight(sd['frontend3D.0.weight'].to(DEV))
+    s, h = packing.fold_bn(sd['frontend3D.1.weight'], sd['frontend3D.1.bias'], sd['frontend3D.1.running_mean'],
+                           sd['frontend3D.1.running_var'])
+    a = sd['frontend3D.2.weight'].to(DEV)
+    raw = torch.from_numpy(synth.lip_crops_u8([1] * B, T=T, H=96, W=96, seed=seed)).to(DEV)
+    lens = [T, max(1, T // 2), T - 2][:B]
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    from deeplip_b200 import _lib
+    outs = []
+    for opt in (1, 2):
+        _lib.set_option('stem', opt)
+        try:
+            o = torch.zeros(B * T, 23, 22, 64, device=DEV, dtype=torch.bfloat16)
+            ops.stem_conv3d(raw, w, s.to(DEV), h.to(DEV), a, crop=(88, 88), out=o, lengths=ln)
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_option('stem', 2)
+        outs.append(o)
+    out = {'max_abs_gen1_vs_gen2': float((outs[0].float() - outs[1].float()).abs().max()),
+           'pad_row_zero': bool((outs[1][:, 22] == 0).all())}
+    # each clip alone, truncated to its length, must give the same valid frames bit for bit (gen2)
+    same = True
+    for b, L in enumerate(lens):
+        ob = ops.stem_conv3d(raw[b:b + 1, :L].contiguous(), w, s.to(DEV), h.to(DEV), a, crop=(88, 88))
+        torch.cuda.synchronize()
+        # the last two valid frames see zero frames beyond the clip in both runs (temporal padding)
+        same = same and bool(torch.equal(ob.view(torch.int16), outs[1][b * T:b * T + L, :22].view(torch.int16)))
+    out['ragged_equals_alone'] = same
+    assert out['pad_row_zero'] and out['ragged_equals_alone'] and out['max_abs_gen1_vs_gen2'] < 0.05, out
     return out
 
 

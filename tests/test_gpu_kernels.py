@@ -70,6 +70,15 @@ def test_stem(kw):
     G.stem_case(**kw)
 
 
+def test_stem_second_generation_ragged_lengths_stacked_rows():
+    G.stem_ragged_stacked_case()
+
+
+def test_stem_second_generation_full_clip():
+    # 75 frames: 38 frame pairs per clip, the last one a half pair; more work units than one wave of CTAs would need
+    G.stem_case(B=3, T=75, u8=True)
+
+
 @pytest.mark.parametrize('kw', [dict(), dict(B=2, T=50, C=512, lengths=[50, 7]), dict(B=1, T=3, C=24)])
 def test_stat_pool(kw):
     G.stat_pool_case(**kw)
