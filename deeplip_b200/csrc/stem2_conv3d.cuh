@@ -99,6 +99,22 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
                : "memory");
 }
 
+// Work split: the units x tiles sequence (tile-major inside a unit) is cut into gridDim.x contiguous ranges [g0, g1) of
+// (nearly) equal length, so that no CTA waits for a last round of whole units (2 432 units on 148 CTAs would be 17
+// rounds of 11 tiles against 16.4).  A range that starts inside a unit first recomputes the tile before it (gs = g0 - 1,
+// nothing stored): the first pooled row needs that tile's last conv row.
+struct Stem2Range { int gs, g0, g1; };
+__device__ __forceinline__ Stem2Range stem2_range(const Stem2Params& p) {
+  const int total = p.units * p.tiles;
+  const int per = total / (int)gridDim.x, rem = total - per * (int)gridDim.x;
+  const int b = (int)blockIdx.x;
+  Stem2Range r;
+  r.g0 = b * per + min(b, rem);
+  r.g1 = r.g0 + per + (b < rem ? 1 : 0);
+  r.gs = (r.g0 % p.tiles) ? r.g0 - 1 : r.g0;
+  return r;
+}
+
 // BN + PReLU on 24 consecutive conv columns of one row, then the horizontal 3-max at stride 2.
 // HALF 0: columns 0..23 loaded, pooled px 0..10 (px 0 has no left neighbour); HALF 1: columns 20..43, px 11..21.
 template <int HALF>
@@ -131,15 +147,21 @@ __device__ __forceinline__ void stem2_epilogue(const Stem2Params& p, uint32_t tm
   const int px0 = HALF ? 11 : 0;
   int acc = 0, buf = 0;
   uint32_t acc_phase = 0;
-  for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-    const int fb = unit / p.pairs_per_clip;
-    const int t0 = 2 * (unit - fb * p.pairs_per_clip);
-    const int nfr = min(2, p.T - t0);
-    uint16_t* yframe0 = p.y + ((size_t)fb * p.T + t0) * p.out_img_rows * kS2Wp * 64;
-    float carry[11];
+  const Stem2Range rg = stem2_range(p);
+  int unit = rg.gs / p.tiles, tile = rg.gs - unit * p.tiles;
+  int nfr = 0;
+  uint16_t* yframe0 = nullptr;
+  float carry[11];
+  {
+    for (int gi = rg.gs; gi < rg.g1; ++gi) {
+      if (tile == 0 || gi == rg.gs) {
+        const int fb = unit / p.pairs_per_clip;
+        const int t0 = 2 * (unit - fb * p.pairs_per_clip);
+        nfr = min(2, p.T - t0);
+        yframe0 = p.y + ((size_t)fb * p.T + t0) * p.out_img_rows * kS2Wp * 64;
 #pragma unroll
-    for (int i = 0; i < 11; ++i) carry[i] = -INFINITY;
-    for (int tile = 0; tile < p.tiles; ++tile) {
+        for (int i = 0; i < 11; ++i) carry[i] = -INFINITY;   // conv row -1 does not exist (a warm-up tile sets it for real)
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t a0 = lane_addr + acc * 256;
@@ -200,7 +222,7 @@ __device__ __forceinline__ void stem2_epilogue(const Stem2Params& p, uint32_t tm
       // starts on the tile after this one
       if (issuer) bulk_wait_group_read0();
       named_bar_sync(2, kS2EpiThreads);
-      if (issuer && !(p.dbg & 2)) {
+      if (issuer && gi >= rg.g0 && !(p.dbg & 2)) {
         const uint8_t* src = stg + buf * kS2StgBytes;
         uint16_t* dst = yframe0 + (size_t)(2 * tile) * kS2Wp * 64;
         bulk_store_s2g(dst, src, 2 * kS2Wp * 128);
@@ -208,6 +230,7 @@ __device__ __forceinline__ void stem2_epilogue(const Stem2Params& p, uint32_t tm
         bulk_commit_group();
       }
       buf ^= 1;
+      if (++tile == p.tiles) { tile = 0; ++unit; }
     }
   }
   if (issuer) bulk_wait_group0();
@@ -294,8 +317,9 @@ stem2_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_const
     const uint32_t src0 = smem_u32(strips) + half * (kS2Pitch * 2) + ox * 4;
     const uint32_t dst0 = smem_u32(ubuf) + half * kS2Plane + ox * 16;
     uint32_t ph = 0, sslot = 0, sph = 0;
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      for (int tile = 0; tile < p.tiles; ++tile) {
+    const Stem2Range rg = stem2_range(p);
+    {
+      for (int gi = rg.gs; gi < rg.g1; ++gi) {
         mbar_wait(&sfull[sslot], sph);
 #pragma unroll 1
         for (int st = group; st < kS2Stages; st += 2) {
@@ -344,10 +368,12 @@ stem2_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_const
     // padding.  Four tiles of strips are in flight: a 16 KB box takes longer to arrive than a tile takes to compute.
     if (elect_one_sync()) {
       uint32_t slot = 0, ph = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        const int fb = unit / p.pairs_per_clip;
-        const int t0 = 2 * (unit - fb * p.pairs_per_clip);
-        for (int tile = 0; tile < p.tiles; ++tile) {
+      const Stem2Range rg = stem2_range(p);
+      int unit = rg.gs / p.tiles, tile = rg.gs - unit * p.tiles;
+      {
+        for (int gi = rg.gs; gi < rg.g1; ++gi) {
+          const int fb = unit / p.pairs_per_clip;
+          const int t0 = 2 * (unit - fb * p.pairs_per_clip);
           mbar_wait(&sempty[slot], ph ^ 1);
           if (p.dbg & 128) {             // timing emulation: no strip loads
             mbar_arrive(&sfull[slot]);
@@ -356,6 +382,7 @@ stem2_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_const
             tma_load_4d(strips + slot * kS2TileStrip, &mapX, &sfull[slot], 0, 8 * tile, t0 - 2, fb);
           }
           if (++slot == kS2StripSlots) { slot = 0; ph ^= 1; }
+          if (++tile == p.tiles) { tile = 0; ++unit; }
         }
       }
     }
@@ -373,8 +400,9 @@ stem2_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_const
       const uint64_t bp0 = umma_desc_noswizzle_kmajor(smem_u32(ubuf) + 3 * kS2RowBytes, kS2UStage, 128);
       uint32_t ph = 0, acc_phase = 0;
       int acc = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        for (int tile = 0; tile < p.tiles; ++tile) {
+      const Stem2Range rg = stem2_range(p);
+      {
+        for (int gi = rg.gs; gi < rg.g1; ++gi) {
           mbar_wait(&tempty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + acc * 256;

@@ -513,7 +513,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
     if (st != DL_OK) return st;
     int grid2 = device_sm_count();
     if (grid2 <= 0) grid2 = 148;
-    if (q.units < grid2) grid2 = q.units;
+    if (q.units * q.tiles < grid2) grid2 = q.units * q.tiles;
     static PerDevice<int> configured2_dev;
     int* configured2 = configured2_dev.slot();
     if (!configured2) return fail(DL_ERR_CUDA, "stem: no current device");

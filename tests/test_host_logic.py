@@ -470,3 +470,16 @@ def test_two_rank_gloo_trial_list_job_on_real_lomgrid(tmp_path):
     text = out.stdout.decode()
     assert out.returncode == 0, text[-3000:]
     assert 'rank 0 ok' in text and 'rank 1 ok' in text
+
+
+def test_stem2_layout_arithmetic_against_torch_on_cpu():
+    """The second-generation stem's data layout restated in numpy (tools/stem2_emulate.py): pre-pass frames -> 14-row
+    strips -> two parity planes of unfolded rows -> no-swizzle K-major descriptor views (SBO 128 B, LBO = plane; the
+    shared window-row-6 step with LBO = one stage) x the weight stack built from packing.pack_stem_weight ->
+    accumulator [128 lanes x 176 columns] -> per-thread BN / PReLU / 3x3-s2 max-pool with the carried conv row, compared
+    with torch's conv3d + max_pool3d.  Checks the design the CUDA kernel implements; the kernel itself is checked on the
+    GPU (tests/gpu_checks.py: stem_case)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'stem2_emulate.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr

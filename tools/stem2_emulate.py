@@ -15,10 +15,13 @@ scale = rng.standard_normal(64).astype(np.float32)
 shift = rng.standard_normal(64).astype(np.float32)
 slope = np.abs(rng.standard_normal(64)).astype(np.float32) * 0.3
 
-# packed weights (64, 320): K = kt*64 + kh*8 + kw (zero padding for kh = 7 / kw = 7)
-wp = np.zeros((64, 5, 8, 8), np.float32)
-wp[:, :, :7, :7] = w
-wp = wp.reshape(64, 320)
+# packed weights (64, 320): K = kt*64 + kh*8 + kw (zero padding for kh = 7 / kw = 7) -- the PRODUCT's packing routine
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deeplip_b200 import packing
+wb = torch.from_numpy(w).to(torch.bfloat16).float()              # the kernel multiplies bf16 weights
+w = wb.numpy()
+wp = packing.pack_stem_weight(wb[:, None]).float().numpy()
 stack = np.zeros((7 * 64, 64), np.float32)
 for i in range(1, 6):
     kt = 5 - i
