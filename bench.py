@@ -327,7 +327,18 @@ def run_job(name, args, rank, world, dev, ex, peaks, full_check):
 
     job.run(extract, score)                         # untimed pass: buffers for the batch and tail shapes, NCCL warm
     torch.cuda.synchronize()
-    res = job.run(extract, score, eer_fn=U.eer_from_scores)
+    # Three timed passes, the MEDIAN one is reported (all three are listed): a list takes 0.03 - 1.4 s, and the first pass
+    # after the step bench has been seen 2x off on a fresh box (clocks and rank skew settling).  Every pass does all the
+    # work -- extraction of every utterance, the all_gather, scoring, EER -- and passes are compared by the max over ranks.
+    passes = []
+    for _ in range(3):
+        r = job.run(extract, score, eer_fn=U.eer_from_scores)
+        torch.cuda.synchronize()
+        passes.append((dl_dist.max_over_ranks(sum(r['ms'].values()), dev), r))
+    order = sorted(range(3), key=lambda i: passes[i][0])
+    res = passes[order[1]][1]
+    pass_ms = [p_[0] for p_ in passes]
+    del passes
     gather_ok = job.verify_gather()
     # ---- the dense formulation (report both): one tensor-core GEMM over the unique left x right
     # utterances + a gather of the 20 000 wanted entries, on the job's real table; rank 0's GPU only (not sharded)
@@ -371,7 +382,8 @@ def run_job(name, args, rank, world, dev, ex, peaks, full_check):
         return None
     out = {'list': JOB_LISTS[name], 'n_utts': res['n_utts'], 'n_trials': res['n_trials'], 'dim': ex.dim,
            'global_batch': args.job_batch, 'per_gpu_batch': job.batch, 'rows_per_rank': job.per, 'scaling': 'strong',
-           'phase_ms_max_over_ranks': ms, 'device_ms': total_ms, 'eer_ms_cpu': res.get('eer_ms_cpu'),
+           'phase_ms_max_over_ranks': ms, 'device_ms': total_ms, 'device_ms_of_the_three_passes': pass_ms,
+           'eer_ms_cpu': res.get('eer_ms_cpu'),
            'wall_s': (total_ms + res.get('eer_ms_cpu', 0.0)) / 1e3,
            'utt_per_s': res['n_utts'] / (total_ms / 1e3), 'trials_per_s_scoring': res['n_trials'] / (ms['score'] / 1e3),
            'allgather_bytes': res['allgather_bytes'],
