@@ -65,7 +65,7 @@ def test_conv_igemm_rejects_bad_shapes():
 
 
 @pytest.mark.parametrize('kw', [dict(B=1, T=3, H=32, W=32), dict(B=2, T=6), dict(B=2, T=5, u8=True),
-                                dict(B=1, T=1, H=16, W=64)])
+                                dict(B=1, T=1, H=16, W=64), dict(B=1, T=2, H=64, W=88), dict(B=1, T=1, H=24, W=88)])
 def test_stem(kw):
     G.stem_case(**kw)
 
