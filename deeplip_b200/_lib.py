@@ -18,7 +18,8 @@ class ConvDesc(C.Structure):
                 ('N', 'H', 'W', 'C', 'ldx', 'Cout', 'R', 'S', 'stride_h', 'stride_w', 'pad_h', 'pad_w',
                  'dil_h', 'dil_w', 'ldy', 'ldf')] + [('f32_slope', C.c_float)] + [(n, C.c_int) for n in
                 ('img_rows', 'img_cols', 'lin', 'valid_h', 'valid_w', 'out_img_rows', 'out_img_cols',
-                 'split_channel', 'split_center_only')] + [('y_split', C.c_void_p), ('center_only_from', C.c_int)]
+                 'split_channel', 'split_center_only')] + [('y_split', C.c_void_p), ('center_only_from', C.c_int),
+                                                                      ('avgpool', C.c_int), ('avgpool_keep_y', C.c_int), ('avgpool_out', C.c_void_p)]
 
 
 _p, _i, _f = C.c_void_p, C.c_int, C.c_float
@@ -32,6 +33,7 @@ SIGNATURES = {
     'dl_conv3x3_c64_halo_bf16': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     'dl_conv_igemm_bf16': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(ConvDesc), _p],
     'dl_frame_pool_temporal_mean': [_p, _i, _i, _i, _i, _p, _p, _p, _p],
+    'dl_temporal_mean_f32': [_p, _i, _i, _i, _p, _p, _p],
     'dl_stat_pool': [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     'dl_attn_stat_pool': [_p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     'dl_attn_logits': [_p, _i, _i, _i, _p, _f, _p, _p],

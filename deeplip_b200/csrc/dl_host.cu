@@ -170,7 +170,7 @@ int make_im2col_nhwc_bf16(CUtensorMap* map, const void* base, int N, int H, int 
 
 namespace dl {
 static std::atomic<int> g_opt_pair{1}, g_opt_pair_resident{1}, g_opt_dbg{0}, g_opt_tap_share{1}, g_opt_frontend{2},
-    g_opt_stft_pad{0}, g_opt_staged{1}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{256}, g_opt_stem{2};
+    g_opt_stft_pad{0}, g_opt_staged{1}, g_opt_prepass{2}, g_opt_small_linear{1}, g_opt_statpool_mlp{4}, g_opt_statpool_slab{256}, g_opt_stem{2}, g_opt_pool_fuse{1};
 int opt_pair() { return g_opt_pair.load(std::memory_order_relaxed); }
 int opt_pair_resident() { return g_opt_pair_resident.load(std::memory_order_relaxed); }
 int opt_staged_epilogue() { return g_opt_staged.load(std::memory_order_relaxed); }
@@ -183,6 +183,7 @@ int opt_statpool_mlp() { return g_opt_statpool_mlp.load(std::memory_order_relaxe
 int opt_statpool_slab() { return g_opt_statpool_slab.load(std::memory_order_relaxed); }
 int opt_stft_pad() { return g_opt_stft_pad.load(std::memory_order_relaxed); }
 int opt_stem() { return g_opt_stem.load(std::memory_order_relaxed); }
+int opt_pool_fuse() { return g_opt_pool_fuse.load(std::memory_order_relaxed); }
 }  // namespace dl
 
 extern "C" {
@@ -196,6 +197,7 @@ int dl_set_option(const char* name, int value) {
   if (!strcmp(name, "small_linear")) { dl::g_opt_small_linear.store(value); return DL_OK; }
   if (!strcmp(name, "statpool_mlp")) { dl::g_opt_statpool_mlp.store(value); return DL_OK; }
   if (!strcmp(name, "statpool_slab")) { dl::g_opt_statpool_slab.store(value); return DL_OK; }
+  if (!strcmp(name, "pool_fuse")) { dl::g_opt_pool_fuse.store(value); return DL_OK; }
   if (!strcmp(name, "stem")) { dl::g_opt_stem.store(value); return DL_OK; }
   if (!strcmp(name, "stft_pad")) { dl::g_opt_stft_pad.store(value); return DL_OK; }
   if (!strcmp(name, "pair_resident")) { dl::g_opt_pair_resident.store(value); return DL_OK; }

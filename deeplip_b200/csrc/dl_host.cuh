@@ -31,6 +31,7 @@ int opt_small_linear();    // 1 = fc layers (P Q == 1, <= 4096 rows) run on line
 int opt_statpool_mlp();    // stat pool: 16-byte loads in flight per lane, 4 (default; measured faster) or 8
 int opt_statpool_slab();   // stat pool: channels per block, 256 (default) or 128 (half a warp per time step; measured slower)
 int opt_stem();            // 2 = channels-on-lanes stem kernel for W = 88 (default), 1 = first-generation kernel for every shape
+int opt_pool_fuse();       // 1 = dl_conv_desc.avgpool is taken in the pair kernel's epilogue where the shape allows it (default), 0 = always the pooling kernel
 int opt_stft_pad();        // stft centre padding: 0 reflect (librosa < 0.10), 1 zeros (librosa >= 0.10)
 int opt_tap_share();     // pair kernel shares one operand-A box across horizontal taps (guarded-linear mode)
 int opt_staged_epilogue();   // 1 = resident pair kernels store their tiles through shared memory + TMA (default), 0 = per-lane stores

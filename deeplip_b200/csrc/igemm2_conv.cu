@@ -168,7 +168,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       for (int t = pair; t < total; t += num_pairs) {
         int mp, n_blk;
         tile_of(t, mp, n_blk);
-        const int m0 = (2 * mp + (int)rank) * 128;
+        const int m0 = (2 * mp + (int)rank) * p.tile_rows;
         const int img = m0 / p.PQ;
         const int rem = m0 - img * p.PQ;
         const int pp = rem / p.Q;
@@ -303,7 +303,7 @@ igemm2_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int t = pair; t < total; t += num_pairs) {
       int mp, n_blk;
       tile_of(t, mp, n_blk);
-      const int tile_row0 = (2 * mp + (int)rank) * 128;
+      const int tile_row0 = (2 * mp + (int)rank) * p.tile_rows;
       long long row = (long long)tile_row0 + quarter * 32 + lane;
       const bool row_ok = igemm_map_row(p, row) && !(p.dbg & 2);
       const int cbase = n_blk * BLOCK_N;

@@ -33,6 +33,14 @@ struct IgemmParams {
   int split_c;
   int skip_n0;         // pair kernel: n blocks >= skip_n0 see the filter's centre tap only (-1: none)
   int half_skip;       // pair kernel, one resident 256-wide n block: channels >= 128 see the centre tap only -> two N=128 MMA streams
+  // K4 in the epilogue (pair kernel, staged 256-wide streaming variant): every pool_rows consecutive GEMM rows are one
+  // image; their per-channel mean goes to pool_out[image * Cout + c].  Tiles then step by tile_rows = the largest
+  // multiple of pool_rows <= 128 rows instead of 128, so that no image straddles two tiles (the MMA still covers 128
+  // rows: the surplus rows are the next tile's first rows, computed twice and pooled once).
+  int tile_rows;       // GEMM rows between consecutive m tiles (128 unless pooling)
+  int pool_rows;       // 0 = off
+  int store_y;         // 0: pooling mode without the bf16 output tensor
+  float* pool_out;
 };
 
 // GEMM row -> row of y / residual, and whether it is stored at all.
@@ -248,9 +256,31 @@ __device__ __forceinline__ void igemm_epilogue_tile_staged(const IgemmParams& p,
     // and starts on the slab after this one
     if (NBUF == 2 && issuer) bulk_wait_group_read0();
     named_bar_sync(1, 256);
-    if (issuer && !(p.dbg & 2)) {
+    if (issuer && !(p.dbg & 2) && p.store_y) {
       tma_store_2d(mapY, sb, col0 + 64 * i, tile_row0);      // col0: this n block's first channel in mapY's tensor
       bulk_commit_group();
+    }
+    if (NBUF == 2 && p.pool_rows > 0) {
+      // ---- K4: per-image mean of this slab's 64 channels, read back from the staged bf16 rows (the values the output
+      // tensor holds).  Thread = (image f of the tile, 4 channels); the pool_rows rows are added in order from 0.f and
+      // scaled by 1 / pool_rows: the arithmetic of frame_pool_kernel, bit for bit.  The slab buffer is rewritten two
+      // slabs later, behind the next slab's barrier, which every thread reaches only after this pass.
+      const int et = (int)threadIdx.x - 64;                  // epilogue warps are warps 2..9
+      const int f = et >> 4, q = et & 15;
+      if (f * p.pool_rows < p.tile_rows) {
+        const long long img = (long long)(tile_row0 / p.pool_rows) + f;
+        if ((img + 1) * p.pool_rows <= (long long)p.M) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          for (int r = 0; r < p.pool_rows; ++r) {
+            const int mm = f * p.pool_rows + r;
+            const uint2 v = *reinterpret_cast<const uint2*>(sb + mm * 128 + (((q >> 1) ^ (mm & 7)) << 4) + (q & 1) * 8);
+            s0 += bf16_lo(v.x); s1 += bf16_hi(v.x); s2 += bf16_lo(v.y); s3 += bf16_hi(v.y);
+          }
+          const float inv = 1.f / (float)p.pool_rows;
+          *reinterpret_cast<float4*>(p.pool_out + img * p.Cout + cbase + 64 * i + 4 * q) =
+              make_float4(s0 * inv, s1 * inv, s2 * inv, s3 * inv);
+        }
+      }
     }
     if (NBUF == 2) sbuf ^= 1;
   }

@@ -325,6 +325,12 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   p.skip_n0 = -1;
   p.half_skip = 0;
   p.num_m_blocks = (int)((M + 127) / 128);
+  p.tile_rows = 128; p.pool_rows = 0; p.store_y = 1; p.pool_out = nullptr;
+  const int pool = d->avgpool ? P * Q : 0;
+  if (pool > 0)
+    DL_CHECK_ARG(d->avgpool_out && y && !y_f32 && split == 0 && !lin && d->out_img_rows == 0 && d->ldy == d->Cout &&
+                     (reinterpret_cast<uintptr_t>(d->avgpool_out) & 15) == 0,
+                 "conv_igemm: avgpool needs avgpool_out (16-byte aligned), a dense bf16 y (scratch), no f32 / split / guarded output");
 
   const int block_n = d->Cout <= 64 ? 64 : (d->Cout <= 128 ? 128 : 256);
   p.num_n_blocks = (d->Cout + block_n - 1) / block_n;
@@ -347,6 +353,15 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
   const bool want_half = d->center_only_from == 128 && d->Cout == 256 && p.taps == 1 && (d->R & 1) && (d->S & 1);
   const int staged = pair ? igemm_pair_staged(p, block_n, want_half) : 0;
   p.half_skip = staged == 2 ? 1 : 0;
+  // K4 in the epilogue: the streaming 256-wide staged variant reads the image means off its staged output tiles
+  const bool pool_fused = pool > 0 && pair && staged == 3 && pool <= 128 && d->Cout % 64 == 0 && opt_pool_fuse();
+  if (pool_fused) {
+    p.tile_rows = (128 / pool) * pool;
+    p.num_m_blocks = (int)((M + p.tile_rows - 1) / p.tile_rows);
+    p.pool_rows = pool;
+    p.pool_out = d->avgpool_out;
+    p.store_y = d->avgpool_keep_y ? 1 : 0;
+  }
 
   CUtensorMap mapA, mapB;
   if (lin) {
@@ -374,11 +389,15 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
         st = make_tiled_2d_bf16(&mapY2, d->y_split, (uint64_t)M, (uint64_t)(d->Cout - split), (uint64_t)d->ldy, 128, 64);
       if (st != DL_OK) return st;
     }
-    return launch_igemm_pair(mapA, mapB, p, block_n, s, staged ? &mapY : nullptr, (staged && split > 0) ? &mapY2 : nullptr);
+    st = launch_igemm_pair(mapA, mapB, p, block_n, s, staged ? &mapY : nullptr, (staged && split > 0) ? &mapY2 : nullptr);
+    if (st != DL_OK || pool == 0 || pool_fused) return st;
+    return dl_frame_pool_temporal_mean(y, d->N, 1, pool, d->Cout, nullptr, d->avgpool_out, nullptr, stream);
   }
   switch (block_n) {
-    case 64: return resident ? launch_igemm<64, true>(mapA, mapB, p, s) : launch_igemm<64, false>(mapA, mapB, p, s);
-    case 128: return resident ? launch_igemm<128, true>(mapA, mapB, p, s) : launch_igemm<128, false>(mapA, mapB, p, s);
-    default: return resident ? launch_igemm<256, true>(mapA, mapB, p, s) : launch_igemm<256, false>(mapA, mapB, p, s);
+    case 64: st = resident ? launch_igemm<64, true>(mapA, mapB, p, s) : launch_igemm<64, false>(mapA, mapB, p, s); break;
+    case 128: st = resident ? launch_igemm<128, true>(mapA, mapB, p, s) : launch_igemm<128, false>(mapA, mapB, p, s); break;
+    default: st = resident ? launch_igemm<256, true>(mapA, mapB, p, s) : launch_igemm<256, false>(mapA, mapB, p, s); break;
   }
+  if (st != DL_OK || pool == 0) return st;
+  return dl_frame_pool_temporal_mean(y, d->N, 1, pool, d->Cout, nullptr, d->avgpool_out, nullptr, stream);
 }

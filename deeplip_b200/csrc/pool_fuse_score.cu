@@ -218,6 +218,39 @@ __global__ void __launch_bounds__(256) frame_pool_kernel(const uint16_t* __restr
   }
 }
 
+// The temporal half of frame_pool_kernel on f32 frame features (the conv epilogue already took the spatial mean,
+// dl_conv_desc.avgpool): same thread layout, same order of additions -> same bits as the one-kernel form.
+__global__ void __launch_bounds__(256) temporal_mean_kernel(const float* __restrict__ ff, int T, int C,
+                                                            const int32_t* __restrict__ lengths,
+                                                            float* __restrict__ utt_mean) {
+  __shared__ float sm[32][64];
+  const int b = blockIdx.x;
+  const int cb = blockIdx.y * 64;
+  const int ct = threadIdx.x & 7, g = threadIdx.x >> 3;
+  const int c = cb + ct * 8;
+  int len = lengths ? lengths[b] : T;
+  len = max(1, min(len, T));
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c < C) {
+    for (int t = g; t < len; t += 32) {
+      const float4* src = reinterpret_cast<const float4*>(ff + ((size_t)b * T + t) * C + c);
+      const float4 u = __ldg(src), w = __ldg(src + 1);
+      acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+      acc[4] += w.x; acc[5] += w.y; acc[6] += w.z; acc[7] += w.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[g][ct * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64 && cb + threadIdx.x < C) {
+    float s = 0.f;
+    for (int gg = 0; gg < 32; ++gg) s += sm[gg][threadIdx.x];
+    utt_mean[(size_t)b * C + cb + threadIdx.x] = s / (float)len;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row z-norm of two modalities + concat (+ L2).  One warp per utterance.
 __device__ __forceinline__ void row_stats(const float* r, int D, int lane, bool biased, float& mean, float& sd) {
@@ -465,6 +498,15 @@ extern "C" int dl_frame_pool_temporal_mean(const void* x, int B, int T, int HW, 
     frame_pool_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, T, HW, C, lengths, frame_feats,
                                                                  utt_mean);
   return check_launch("frame_pool_kernel");
+}
+
+extern "C" int dl_temporal_mean_f32(const float* frame_feats, int B, int T, int C, const int32_t* lengths,
+                                    float* utt_mean, void* stream) {
+  DL_CHECK_ARG(frame_feats && utt_mean, "temporal_mean: null pointer");
+  DL_CHECK_ARG(B > 0 && T > 0 && C > 0 && C % 8 == 0 && C <= 2048, "temporal_mean: bad shape");
+  DL_CHECK_ARG((reinterpret_cast<uintptr_t>(frame_feats) & 15) == 0, "temporal_mean: frame_feats must be 16-byte aligned");
+  temporal_mean_kernel<<<dim3(B, (C + 63) / 64), 256, 0, (cudaStream_t)stream>>>(frame_feats, T, C, lengths, utt_mean);
+  return check_launch("temporal_mean_kernel");
 }
 
 extern "C" int dl_znorm_concat(const float* a, int Da, const float* v, int Dv, int B, int biased, int video_first,

@@ -169,7 +169,7 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
 def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=(1, 1), scale=None, shift=None,
                slope=None, residual=None, want_bf16=True, want_f32=False, scale2=None, shift2=None,
                f32_slope=1.0, H=None, W=None, out=None, out_channel_offset=0, residual_channel_offset=0, split=None,
-               center_only_from=0):
+               center_only_from=0, avgpool=False, avgpool_keep_y=False):
     """x: (N,H,W,ldx) bf16 channels-last -- or (N,img_rows,img_cols,ldx) stacked / guarded with the true extents
     passed as H, W.  `out` may be a wider (channel slice) and / or guarded (N, >=P, >=Q, ld) caller-owned buffer;
     with `out`, `residual` is a buffer of out's shape read at `residual_channel_offset` (the kernel indexes the residual
@@ -178,6 +178,9 @@ def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=
     center_only, are declared to have zero weights off the centre tap (dl_conv_desc.split_channel); the first return
     value is then the pair (y[..., :c], y[..., c:]) as two dense tensors.
     center_only_from=c: declares channels >= c centre-tap-only without splitting the output (dl_conv_desc.center_only_from).
+    avgpool=True (K4 in the epilogue, dl_conv_desc.avgpool): the second return value is the global average pool of every
+    output image, (N, Cout) f32; the first one is only defined with avgpool_keep_y (else it is scratch the fused path
+    does not write).
     Returns (y_bf16 (N,P,Q,Cout) | out | None, y_f32 (N*P*Q,Cout) | None)."""
     _need_cuda(x, w_packed, scale, shift, slope, residual, scale2, shift2)
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
@@ -224,6 +227,14 @@ def conv_igemm(x, w_packed, Cin, Cout, R=1, S=1, stride=(1, 1), pad=(0, 0), dil=
         r_ptr = C.c_void_p(residual.data_ptr() + 2 * residual_channel_offset)
     d = ConvDesc(N, H, W, Cin, ldx, Cout, R, S, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ldy, Cout,
                  float(f32_slope), img_rows, img_cols, 0, 0, 0, out_rows, out_cols, 0, 0, None, int(center_only_from))
+    if avgpool:
+        assert out is None and not want_f32 and want_bf16
+        yf = torch.empty((N, Cout), device=x.device, dtype=torch.float32)      # image means ride in the f32 slot of the return
+        d.avgpool, d.avgpool_keep_y, d.avgpool_out = 1, int(bool(avgpool_keep_y)), yf.data_ptr()
+        st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
+                                           r_ptr, _ptr(y), None, _ptr(scale2), _ptr(shift2), C.byref(d), _stream())
+        _lib.check(st, 'dl_conv_igemm_bf16')
+        return (y if avgpool_keep_y else None), yf
     st = _lib.lib().dl_conv_igemm_bf16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope),
                                        r_ptr, y_ptr if y_ptr is not None else _ptr(y), _ptr(yf),
                                        _ptr(scale2), _ptr(shift2), C.byref(d), _stream())
@@ -279,6 +290,19 @@ def frame_pool_temporal_mean(x, B, T, lengths=None, want_frames=True, want_mean=
     st = _lib.lib().dl_frame_pool_temporal_mean(_ptr(x), B, T, HW, Cc, _ptr(lengths), _ptr(ff), _ptr(um), _stream())
     _lib.check(st, 'dl_frame_pool_temporal_mean')
     return ff, um
+
+
+def temporal_mean(frame_feats, B, T, lengths=None):
+    """frame_feats: (B*T, C) or (B, T, C) f32 -> (B, C) f32 mean over the first lengths[b] frames (the temporal half of
+    K4; same bits as frame_pool_temporal_mean's utt_mean)."""
+    _need_cuda(frame_feats, lengths)
+    assert frame_feats.dtype == torch.float32 and frame_feats.is_contiguous()
+    Cc = frame_feats.shape[-1]
+    assert frame_feats.numel() == B * T * Cc
+    um = torch.empty((B, Cc), device=frame_feats.device, dtype=torch.float32)
+    st = _lib.lib().dl_temporal_mean_f32(_ptr(frame_feats), B, T, Cc, _ptr(lengths), _ptr(um), _stream())
+    _lib.check(st, 'dl_temporal_mean_f32')
+    return um
 
 
 def stat_pool(x, Cc, lengths=None, want_f32=True, want_bf16=True, logits=None):

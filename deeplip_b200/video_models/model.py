@@ -84,8 +84,9 @@ class Lipreading(nn.Module):
             self._pk = pk
         return self._pk
 
-    def trunk_maps(self, x, lengths=None):
-        """x: (B,T,H,W) f32 normalised frames or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T,3,3,512) bf16.
+    def trunk_maps(self, x, lengths=None, avgpool=False):
+        """x: (B,T,H,W) f32 normalised frames or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T,3,3,512) bf16; with
+        avgpool=True the per-frame pooled features (B*T,512) f32 instead (K4's spatial half in the last conv's epilogue).
         lengths (int32 CUDA, optional): frames at or beyond a clip's length enter the stem as zero normalised
         frames (what pad_packed_collate produces), whatever the padding bytes of a raw u8 batch are."""
         if self.training:
@@ -97,15 +98,14 @@ class Lipreading(nn.Module):
             # stem writes straight into the stacked-rows layout layer1's halo kernel consumes
             buf = self.trunk.stacked_buffers(B * T, H // 4, W // 4, x.device, 2 * len(self.trunk.layer1) + 1)[-1]
             ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], out=buf, lengths=lengths)
-            return self.trunk.forward_nhwc(buf, stacked_H=H // 4)
+            return self.trunk.forward_nhwc(buf, stacked_H=H // 4, avgpool=avgpool)
         y = ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], lengths=lengths)
-        return self.trunk.forward_nhwc(y)
+        return self.trunk.forward_nhwc(y, avgpool=avgpool)
 
     def forward(self, x, lengths=None):
         B, C, T, H, W = x.size()
         assert C == 1
-        y = self.trunk_maps(x[:, 0])
-        feats, _ = ops.frame_pool_temporal_mean(y, B, T, want_frames=True, want_mean=False)
+        feats = self.trunk_maps(x[:, 0], avgpool=True).view(B, T, -1)
         if self.extract_feats:
             return feats                  # (B, T, 512); lengths unused when extract_feats (model.py:105)
         return self.tcn(feats, lengths, B)
@@ -114,6 +114,5 @@ class Lipreading(nn.Module):
         """Fused form of train_fusion.py:400: mean over the (valid) frames of each clip -> (B,512).
         x as in trunk_maps; lengths: int32 CUDA tensor of valid frame counts (zero-padded tails)."""
         B, T = x.shape[0], x.shape[1]
-        y = self.trunk_maps(x, lengths)
-        _, mean = ops.frame_pool_temporal_mean(y, B, T, lengths=lengths, want_frames=False, want_mean=True)
-        return mean
+        feats = self.trunk_maps(x, lengths, avgpool=True)          # (B*T, 512) f32
+        return ops.temporal_mean(feats, B, T, lengths=lengths)

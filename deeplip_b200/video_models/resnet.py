@@ -161,10 +161,11 @@ class BasicBlock(nn.Module):
                        pk['a2'], residual=x, out=out)
         return out
 
-    def forward_nhwc(self, x, H=None, W=None):
+    def forward_nhwc(self, x, H=None, W=None, avgpool=False):
         """x: (N,H,W,inplanes) bf16 -> (N,P,Q,planes) bf16  (reference forward :56-69).  With H (W) given, x is in
         a stacked / guarded layout (N, img_rows >= H, img_cols >= W, C); only blocks with a downsample branch
-        accept that."""
+        accept that.  avgpool=True: returns the global average pool of the block's output instead, (N, planes) f32,
+        taken in the last conv's epilogue (resnet.py:125-126 fused, K4)."""
         pk = self._packed()
         st = (self.stride, self.stride)
         out, _ = ops.conv_igemm(x, pk['w1'], self.inplanes, self.planes, 3, 3, st, (1, 1), (1, 1),
@@ -175,9 +176,9 @@ class BasicBlock(nn.Module):
         else:
             assert H is None and W is None, 'identity residual needs the dense layout'
             res = x
-        out, _ = ops.conv_igemm(out, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1),
-                                pk['s2'], pk['h2'], pk['a2'], residual=res)
-        return out
+        out, pooled = ops.conv_igemm(out, pk['w2'], self.planes, self.planes, 3, 3, (1, 1), (1, 1), (1, 1),
+                                     pk['s2'], pk['h2'], pk['a2'], residual=res, avgpool=avgpool)
+        return pooled if avgpool else out
 
     def forward(self, x):
         y = self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
@@ -270,9 +271,12 @@ class ResNet(nn.Module):
         return ops.BUFFERS.get(('stacked', id(self), N, H, W, str(device), count), lambda: [
             torch.zeros((N, H + 1, W, 64), device=device, dtype=torch.bfloat16) for _ in range(count)])
 
-    def forward_nhwc(self, x, stacked_H=None):
+    def forward_nhwc(self, x, stacked_H=None, avgpool=False):
         """(N,H,W,64) bf16 -- or stacked rows (N,H+1,W,64) with stacked_H=H -- -> (N,P,Q,512) bf16, before the
-        global average pool."""
+        global average pool; with avgpool=True the pooled (N,512) f32 features instead (the pool rides in the epilogue
+        of layer4's last conv)."""
+        last = list(self.layer4)[-1]
+        kw = lambda blk: dict(avgpool=True) if (avgpool and blk is last) else {}
         N, rows, W, _ = x.shape
         H = stacked_H or rows
         if self.halo_enabled(W):
@@ -308,7 +312,7 @@ class ResNet(nn.Module):
                     else:
                         x = blocks[0].forward_nhwc(x)
                     for blk in blocks[1:]:
-                        x = blk.forward_nhwc(x)
+                        x = blk.forward_nhwc(x, **kw(blk))
                 return x
             else:
                 x = self.layer2[0].forward_nhwc(x, H=H)
@@ -319,12 +323,9 @@ class ResNet(nn.Module):
                 x = blk.forward_nhwc(x)
             rest = list(self.layer2) + list(self.layer3)
         for blk in rest + list(self.layer4):
-            x = blk.forward_nhwc(x)
+            x = blk.forward_nhwc(x, **kw(blk))
         return x
 
     def forward(self, x):
         """Reference signature: (N,64,H,W) f32 -> (N,512) f32 (resnet.py:120-127)."""
-        y = self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
-        N = y.shape[0]
-        feats, _ = ops.frame_pool_temporal_mean(y, N, 1, want_frames=True, want_mean=False)
-        return feats.view(N, -1)
+        return self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), avgpool=True)

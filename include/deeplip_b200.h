@@ -165,6 +165,16 @@ typedef struct dl_conv_desc {
    * N = 128 MMAs over all taps and the skip half with N = 128 MMAs on the centre tap only (5/9 of the tensor work of
    * the N = 256 form); every other kernel ignores the hint and multiplies the zeros: same bits. */
   int center_only_from;
+  /* K4 in the conv's epilogue (0 = off): avgpool = 1 asks for the global average pool of every output image
+   * (AdaptiveAvgPool2d(1), models/video_models/resnet.py:125-126) as avgpool_out[n * Cout + c] f32, computed from the
+   * bf16-rounded outputs in the order dl_frame_pool_temporal_mean uses (same bits).  Where the shape allows it -- the
+   * CTA-pair kernel with the staged epilogue, P*Q <= 128, Cout % 64 == 0 -- the means are taken from the staged output
+   * tiles (m tiles then step by the largest multiple of P*Q rows <= 128, so that no image straddles two tiles) and,
+   * with avgpool_keep_y = 0, the bf16 tensor is not written at all; otherwise the conv runs as usual and a pooling
+   * kernel follows.  y must be a valid (N, P, Q, Cout) buffer either way (scratch when avgpool_keep_y = 0).
+   * Needs a dense output (no split, no guarded / sliced y), no f32 side output. */
+  int avgpool, avgpool_keep_y;
+  float* avgpool_out;
 } dl_conv_desc;
 
 int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
@@ -191,6 +201,11 @@ int dl_conv3x3_c64_halo_bf16(const void* x, const void* w_packed, const float* s
  */
 int dl_frame_pool_temporal_mean(const void* x, int B, int T, int HW, int C, const int32_t* lengths,
                                 float* frame_feats, float* utt_mean, void* stream);
+/* The temporal half of K4 on frame features that already exist (dl_conv_desc.avgpool): frame_feats (B, T, C) f32 ->
+ * utt_mean (B, C) f32 = mean over the first lengths[b] frames (NULL = T), summed in dl_frame_pool_temporal_mean's
+ * order (same bits as the one-kernel form). */
+int dl_temporal_mean_f32(const float* frame_feats, int B, int T, int C, const int32_t* lengths, float* utt_mean,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K6  statistics pooling.  Replaces MeanStdPooling (models/audio_models/pooling.py:18-26):

@@ -1062,3 +1062,68 @@ def frontend_pcm16_case(B=3, nsamp=24000, seed=4):
             out['%s%s' % (kind, '' if ln is None else '_ragged')] = bool(torch.equal(a32, b32) and torch.equal(ab, bb))
     assert all(out.values()), out
     return out
+
+
+def avgpool_fused_case(N=2400, C=512, lengths=(75, 3, 40), seed=0):
+    """K4 in the epilogue of a 3x3 conv with residual (layer4's last conv at pair-kernel size): the image means taken
+    from the staged output tiles (126-row m tiles) equal, BIT FOR BIT, the unfused path (conv as usual, then the pooling
+    kernel), with and without the bf16 tensor being written; and the temporal half run on those frame features equals
+    the one-kernel K4 (ragged lengths included)."""
+    from deeplip_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn(N, 3, 3, C, device=DEV, generator=g).to(torch.bfloat16)
+    res = torch.randn(N, 3, 3, C, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(C, 9 * C, device=DEV, generator=g) * 0.02).to(torch.bfloat16)
+    sc = torch.rand(C, device=DEV, generator=g) + 0.5
+    sh = torch.randn(C, device=DEV, generator=g) * 0.1
+    sl = torch.rand(C, device=DEV, generator=g) * 0.5
+    conv = lambda **kw: ops.conv_igemm(x, w, C, C, 3, 3, (1, 1), (1, 1), (1, 1), sc, sh, sl, residual=res, **kw)
+    y_ref, _ = conv()
+    out = {}
+    _lib.set_option('pool_fuse', 0)
+    try:
+        y0, p0 = conv(avgpool=True, avgpool_keep_y=True)
+    finally:
+        _lib.set_option('pool_fuse', 1)
+    y1, p1 = conv(avgpool=True, avgpool_keep_y=True)
+    _, p2 = conv(avgpool=True)
+    torch.cuda.synchronize()
+    out['y_unfused_equal'] = bool(torch.equal(y0, y_ref))
+    out['y_fused_equal'] = bool(torch.equal(y1, y_ref))
+    out['pool_fused_equals_unfused'] = bool(torch.equal(p0, p1))
+    out['pool_without_y_equal'] = bool(torch.equal(p0, p2))
+    ref = y_ref.float().view(N, 9, C).mean(1)
+    out['pool_abs_vs_torch'] = float((p1 - ref).abs().max())
+    T = 75
+    B = N // T
+    ln = torch.tensor([lengths[i % len(lengths)] for i in range(B)], dtype=torch.int32, device=DEV)
+    ff, um = ops.frame_pool_temporal_mean(y_ref, B, T, lengths=ln)
+    um2 = ops.temporal_mean(p1, B, T, lengths=ln)
+    torch.cuda.synchronize()
+    out['frame_feats_equal'] = bool(torch.equal(ff.view(N, C), p1))
+    out['temporal_mean_equal'] = bool(torch.equal(um, um2))
+    assert all(v for k, v in out.items() if k != 'pool_abs_vs_torch') and out['pool_abs_vs_torch'] < 1e-4, out
+    return out
+
+
+def avgpool_model_case(B=28, T=75, seed=3):
+    """Lipreading.utterance_embedding at a batch that puts layer4's last conv on the pair kernel (fused K4) against the
+    same call with the fusion switched off, and against every clip run alone (small batches take the unfused path):
+    bit-identical, i.e. an utterance's embedding does not depend on which path its batch size selects."""
+    from deeplip_b200 import _lib
+    from deeplip_b200.pipeline import build_models
+    _, video = build_models(DEV, seed=seed)
+    raw = torch.from_numpy(synth.lip_crops_u8(list(range(B)), T=T, H=96, W=96, seed=seed)).to(DEV)
+    ln = torch.tensor([T - (3 * i) % 40 for i in range(B)], dtype=torch.int32, device=DEV)
+    fused = video.utterance_embedding(raw, ln).clone()
+    _lib.set_option('pool_fuse', 0)
+    try:
+        plain = video.utterance_embedding(raw, ln).clone()
+    finally:
+        _lib.set_option('pool_fuse', 1)
+    alone = torch.cat([video.utterance_embedding(raw[i:i + 1, :int(ln[i])].contiguous()) for i in (0, 5, B - 1)])
+    torch.cuda.synchronize()
+    out = {'fused_equals_unfused': bool(torch.equal(fused, plain)),
+           'batch_equals_alone': bool(torch.equal(fused[[0, 5, B - 1]], alone))}
+    assert all(out.values()), out
+    return out

@@ -124,3 +124,7 @@ def test_scoring_empty_list():
                                 dict(delta=True, feat_type='stft', B=2, nsamp=8000)])
 def test_frontend(kw):
     G.frontend_case(**kw)
+
+
+def test_avgpool_in_the_conv_epilogue_is_bit_identical_to_the_pooling_kernel():
+    G.avgpool_fused_case()

@@ -109,3 +109,7 @@ def test_reference_wire_format_roundtrip(tmp_path):
     eer, thr = U.eer_cos_grid('run1', trial_path=p, root=str(tmp_path / 'exp'))
     eer2, _ = U.eer_cos(tl, emb)
     assert abs(eer - eer2) < 1e-12 and 0 < eer < 0.5
+
+
+def test_video_embedding_with_fused_avgpool_equals_unfused_and_alone():
+    G.avgpool_model_case()
