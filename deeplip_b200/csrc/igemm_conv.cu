@@ -233,6 +233,21 @@ bool igemm_pair_resident(const IgemmParams& p, int block_n);   // the pair kerne
 
 }  // namespace dl
 
+namespace dl {
+// Unfused form of dl_conv_desc.avgpool: the pooling kernel over y (N images of `pool` rows).  frame_pool_kernel works
+// on (utterance, frame) pairs with 32 frame groups per block: N images are presented as N / 32 "utterances" of 32
+// frames (+ a tail of single-frame ones), which keeps all 256 threads of a block busy; same arithmetic per image.
+static int avgpool_unfused(const void* y, int N, int pool, int Cout, float* out, void* stream) {
+  const int nb = N / 32, rem = N - nb * 32;
+  int st = DL_OK;
+  if (nb > 0) st = dl_frame_pool_temporal_mean(y, nb, 32, pool, Cout, nullptr, out, nullptr, stream);
+  if (st == DL_OK && rem > 0)
+    st = dl_frame_pool_temporal_mean(static_cast<const uint16_t*>(y) + (size_t)nb * 32 * pool * Cout, rem, 1, pool, Cout, nullptr,
+                                     out + (size_t)nb * 32 * Cout, nullptr, stream);
+  return st;
+}
+}  // namespace dl
+
 extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const float* scale, const float* shift,
                                   const float* slope, const void* residual, void* y, float* y_f32,
                                   const float* scale2, const float* shift2, const dl_conv_desc* d, void* stream) {
@@ -391,7 +406,7 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
     }
     st = launch_igemm_pair(mapA, mapB, p, block_n, s, staged ? &mapY : nullptr, (staged && split > 0) ? &mapY2 : nullptr);
     if (st != DL_OK || pool == 0 || pool_fused) return st;
-    return dl_frame_pool_temporal_mean(y, d->N, 1, pool, d->Cout, nullptr, d->avgpool_out, nullptr, stream);
+    return avgpool_unfused(y, d->N, pool, d->Cout, d->avgpool_out, stream);
   }
   switch (block_n) {
     case 64: st = resident ? launch_igemm<64, true>(mapA, mapB, p, s) : launch_igemm<64, false>(mapA, mapB, p, s); break;
@@ -399,5 +414,5 @@ extern "C" int dl_conv_igemm_bf16(const void* x, const void* w_packed, const flo
     default: st = resident ? launch_igemm<256, true>(mapA, mapB, p, s) : launch_igemm<256, false>(mapA, mapB, p, s); break;
   }
   if (st != DL_OK || pool == 0) return st;
-  return dl_frame_pool_temporal_mean(y, d->N, 1, pool, d->Cout, nullptr, d->avgpool_out, nullptr, stream);
+  return avgpool_unfused(y, d->N, pool, d->Cout, d->avgpool_out, stream);
 }

@@ -39,7 +39,8 @@ const char* dl_last_error(void);
  * "small_linear" (1 = fc layers on linear_small_kernel, 0 = igemm),
  * "statpool_mlp" (4 | 8 loads in flight), "staged_epilogue" (1 = the CTA-pair kernels send their output tiles through
  * shared-memory slabs and TMA stores, 0 = per-lane 16-byte stores; bit-identical), "stft_pad" (0 reflect | 1 zeros: a
- * convention, not a tuning switch).  Results agree to fp32 summation order either way.
+ * convention, not a tuning switch), "pool_fuse" (1 = dl_conv_desc.avgpool is taken in the pair kernel's epilogue where
+ * the shape allows it, 0 = always conv + pooling kernel; bit-identical).  Results agree to fp32 summation order either way.
  * "dbg" (default 0) is a measurement aid only: bits 1/2/4 drop the residual / stores / whole epilogue of the
  * pair kernel, 8 issues one MMA in four, 16/32 idle the stem's builders / epilogue, 4096/8192 widen the stem's MMAs,
  * 16384 drops its strip loads, bits 16..19 set its strip ring depth (tools/entry_ablate.py, tools/stem_try.py); in the
