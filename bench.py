@@ -569,7 +569,7 @@ def run_ours(args, rank, world, local):
     # DRAM bytes per launch: ncu cannot run inside the bench (a number taken under a profiler is not a bench value), so
     # this cites the committed capture of the same step, and says which commit's kernels it saw
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, 'profiles', 'r2d_trunk_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r2e_trunk_traffic.json')
     if os.path.exists(tpath) and B == 64:
         tj = json.load(open(tpath))
         traffic = tj['trunk_dram_bytes_per_step'] / max(1, n_trunk)

@@ -29,7 +29,7 @@ launches = [d for d in byid.values() if 'us' in d]
 per_step = len(launches) // steps
 last = launches[-per_step:]                       # the last step: warm caches of packed weights, steady allocator
 i0 = next(i for i, d in enumerate(last) if 'stem_conv3d' in d['name'] or 'stem2_conv3d' in d['name'])
-i1 = next(i for i, d in enumerate(last) if 'frame_pool' in d['name'])
+i1 = next(i for i, d in enumerate(last) if 'frame_pool' in d['name'] or 'temporal_mean' in d['name'])
 trunk = last[i0 + 1:i1]                        # the ResNet-18 body: everything between the stem and the frame pool
 txt = ['one AV extraction step, B=64, commit %s: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,'
        'dram__bytes_write.sum --clock-control none, per launch (last of %d steps)' % (commit, steps), '']
