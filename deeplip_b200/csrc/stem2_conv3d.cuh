@@ -135,8 +135,31 @@ __device__ __forceinline__ void stem2_row(const uint32_t (&v)[24], float sc, flo
   }
 }
 
+// Pool-first form for channels whose BN + PReLU is monotone (slope >= 0): max(f(v)) == f(max v) for scale >= 0 and
+// == f(min v) for scale <= 0 -- exactly, f being applied to one of the v either way -- so the 3x3/2 pooling runs on the
+// RAW accumulators (FMNMX3 only) and BN + PReLU touch the 22 pooled values of a tile instead of its 96 conv values.
+// kMax: horizontal max (else min) of the raw columns, same windows as stem2_row.
+template <int HALF, bool kMax>
+__device__ __forceinline__ void stem2_row_raw(const uint32_t (&v)[24], float (&hp)[11]) {
+  auto op = [](float a, float b) { return kMax ? fmaxf(a, b) : fminf(a, b); };
+  float z[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) z[k] = __uint_as_float(v[k]);
+  if (HALF == 0) {
+    hp[0] = op(z[0], z[1]);
+#pragma unroll
+    for (int i = 1; i < 11; ++i) hp[i] = op(op(z[2 * i - 1], z[2 * i]), z[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 11; ++i) hp[i] = op(op(z[2 * i + 1], z[2 * i + 2]), z[2 * i + 3]);
+  }
+}
+
+// Epilogue modes (one per warp, from its 32 channels' parameters): 0 = general (BN + PReLU on every conv value, then
+// the max-pool: any parameters), 1 = pool-first, all scales >= 0 (max of the raw values), 2 = pool-first with mixed
+// signs of the scale (max AND min of the raw values, the thread keeps the one its channel needs).
 // Epilogue of one warp over all units of this CTA.  q = TMEM lane quarter: lanes 0..63 = frame t0, 64..127 = frame t0+1.
-template <int HALF>
+template <int HALF, int MODE>
 __device__ __forceinline__ void stem2_epilogue(const Stem2Params& p, uint32_t tmem_base, uint64_t* tfull,
                                                uint64_t* tempty, uint8_t* stg, int q, int lane) {
   const int g = q >> 1;
@@ -152,6 +175,8 @@ __device__ __forceinline__ void stem2_epilogue(const Stem2Params& p, uint32_t tm
   int nfr = 0;
   uint16_t* yframe0 = nullptr;
   float carry[11];
+  float carry_mn[MODE == 2 ? 11 : 1];          // MODE 2: the min-pooled raw row next to the max-pooled one
+  const bool use_min = sc < 0.f;               // MODE 2: this channel's BN turns the order around
   {
     for (int gi = rg.gs; gi < rg.g1; ++gi) {
       if (tile == 0 || gi == rg.gs) {
@@ -160,7 +185,10 @@ __device__ __forceinline__ void stem2_epilogue(const Stem2Params& p, uint32_t tm
         nfr = min(2, p.T - t0);
         yframe0 = p.y + ((size_t)fb * p.T + t0) * p.out_img_rows * kS2Wp * 64;
 #pragma unroll
-        for (int i = 0; i < 11; ++i) carry[i] = -INFINITY;   // conv row -1 does not exist (a warm-up tile sets it for real)
+        for (int i = 0; i < 11; ++i) {                       // conv row -1 does not exist (a warm-up tile sets it for real)
+          carry[i] = -INFINITY;
+          if (MODE == 2) carry_mn[i] = INFINITY;
+        }
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -181,31 +209,67 @@ __device__ __forceinline__ void stem2_epilogue(const Stem2Params& p, uint32_t tm
         mbar_arrive(&tempty[acc]);                    // the accumulator is in registers: the next tile's MMAs may start
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        float h0[11], h1[11];
-        if (p.dbg & 64) {                // timing emulation: no BN / PReLU / pooling arithmetic
+        if (MODE == 0) {
+          float h0[11], h1[11];
+          if (p.dbg & 64) {                // timing emulation: no BN / PReLU / pooling arithmetic
 #pragma unroll
-          for (int i = 0; i < 11; ++i) { h0[i] = __uint_as_float(v0[i]); h1[i] = __uint_as_float(v1[i]); }
+            for (int i = 0; i < 11; ++i) { h0[i] = __uint_as_float(v0[i]); h1[i] = __uint_as_float(v1[i]); }
+          } else {
+            stem2_row<HALF>(v0, sc, sh, sl, h0);
+            stem2_row<HALF>(v1, sc, sh, sl, h1);
+          }
+#pragma unroll
+          for (int i = 0; i < 11; ++i) {
+            pa[i] = fmaxf(fmaxf(carry[i], h0[i]), h1[i]);
+            pb[i] = h1[i];
+          }
+          float h2[11], h3[11];
+          if (p.dbg & 64) {
+#pragma unroll
+            for (int i = 0; i < 11; ++i) { h2[i] = __uint_as_float(v2[i]); h3[i] = __uint_as_float(v3[i]); }
+          } else {
+            stem2_row<HALF>(v2, sc, sh, sl, h2);
+            stem2_row<HALF>(v3, sc, sh, sl, h3);
+          }
+#pragma unroll
+          for (int i = 0; i < 11; ++i) {
+            pb[i] = fmaxf(fmaxf(pb[i], h2[i]), h3[i]);
+            carry[i] = h3[i];
+          }
         } else {
-          stem2_row<HALF>(v0, sc, sh, sl, h0);
-          stem2_row<HALF>(v1, sc, sh, sl, h1);
-        }
+          // pool the raw accumulators, then BN + PReLU on the 22 pooled values
+          float h0[11], h1[11], h2[11], h3[11];
+          stem2_row_raw<HALF, true>(v0, h0);
+          stem2_row_raw<HALF, true>(v1, h1);
+          stem2_row_raw<HALF, true>(v2, h2);
+          stem2_row_raw<HALF, true>(v3, h3);
 #pragma unroll
-        for (int i = 0; i < 11; ++i) {
-          pa[i] = fmaxf(fmaxf(carry[i], h0[i]), h1[i]);
-          pb[i] = h1[i];
-        }
-        float h2[11], h3[11];
-        if (p.dbg & 64) {
+          for (int i = 0; i < 11; ++i) {
+            pa[i] = fmaxf(fmaxf(carry[i], h0[i]), h1[i]);
+            pb[i] = fmaxf(fmaxf(h1[i], h2[i]), h3[i]);
+            carry[i] = h3[i];
+          }
+          if (MODE == 2) {
+            float qa[11], qb[11];
+            stem2_row_raw<HALF, false>(v0, h0);
+            stem2_row_raw<HALF, false>(v1, h1);
+            stem2_row_raw<HALF, false>(v2, h2);
+            stem2_row_raw<HALF, false>(v3, h3);
 #pragma unroll
-          for (int i = 0; i < 11; ++i) { h2[i] = __uint_as_float(v2[i]); h3[i] = __uint_as_float(v3[i]); }
-        } else {
-          stem2_row<HALF>(v2, sc, sh, sl, h2);
-          stem2_row<HALF>(v3, sc, sh, sl, h3);
-        }
+            for (int i = 0; i < 11; ++i) {
+              qa[i] = fminf(fminf(carry_mn[i], h0[i]), h1[i]);
+              qb[i] = fminf(fminf(h1[i], h2[i]), h3[i]);
+              carry_mn[i] = h3[i];
+              pa[i] = use_min ? qa[i] : pa[i];
+              pb[i] = use_min ? qb[i] : pb[i];
+            }
+          }
 #pragma unroll
-        for (int i = 0; i < 11; ++i) {
-          pb[i] = fmaxf(fmaxf(pb[i], h2[i]), h3[i]);
-          carry[i] = h3[i];
+          for (int i = 0; i < 11; ++i) {
+            const float ta = fmaf(pa[i], sc, sh), tb = fmaf(pb[i], sc, sh);
+            pa[i] = ta > 0.f ? ta : ta * sl;
+            pb[i] = tb > 0.f ? tb : tb * sl;
+          }
         }
       }
       // pooled rows 2*tile and 2*tile+1 of frame g, pixels px0 .. px0+10, channel ch -> staging [g][row][px][ch]
@@ -441,8 +505,21 @@ stem2_conv3d_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_const
     }
   } else {
     // =============================================================== epilogue: 8 warps = 4 lane quarters x 2 column halves
-    if (warp >> 2) stem2_epilogue<1>(p, tmem_base, tfull, tempty, stg, warp & 3, lane);
-    else stem2_epilogue<0>(p, tmem_base, tfull, tempty, stg, warp & 3, lane);
+    // mode of this warp from its 32 channels (frame g = (warp & 3) >> 1, channels 32 * (warp & 1) + lane)
+    const int chn = (warp & 1) * 32 + lane;
+    const bool mono = __all_sync(0xffffffffu, __ldg(p.slope + chn) >= 0.f) && !(p.dbg & 2048);   // dbg 2048: general mode
+    const bool pos = __all_sync(0xffffffffu, __ldg(p.scale + chn) >= 0.f);
+    const int mode = !mono ? 0 : ((pos && !(p.dbg & 4096)) ? 1 : 2);                              // dbg 4096: mode 2 for all
+    const int q = warp & 3;
+    if (warp >> 2) {
+      if (mode == 0) stem2_epilogue<1, 0>(p, tmem_base, tfull, tempty, stg, q, lane);
+      else if (mode == 1) stem2_epilogue<1, 1>(p, tmem_base, tfull, tempty, stg, q, lane);
+      else stem2_epilogue<1, 2>(p, tmem_base, tfull, tempty, stg, q, lane);
+    } else {
+      if (mode == 0) stem2_epilogue<0, 0>(p, tmem_base, tfull, tempty, stg, q, lane);
+      else if (mode == 1) stem2_epilogue<0, 1>(p, tmem_base, tfull, tempty, stg, q, lane);
+      else stem2_epilogue<0, 2>(p, tmem_base, tfull, tempty, stg, q, lane);
+    }
   }
 
   tc_fence_before();

@@ -290,8 +290,19 @@ def staged_epilogue_bitwise_case(seed=9):
 
 
 
-def stem_case(B=2, T=6, H=88, W=88, u8=False, seed=0):
+def stem_case(B=2, T=6, H=88, W=88, u8=False, seed=0, signs=None):
+    """signs: None = positive BN scales and PReLU slopes (the second-generation stem pools the raw accumulators first, max
+    only); 'mixed_scale' = negative BN weights on a few channels of the first 32 (those warps pool max AND min, the other
+    warps max only); 'neg_slope' = negative PReLU slopes on a few channels of the last 32 (those warps take the general
+    order: BN + PReLU on every conv value, then the max-pool)."""
     sd = synth.make_video_state_dict(seed=seed + 1, randomize=True)
+    if signs == 'mixed_scale':
+        sd['frontend3D.1.weight'][[1, 7, 30]] *= -1.0
+    elif signs == 'neg_slope':
+        sd['frontend3D.2.weight'][[33, 40, 63]] *= -1.0
+        sd['frontend3D.1.weight'][[2, 35]] *= -1.0
+    elif signs is not None:
+        raise ValueError(signs)
     if u8:
         raw = torch.from_numpy(synth.lip_crops_u8([1] * B, T=T, H=H + 8, W=W + 8, seed=seed + 1))
         x = torch.stack([models_ref.video_preprocess(r, crop=H) for r in raw])        # (B,T,H,W) f32

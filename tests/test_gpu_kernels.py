@@ -74,6 +74,12 @@ def test_stem_second_generation_ragged_lengths_stacked_rows():
     G.stem_ragged_stacked_case()
 
 
+@pytest.mark.parametrize('signs', ['mixed_scale', 'neg_slope'])
+def test_stem_second_generation_epilogue_modes(signs):
+    # the three epilogue modes of stem2_conv3d.cuh (pool-first max, pool-first max + min, general) inside one launch
+    G.stem_case(B=2, T=5, u8=True, signs=signs)
+
+
 def test_stem_second_generation_full_clip():
     # 75 frames: 38 frame pairs per clip, the last one a half pair; more work units than one wave of CTAs would need
     G.stem_case(B=3, T=75, u8=True)

@@ -16,9 +16,14 @@ if len(sys.argv) > 1 and sys.argv[1] == 'ncu':
     torch.cuda.synchronize()
     sys.exit(0)
 cases = [(0, 'full')] + [(int(a, 0), 'dbg ' + a) for a in sys.argv[1:]]
+outs = {}
 for rnd in range(2):
     for dbg, what in cases:
         _lib.set_option('dbg', dbg)
         t = timeit(f, n=10); torch.cuda.synchronize()
+        outs[dbg] = f().clone()
         print('stem gen2 %-28s %7.1f us (incl. prepass)' % (what, t), flush=True)
 _lib.set_option('dbg', 0)
+for d, o in outs.items():
+    if d in (2048, 4096):
+        print('dbg %d output bit-identical to the default:' % d, torch.equal(o, outs[0]))
