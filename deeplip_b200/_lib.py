@@ -30,6 +30,8 @@ SIGNATURES = {
     'dl_frontend_features_pcm16': [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p],
     'dl_nct_to_ntc_bf16': [_p, _i, _i, _i, _p, _i, _p],
     'dl_stem_conv3d_bn_prelu_pool': [_p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _i, _p, _p, _p],
+    'dl_stem_prepass': [_p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    'dl_stem_conv3d_prepassed': [_i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p],
     'dl_conv3x3_c64_halo_bf16': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     'dl_conv_igemm_bf16': [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(ConvDesc), _p],
     'dl_frame_pool_temporal_mean': [_p, _i, _i, _i, _i, _p, _p, _p, _p],

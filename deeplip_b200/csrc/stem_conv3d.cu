@@ -434,12 +434,14 @@ extern "C" long long dl_stem_workspace_bytes(int B, int T, int H, int W) {
   return (long long)B * T * (H + 8) * pitch * 2;
 }
 
-extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
-                                            float mean, float std, const void* w_packed, const float* scale,
-                                            const float* shift, const float* slope, void* y, int out_img_rows,
-                                            const int32_t* lengths, void* workspace, void* stream) {
+// phases: 1 = pre-pass only (x -> workspace), 2 = main kernel only (workspace -> y), 3 = both
+static int stem_impl(int phases, const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
+                     float mean, float std, const void* w_packed, const float* scale,
+                     const float* shift, const float* slope, void* y, int out_img_rows,
+                     const int32_t* lengths, void* workspace, void* stream) {
   using namespace dl;
-  DL_CHECK_ARG(x && w_packed && scale && shift && slope && y && workspace, "stem: null pointer");
+  DL_CHECK_ARG(((phases & 1) == 0 || x) && ((phases & 2) == 0 || (w_packed && scale && shift && slope && y)) && workspace,
+               "stem: null pointer");
   DL_CHECK_ARG(B > 0 && T > 0, "stem: empty batch");
   DL_CHECK_ARG(H >= 8 && W >= 32 && H % 4 == 0 && W % 4 == 0 && W <= 120, "stem: H, W must be multiples of 4, 32 <= W <= 120");
   if (is_u8) {
@@ -477,7 +479,9 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   const int rows = H + 8, pitch = p.strip_pitch;
   // CenterCrop: delta = int(round(w - tw) / 2.)  (models/video_models/preprocess.py:88-90)
   const int dh = is_u8 ? (Hraw - H) / 2 : 0, dw = is_u8 ? (Wraw - W) / 2 : 0;
-  if (opt_prepass() >= 2 || lengths) {
+  if (!(phases & 1)) {
+    // the caller ran dl_stem_prepass on this workspace already (e.g. on another stream, under the audio branch)
+  } else if (opt_prepass() >= 2 || lengths) {
     const int aligned4 = (Wraw % 4 == 0 && ((uintptr_t)x & 3) == 0) ? 1 : 0;
     stem_prepass2_kernel<<<(unsigned)(B * T), 256, 0, cs>>>(
         x, is_u8, H, W, Hraw, Wraw, dh, dw, is_u8 ? 1.0f / (255.0f * std) : 1.0f, is_u8 ? -mean / std : 0.0f, rows,
@@ -492,6 +496,7 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
     st = check_launch("stem_prepass_kernel");
     if (st != DL_OK) return st;
   }
+  if (!(phases & 2)) return DL_OK;
 
   if (opt_stem() >= 2 && W == 2 * kS2Wo && H % 8 == 0) {
     // ---- second generation (stem2_conv3d.cuh): channels on lanes, four conv rows per tile
@@ -549,4 +554,25 @@ extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int
   }
   stem_conv3d_kernel<<<grid, kStemThreads, smem, cs>>>(mapW, mapX, p);
   return check_launch("stem_conv3d_kernel");
+}
+
+extern "C" int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
+                                            float mean, float std, const void* w_packed, const float* scale,
+                                            const float* shift, const float* slope, void* y, int out_img_rows,
+                                            const int32_t* lengths, void* workspace, void* stream) {
+  return stem_impl(3, x, is_u8, B, T, H, W, Hraw, Wraw, mean, std, w_packed, scale, shift, slope, y, out_img_rows, lengths,
+                   workspace, stream);
+}
+
+extern "C" int dl_stem_prepass(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw, float mean,
+                               float std, const int32_t* lengths, void* workspace, void* stream) {
+  return stem_impl(1, x, is_u8, B, T, H, W, Hraw, Wraw, mean, std, nullptr, nullptr, nullptr, nullptr, nullptr, 0, lengths,
+                   workspace, stream);
+}
+
+extern "C" int dl_stem_conv3d_prepassed(int B, int T, int H, int W, const void* w_packed, const float* scale,
+                                        const float* shift, const float* slope, void* y, int out_img_rows,
+                                        void* workspace, void* stream) {
+  return stem_impl(2, nullptr, 0, B, T, H, W, H, W, 0.f, 1.f, w_packed, scale, shift, slope, y, out_img_rows, nullptr,
+                   workspace, stream);
 }

@@ -134,10 +134,14 @@ def nct_to_ntc_bf16(x, ld=None):
 
 
 # ------------------------------------------------------------------ K2
-def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std=0.165, out=None, lengths=None):
+def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std=0.165, out=None, lengths=None,
+                phase='both'):
     """x: (B,T,H,W) f32 normalised frames, or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T, H/4, W/4, 64) bf16.
     out: optional pre-zeroed (B*T, rows >= H/4, W/4, 64) buffer in the stacked-rows layout.
-    lengths: int32 CUDA (B,) valid frames per clip; later frames are treated as zero normalised frames."""
+    lengths: int32 CUDA (B,) valid frames per clip; later frames are treated as zero normalised frames.
+    phase: 'both' (default), or the two halves as calls of their own -- 'prepass' (x -> the cached workspace; returns
+    None; w_packed / scale / shift / slope may be None) and 'main' (workspace -> y; x is only consulted for its shape)
+    -- for callers that run the pre-pass on another stream (AVExtractor does, under the audio branch)."""
     _need_cuda(x, w_packed, scale, shift, slope, lengths)
     if lengths is not None:
         assert lengths.dtype == torch.int32 and lengths.numel() == x.shape[0]
@@ -151,13 +155,24 @@ def stem_conv3d(x, w_packed, scale, shift, slope, crop=(88, 88), mean=0.421, std
         x = x.float()
         H, W = x.shape[2], x.shape[3]
         Hraw, Wraw, is_u8 = H, W, 0
+    ws = _workspace(x.device, _lib.lib().dl_stem_workspace_bytes(B, T, H, W))
+    if phase == 'prepass':
+        st = _lib.lib().dl_stem_prepass(_ptr(x), is_u8, B, T, H, W, Hraw, Wraw, float(mean), float(std), _ptr(lengths),
+                                        _ptr(ws), _stream())
+        _lib.check(st, 'dl_stem_prepass')
+        return None
     if out is None:
         y = torch.empty((B * T, H // 4, W // 4, 64), device=x.device, dtype=torch.bfloat16)
     else:
         y = out
         assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.shape[0] == B * T and \
             y.shape[1] >= H // 4 and y.shape[2] == W // 4 and y.shape[3] == 64
-    ws = _workspace(x.device, _lib.lib().dl_stem_workspace_bytes(B, T, H, W))
+    if phase == 'main':
+        st = _lib.lib().dl_stem_conv3d_prepassed(B, T, H, W, _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope), _ptr(y),
+                                                 y.shape[1], _ptr(ws), _stream())
+        _lib.check(st, 'dl_stem_conv3d_prepassed')
+        return y
+    assert phase == 'both'
     st = _lib.lib().dl_stem_conv3d_bn_prelu_pool(_ptr(x), is_u8, B, T, H, W, Hraw, Wraw, float(mean), float(std),
                                                  _ptr(w_packed), _ptr(scale), _ptr(shift), _ptr(slope), _ptr(y),
                                                  y.shape[1], _ptr(lengths), _ptr(ws), _stream())

@@ -24,6 +24,11 @@ class AVExtractor:
         self.audio, self.video = audio_model, video_model
         self.fusion, self.fusion_model = fusion, fusion_model
         self.feat_type, self.n_feat, self.cmvn, self.l2norm, self.delta = feat_type, n_feat, cmvn, l2norm, delta
+        # extract(): the stem's pre-pass on a side stream under the audio branch.  Off by default: interleaved A/B at
+        # B = 64 in the power-capped state, 3.547 vs 3.560 ms per step (tools/prepass_overlap_ab.py) -- the box's power
+        # budget, not free issue slots, is what the step runs against; bit-identical either way.
+        self.overlap_prepass = False
+        self._side = self._side_done = None
 
     def audio_embedding(self, wav, wav_lengths=None):
         """wav (B,nsamp) f32 -- or int16 PCM, value / 32768 -- CUDA -> xv (B,E) f32 (LMCL convention: 2nd fc output,
@@ -39,14 +44,14 @@ class AVExtractor:
         xv, _ = self.audio.embed_ntc(feat, frames)
         return xv
 
-    def video_embedding(self, video, video_lengths=None):
+    def video_embedding(self, video, video_lengths=None, prepassed=False):
         """video (B,T,H,W) f32 / (B,T,96,96) u8, or (B,G,T,..) for G clips per utterance -> (B,512)."""
         if video.dim() == 5:
             B, G = video.shape[:2]
             em = self.video.utterance_embedding(video.reshape(B * G, *video.shape[2:]),
                                                 None if video_lengths is None else video_lengths.reshape(-1))
             return em.view(B, G, -1).mean(dim=1)      # mean over clips (train_fusion.py:401)
-        return self.video.utterance_embedding(video, video_lengths)
+        return self.video.utterance_embedding(video, video_lengths, prepassed=prepassed)
 
     def fuse(self, xv_audio, em_video, out=None):
         """out: optional caller-owned (B, D) f32 rows the fused embeddings are written to (the job's all-gather
@@ -81,6 +86,22 @@ class AVExtractor:
 
     @torch.no_grad()
     def extract(self, wav, video, wav_lengths=None, video_lengths=None, out=None):
+        if self.overlap_prepass and self.fusion not in ('video', 'audio') and video.dim() == 4:
+            # The stem's pre-pass (HBM-bound, no shared memory, 36 us at B = 64) runs on a side stream under the audio
+            # branch, whose kernels leave room for it (the persistent TDNN CTAs use one CTA's worth of shared memory
+            # and a third of the registers of an SM; the small kernels do not fill the chip).  Same kernels, same bits.
+            main = torch.cuda.current_stream(video.device)
+            if self._side is None or self._side.device != video.device:
+                self._side = torch.cuda.Stream(device=video.device)
+                self._side_done = torch.cuda.Event()
+            self._side.wait_stream(main)                # everything enqueued so far, the previous step's stem included
+            with torch.cuda.stream(self._side):
+                self.video.stem_prepass(video, video_lengths)
+                self._side_done.record(self._side)
+            xv = self.audio_embedding(wav, wav_lengths)
+            main.wait_event(self._side_done)
+            em = self.video_embedding(video, video_lengths, prepassed=True)
+            return self.fuse(xv, em, out=out)
         xv = self.audio_embedding(wav, wav_lengths) if self.fusion != 'video' else None
         em = self.video_embedding(video, video_lengths) if self.fusion != 'audio' else None
         return self.fuse(xv, em, out=out)

@@ -84,7 +84,13 @@ class Lipreading(nn.Module):
             self._pk = pk
         return self._pk
 
-    def trunk_maps(self, x, lengths=None, avgpool=False):
+    def stem_prepass(self, x, lengths=None):
+        """The stem's pre-pass alone (x -> the cached workspace), for callers that overlap it with other work on another
+        stream and then call trunk_maps / utterance_embedding with prepassed=True on the same x."""
+        pk = self._packed()
+        ops.stem_conv3d(x, None, None, None, None, lengths=lengths, phase='prepass')
+
+    def trunk_maps(self, x, lengths=None, avgpool=False, prepassed=False):
         """x: (B,T,H,W) f32 normalised frames or (B,T,Hraw,Wraw) uint8 raw crops -> (B*T,3,3,512) bf16; with
         avgpool=True the per-frame pooled features (B*T,512) f32 instead (K4's spatial half in the last conv's epilogue).
         lengths (int32 CUDA, optional): frames at or beyond a clip's length enter the stem as zero normalised
@@ -97,9 +103,10 @@ class Lipreading(nn.Module):
         if self.trunk.halo_enabled(W // 4):
             # stem writes straight into the stacked-rows layout layer1's halo kernel consumes
             buf = self.trunk.stacked_buffers(B * T, H // 4, W // 4, x.device, 2 * len(self.trunk.layer1) + 1)[-1]
-            ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], out=buf, lengths=lengths)
+            ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], out=buf, lengths=lengths,
+                            phase='main' if prepassed else 'both')
             return self.trunk.forward_nhwc(buf, stacked_H=H // 4, avgpool=avgpool)
-        y = ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], lengths=lengths)
+        y = ops.stem_conv3d(x, pk['w'], pk['s'], pk['h'], pk['a'], lengths=lengths, phase='main' if prepassed else 'both')
         return self.trunk.forward_nhwc(y, avgpool=avgpool)
 
     def forward(self, x, lengths=None):
@@ -110,9 +117,9 @@ class Lipreading(nn.Module):
             return feats                  # (B, T, 512); lengths unused when extract_feats (model.py:105)
         return self.tcn(feats, lengths, B)
 
-    def utterance_embedding(self, x, lengths=None):
+    def utterance_embedding(self, x, lengths=None, prepassed=False):
         """Fused form of train_fusion.py:400: mean over the (valid) frames of each clip -> (B,512).
         x as in trunk_maps; lengths: int32 CUDA tensor of valid frame counts (zero-padded tails)."""
         B, T = x.shape[0], x.shape[1]
-        feats = self.trunk_maps(x, lengths, avgpool=True)          # (B*T, 512) f32
+        feats = self.trunk_maps(x, lengths, avgpool=True, prepassed=prepassed)          # (B*T, 512) f32
         return ops.temporal_mean(feats, B, T, lengths=lengths)

@@ -107,6 +107,13 @@ int dl_nct_to_ntc_bf16(const float* x, int B, int C, int T, void* y, int ldc, vo
  *     on stem_conv3d_kernel.  Same contract, results equal to fp32 summation order.
  */
 long long dl_stem_workspace_bytes(int B, int T, int H, int W);
+/* The two halves of dl_stem_conv3d_bn_prelu_pool as calls of their own, for callers that run the pre-pass (x ->
+ * workspace: HBM-bound, no shared memory) on another stream under kernels that leave room for it -- the audio branch
+ * of deeplip_b200.pipeline -- and the main kernel (workspace -> y) afterwards.  Same arithmetic, same bits. */
+int dl_stem_prepass(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw, float mean, float std,
+                    const int32_t* lengths, void* workspace, void* stream);
+int dl_stem_conv3d_prepassed(int B, int T, int H, int W, const void* w_packed, const float* scale, const float* shift,
+                             const float* slope, void* y, int out_img_rows, void* workspace, void* stream);
 int dl_stem_conv3d_bn_prelu_pool(const void* x, int is_u8, int B, int T, int H, int W, int Hraw, int Wraw,
                                  float mean, float std, const void* w_packed, const float* scale,
                                  const float* shift, const float* slope, void* y, int out_img_rows,

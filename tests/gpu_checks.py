@@ -1138,3 +1138,23 @@ def avgpool_model_case(B=28, T=75, seed=3):
            'batch_equals_alone': bool(torch.equal(fused[[0, 5, B - 1]], alone))}
     assert all(out.values()), out
     return out
+
+
+def prepass_overlap_case(B=3, T=7, seed=2):
+    """AVExtractor.overlap_prepass: the stem's pre-pass on a side stream under the audio branch (dl_stem_prepass +
+    dl_stem_conv3d_prepassed) gives the bits of the one-call form, ragged lengths included, also back to back."""
+    from deeplip_b200.pipeline import AVExtractor, build_models
+    audio, video = build_models(DEV, seed=seed)
+    ex = AVExtractor(audio, video)
+    raw = torch.from_numpy(synth.lip_crops_u8(list(range(B)), T=T, H=96, W=96, seed=seed)).to(DEV)
+    wav = torch.from_numpy(synth.speech_like_audio(list(range(B)), nsamp=16000, seed=seed)).to(DEV)
+    vl = torch.tensor([T, T - 3, T - 1][:B], dtype=torch.int32, device=DEV)
+    ref = [ex.extract(wav, raw).clone(), ex.extract(wav, raw, None, vl).clone()]
+    ex.overlap_prepass = True
+    got = [ex.extract(wav, raw).clone(), ex.extract(wav, raw, None, vl).clone()]
+    rep = [ex.extract(wav, raw).clone() for _ in range(4)]
+    torch.cuda.synchronize()
+    out = {'equal': bool(torch.equal(ref[0], got[0])), 'ragged_equal': bool(torch.equal(ref[1], got[1])),
+           'back_to_back_equal': all(bool(torch.equal(r, ref[0])) for r in rep)}
+    assert all(out.values()), out
+    return out

@@ -113,3 +113,7 @@ def test_reference_wire_format_roundtrip(tmp_path):
 
 def test_video_embedding_with_fused_avgpool_equals_unfused_and_alone():
     G.avgpool_model_case()
+
+
+def test_stem_prepass_on_a_side_stream_gives_the_same_bits():
+    G.prepass_overlap_case()
