@@ -52,6 +52,36 @@ def all_gather_rows(local_rows, n_total, rank, world):
     return full[:n_total]
 
 
+class OverlappedGather:
+    """all_gather_rows of one step's rows on a communication stream of its own, so that the collective (and its wait
+    for the slowest rank) overlaps the NEXT step's kernels instead of holding the compute stream: with one collective per
+    step on the compute stream the ranks run in lockstep, and every step costs the slowest rank's time plus the skew.
+    Call it with the rows (valid on the current stream); the result is valid on `.stream` -- consume it there (or after
+    `.wait()`, which makes the current stream wait for it).  CUDA only; world == 1 is the identity."""
+
+    def __init__(self, n_total, rank, world, device):
+        self.n_total, self.rank, self.world = n_total, rank, world
+        self.stream = torch.cuda.Stream(device=device) if world > 1 else None
+        self._ev = torch.cuda.Event() if world > 1 else None
+        self._done = torch.cuda.Event() if world > 1 else None
+
+    def __call__(self, rows):
+        if self.world == 1:
+            return rows
+        main = torch.cuda.current_stream(rows.device)
+        self._ev.record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._ev)
+            rows.record_stream(self.stream)             # the caching allocator must not recycle it under the collective
+            out = all_gather_rows(rows, self.n_total, self.rank, self.world)
+            self._done.record(self.stream)
+        return out
+
+    def wait(self):
+        if self.world > 1:
+            torch.cuda.current_stream().wait_event(self._done)
+
+
 def gather_scores(local_scores, n_total, rank, world):
     """Concatenate per-rank score slices (contiguous trial shards) into the full vector on every rank."""
     if world == 1:

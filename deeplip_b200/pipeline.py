@@ -190,7 +190,9 @@ class HostPipeline:
 
     @torch.no_grad()
     def run(self, batches, post=None):
-        """batches: sequence of (wav_host (B,nsamp) f32 pinned, video_host (B,T,H,W) u8/f32 pinned) or, for ragged
+        """post: optional callable applied to every batch's fused embeddings before they go to the host (bench.py: the
+        all_gather of the step's rows); a dist.OverlappedGather runs on its own stream, under the next batch's kernels.
+        batches: sequence of (wav_host (B,nsamp) f32 pinned, video_host (B,T,H,W) u8/f32 pinned) or, for ragged
         batches (zero-padded tails, pad_packed_collate convention), (wav, video, wav_lengths, video_lengths) with the
         lengths as pinned int32 host vectors.  Returns the list of fused embeddings as pinned host tensors (valid after
         the final synchronize, which this method performs, and until the next run(): they are views of one pinned pool
@@ -227,8 +229,10 @@ class HostPipeline:
                 main.wait_event(self._ready[slot])
                 emb = self.ex.fuse(xv, self.ex.video_embedding(vid_d, vl_d))
             self._free[slot].record(main)
+            pstream = None
             if post is not None:
                 emb = post(emb)
+                pstream = getattr(post, 'stream', None)      # dist.OverlappedGather: the result lives on its stream
             if pool is None:       # one pinned pool, kept across runs (cudaHostAlloc per step would serialise the pipeline)
                 need = (len(batches),) + tuple(emb.shape)
                 pool = self._out_pool
@@ -236,7 +240,11 @@ class HostPipeline:
                     pool = torch.empty(need, dtype=emb.dtype, pin_memory=True)
                     self._out_pool = pool
             h = pool[k]
-            h.copy_(emb, non_blocking=True)
+            if pstream is not None:                          # D2H behind the collective, off the compute stream
+                with torch.cuda.stream(pstream):
+                    h.copy_(emb, non_blocking=True)
+            else:
+                h.copy_(emb, non_blocking=True)
             outs.append(h)
         torch.cuda.synchronize(self.device)
         return outs

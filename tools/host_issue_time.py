@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from deeplip_b200.pipeline import AVExtractor, GraphedExtractor, build_models
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))          # under torchrun: N independent ranks contending for the host
+RANK = int(os.environ.get('RANK', 0))
 audio, video = build_models('cuda', seed=1)
 ex = AVExtractor(audio, video)
 batches = []
@@ -14,7 +16,7 @@ for r in range(4):
 for i in range(5):
     ex.extract(*batches[i % 4])
 torch.cuda.synchronize()
-print('OMP_NUM_THREADS', os.environ.get('OMP_NUM_THREADS'), 'torch threads', torch.get_num_threads(), 'cpus', len(os.sched_getaffinity(0)))
+if RANK == 0: print('OMP_NUM_THREADS', os.environ.get('OMP_NUM_THREADS'), 'torch threads', torch.get_num_threads(), 'cpus', len(os.sched_getaffinity(0)))
 for rep in range(3):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -26,7 +28,7 @@ for rep in range(3):
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    print('eager: host issue %.3f ms/step, GPU %.3f ms/step, wall %.3f ms/step' % ((t1 - t0) / n * 1e3, a.elapsed_time(b) / n, (t2 - t0) / n * 1e3), flush=True)
+    if RANK == 0: print('eager: host issue %.3f ms/step, GPU %.3f ms/step, wall %.3f ms/step' % ((t1 - t0) / n * 1e3, a.elapsed_time(b) / n, (t2 - t0) / n * 1e3), flush=True)
 g = GraphedExtractor(ex, *batches[0])
 for rep in range(3):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,4 +40,4 @@ for rep in range(3):
     b.record()
     t1 = time.perf_counter()
     torch.cuda.synchronize()
-    print('graph: host issue %.3f ms/step, GPU %.3f ms/step (incl. the two input copies)' % ((t1 - t0) / n * 1e3, a.elapsed_time(b) / n), flush=True)
+    if RANK == 0: print('graph: host issue %.3f ms/step, GPU %.3f ms/step (incl. the two input copies)' % ((t1 - t0) / n * 1e3, a.elapsed_time(b) / n), flush=True)
