@@ -483,3 +483,14 @@ def test_stem2_layout_arithmetic_against_torch_on_cpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'stem2_emulate.py')], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr
+
+
+def test_overlapped_gather_is_the_identity_for_one_rank():
+    """dist.OverlappedGather at world == 1 neither needs CUDA nor touches its argument (bench.py's N = 1 line); the
+    multi-rank form is checked bit for bit against the synchronous collective on NCCL inside bench.py
+    (`step_collective.overlapped_equals_synchronous_all_ranks`)."""
+    from deeplip_b200 import dist as D
+    og = D.OverlappedGather(7, 0, 1, 'cpu')
+    x = torch.arange(14.0).view(7, 2)
+    assert og(x) is x and og.stream is None
+    og.wait()
