@@ -17,11 +17,15 @@
 //     SBO = 128 B between 8-pixel groups, LBO = plane size between the two K halves.  616 chunks per stage instead of
 //     176 x 7 im2col chunks, and no tensor-memory stores;
 //   * the accumulator row of a thread is ONE channel of ONE frame over 176 pixels: BN + PReLU use three per-thread
-//     scalars, the 3x3/2 max-pool runs in registers (the last conv row of a tile is carried to the next tile), and the
-//     pooled rows leave through a 11 KB staging buffer and two bulk stores of 5.6 KB (two whole NHWC rows per frame).
+//     scalars, the 3x3/2 max-pool runs in registers (the last conv row of a tile is carried to the next tile) -- on the
+//     RAW accumulators where the channel's BN + PReLU is monotone (slope >= 0), so that BN + PReLU touch 22 pooled
+//     values per thread and tile instead of 96 -- and the pooled rows leave through a 11 KB staging buffer and two bulk
+//     stores of 5.6 KB (two whole NHWC rows per frame).
 //
 // Work unit = two consecutive output frames of a clip; tile = 4 conv rows (2 pooled rows); 6 pipeline stages per tile
-// (input frames t0-2 .. t0+3), 4 MMAs of 128 x 176 x 16 per stage.  Shapes: W = 88 (the corpus crop; Wo = 44), H % 8 == 0;
+// (input frames t0-2 .. t0+3), 3 MMAs of 128 x 176 x 16 per stage for window rows 0..5 + one MMA per stage PAIR for
+// window row 6 (its two K halves are the same place in two consecutive stages): 21 per tile.  The units x tiles
+// sequence is cut into equal contiguous ranges, one per CTA.  Shapes: W = 88 (the corpus crop; Wo = 44), H % 8 == 0;
 // other shapes run on the first-generation kernel.
 #pragma once
 #include "dl_host.cuh"
