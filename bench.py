@@ -498,6 +498,7 @@ def run_ours(args, rank, world, local):
             if l2_flush:
                 flush.zero_()
             step(i, from_host)
+        ogather.wait()           # the last step's collective (communication stream) belongs to the timed region
         ev1.record()
         torch.cuda.synchronize()
         dl_dist.barrier()
