@@ -313,7 +313,7 @@ class ResNet(nn.Module):
                         x = blocks[0].forward_nhwc(x)
                     for blk in blocks[1:]:
                         x = blk.forward_nhwc(x, **kw(blk))
-                return x
+                return self._pooled(x, avgpool)
             else:
                 x = self.layer2[0].forward_nhwc(x, H=H)
                 rest = list(self.layer2)[1:] + list(self.layer3)
@@ -324,6 +324,15 @@ class ResNet(nn.Module):
             rest = list(self.layer2) + list(self.layer3)
         for blk in rest + list(self.layer4):
             x = blk.forward_nhwc(x, **kw(blk))
+        return self._pooled(x, avgpool)
+
+    @staticmethod
+    def _pooled(x, avgpool):
+        """The last block pools in its epilogue; a layer4 of ONE block ends on a fused entry block, which does not: pool
+        its maps with the stand-alone kernel (same arithmetic)."""
+        if avgpool and x.dim() == 4:
+            feats, _ = ops.frame_pool_temporal_mean(x, x.shape[0], 1, want_frames=True, want_mean=False)
+            return feats.view(x.shape[0], -1)
         return x
 
     def forward(self, x):
