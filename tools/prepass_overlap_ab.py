@@ -1,6 +1,7 @@
 """Stem pre-pass on a side stream under the audio branch (AVExtractor.overlap_prepass) against the plain order:
 interleaved A/B of the whole step at B = 64, rotating inputs.   python tools/prepass_overlap_ab.py"""
-import os, sys, statistics
+import os, sys, statistics, time
+BURST = len(sys.argv) > 1 and sys.argv[1] == 'burst'
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from deeplip_b200.pipeline import AVExtractor, build_models
@@ -10,8 +11,11 @@ batches = []
 for r in range(4):
     raw, wav = bench.synth_batch(64, seed=r + 1)
     batches.append((torch.from_numpy(wav).cuda(), torch.from_numpy(raw).cuda()))
-def run(flag, n=10):
+def run(flag, n=20):
     ex.overlap_prepass = flag
+    torch.cuda.synchronize()
+    if BURST:
+        time.sleep(2.0)          # bench.py's protocol: every timed region starts from an idle GPU
     for i in range(3):
         ex.extract(*batches[i % 4])
     torch.cuda.synchronize()
