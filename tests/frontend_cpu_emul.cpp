@@ -9,6 +9,10 @@
 //   usage: frontend_cpu_emul linear M C Cout ldx ldw with_bf16 with_scale2 in.bin out.bin     (linear_small.cuh)
 //   in.bin = x (M,ldx) u16 | w (Cout,ldw) u16 | scale, shift, slope, scale2, shift2 (Cout f32 each); f32_slope = 0.2
 //   out.bin = y (M,Cout) u16 | yf (M,Cout) f32
+//   usage: frontend_cpu_emul pool B T HW C in.bin out.bin                                    (pool_kernels.cuh)
+//   in.bin = lengths (B i32) | x (B*T, HW, C) u16 bf16
+//   out.bin = frame_feats (B,T,C) f32 | utt_mean (B,C) f32 [frame_pool_kernel] | utt_mean (B,C) f32 [temporal_mean_kernel
+//             on those frame features]
 //   usage: frontend_cpu_emul plda n_utt D R n_trials c0 in.bin out.bin - -                   (plda_score.cuh)
 //   in.bin = emb (n_utt,D) f32 | M (R,D) f32 | bias, k1, k2 (R f32 each) | enrol, test (n_trials i32 each)
 //   out.bin = u (n_utt,R) f32 | scores (n_trials) f32
@@ -36,6 +40,9 @@ thread_local Idx3 threadIdx, blockIdx;
 Idx3 gridDim, blockDim;
 struct uint4 { unsigned x, y, z, w; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#define DL_STATIC_SHARED static          // a kernel's static shared array: one per process here (blocks run one after another)
 using std::max;
 using std::min;
 template <typename T> inline T __ldg(const T* p) { return *p; }
@@ -83,6 +90,7 @@ alignas(16) float lin_part[16 * 4 * 64];
 #include "../deeplip_b200/csrc/stem_prepass.cuh"
 #include "../deeplip_b200/csrc/linear_small.cuh"
 #include "../deeplip_b200/csrc/plda_score.cuh"
+#include "../deeplip_b200/csrc/pool_kernels.cuh"
 
 template <typename Fn>
 static void launch(int gx, int gy, Fn fn, int nthreads = 256) {
@@ -159,6 +167,29 @@ static int linear_main(char** a) {
   return 0;
 }
 
+static int pool_main(char** a) {
+  using namespace dl;
+  const int B = atoi(a[2]), T = atoi(a[3]), HW = atoi(a[4]), C = atoi(a[5]);
+  std::vector<int32_t> len(B);
+  std::vector<uint16_t> x((size_t)B * T * HW * C);
+  FILE* f = fopen(a[6], "rb");
+  if (!f || fread(len.data(), 4, len.size(), f) != len.size() || fread(x.data(), 2, x.size(), f) != x.size()) return 3;
+  fclose(f);
+  std::vector<float> ff((size_t)B * T * C, -777.f), um((size_t)B * C, -777.f), um2((size_t)B * C, -777.f);
+  const uint16_t* px = x.data();
+  const int32_t* pl = len.data();
+  float *pf = ff.data(), *pu = um.data(), *pu2 = um2.data();
+  if (HW == 9) launch(B, (C + 63) / 64, [&] { frame_pool_kernel<9>(px, T, HW, C, pl, pf, pu); });
+  else launch(B, (C + 63) / 64, [&] { frame_pool_kernel<0>(px, T, HW, C, pl, pf, pu); });
+  launch(B, (C + 63) / 64, [&] { temporal_mean_kernel(pf, T, C, pl, pu2); });
+  f = fopen(a[7], "wb");
+  fwrite(ff.data(), 4, ff.size(), f);
+  fwrite(um.data(), 4, um.size(), f);
+  fwrite(um2.data(), 4, um2.size(), f);
+  fclose(f);
+  return 0;
+}
+
 static int plda_main(char** a) {
   using namespace dl;
   const int n_utt = atoi(a[2]), D = atoi(a[3]), R = atoi(a[4]), nt = atoi(a[5]);
@@ -183,6 +214,7 @@ static int plda_main(char** a) {
 
 int main(int argc, char** argv) {
   using namespace dl;
+  if (argc == 8 && !strcmp(argv[1], "pool")) return pool_main(argv);
   if (argc == 11 && !strcmp(argv[1], "plda")) return plda_main(argv);
   if (argc == 11 && !strcmp(argv[1], "linear")) return linear_main(argv);
   if (argc != 10) return 2;

@@ -494,3 +494,32 @@ def test_overlapped_gather_is_the_identity_for_one_rank():
     x = torch.arange(14.0).view(7, 2)
     assert og(x) is x and og.stream is None
     og.wait()
+
+
+@pytest.mark.parametrize('B,T,HW,C,lengths', [(3, 75, 9, 512, [75, 40, 1]), (2, 37, 9, 64, [37, 33]), (2, 5, 4, 72, [5, 2])])
+def test_k4_kernels_source_on_cpu_threads(tmp_path, B, T, HW, C, lengths):
+    """frame_pool_kernel (spatial mean + masked temporal mean, model.py:16-17 / train_fusion.py:400) and
+    temporal_mean_kernel (the temporal half alone, used when the conv epilogue took the spatial mean) from their CUDA
+    source on CPU threads: both against numpy, and the two utterance means against each other BIT FOR BIT -- the
+    claim dl_conv_desc.avgpool rests on."""
+    exe = str(tmp_path / 'emul')
+    subprocess.run(['g++', '-std=c++20', '-O2', '-pthread', '-Wno-unknown-pragmas', '-Wno-attributes', '-o', exe,
+                    os.path.join(ROOT, 'tests', 'frontend_cpu_emul.cpp')], check=True)
+    rng = np.random.default_rng(1)
+    xf = rng.standard_normal((B * T, HW, C)).astype(np.float32)
+    xb = ((xf.view(np.uint32) + 0x7fff + ((xf.view(np.uint32) >> 16) & 1)) >> 16).astype(np.uint16)      # bf16 rn
+    xr = (xb.astype(np.uint32) << 16).view(np.float32)
+    with open(str(tmp_path / 'in.bin'), 'wb') as f:
+        f.write(np.asarray(lengths, np.int32).tobytes())
+        f.write(xb.tobytes())
+    subprocess.run([exe, 'pool', str(B), str(T), str(HW), str(C), str(tmp_path / 'in.bin'), str(tmp_path / 'out.bin')],
+                   check=True, capture_output=True)
+    out = np.fromfile(str(tmp_path / 'out.bin'), np.float32)
+    ff = out[:B * T * C].reshape(B, T, C)
+    um = out[B * T * C:B * T * C + B * C].reshape(B, C)
+    um2 = out[B * T * C + B * C:].reshape(B, C)
+    ref_ff = xr.reshape(B, T, HW, C).astype(np.float64).mean(2)
+    assert np.abs(ff - ref_ff).max() < 1e-5
+    for b, n in enumerate(lengths):
+        assert np.abs(um[b] - ref_ff[b, :n].mean(0)).max() < 1e-5
+    assert np.array_equal(um.view(np.uint32), um2.view(np.uint32))
