@@ -523,3 +523,25 @@ def test_k4_kernels_source_on_cpu_threads(tmp_path, B, T, HW, C, lengths):
     for b, n in enumerate(lengths):
         assert np.abs(um[b] - ref_ff[b, :n].mean(0)).max() < 1e-5
     assert np.array_equal(um.view(np.uint32), um2.view(np.uint32))
+
+
+def test_pool_first_identity_of_the_stem_epilogue():
+    """stem2_conv3d.cuh pools the RAW accumulators where a channel's BN + PReLU is monotone: for slope >= 0,
+    max_i f(v_i) == f(max_i v_i) when scale >= 0 and == f(min_i v_i) when scale <= 0, f(v) = prelu(fma(v, scale, shift)),
+    bit for bit in f32 (every rounding step of f is monotone, and f is applied to one of the v_i either way).  Checked
+    here on random 3x3 windows incl. ties, zeros, a zero scale and slopes 0 and > 1; a negative slope breaks it (the
+    kernel then takes the general order), which the last assertion demonstrates."""
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((4000, 9)).astype(np.float32) * 3
+    v[::7, 3] = v[::7, 5]                       # ties
+    v[::11] = 0.0                               # all-zero windows (padding frames of a ragged batch)
+
+    def f(x, sc, sh, sl):
+        z = (x.astype(np.float64) * np.float64(sc) + np.float64(sh)).astype(np.float32)     # fma: one rounding
+        return np.where(z > 0, z, (z * np.float32(sl)).astype(np.float32))
+    for sc, sh, sl in [(1.3, -0.2, 0.25), (-0.7, 0.4, 0.0), (0.0, 0.3, 0.5), (2.5, 0.0, 1.7), (-1.1, -0.3, 0.9)]:
+        general = f(v, sc, sh, sl).max(axis=1)
+        pooled = f(v.max(axis=1) if sc >= 0 else v.min(axis=1), sc, sh, sl)
+        assert np.array_equal(general.view(np.uint32), pooled.view(np.uint32)), (sc, sh, sl)
+    general = f(v, 1.3, -0.2, -0.5).max(axis=1)
+    assert not np.array_equal(general, f(v.max(axis=1), 1.3, -0.2, -0.5))
